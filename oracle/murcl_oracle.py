@@ -287,9 +287,9 @@ def pretrain_step(feat_list, clusters_list, sd_model: StateDict, sd_fc: StateDic
                                                                               **{"f." + a: v for a, v in sd_fc.items()}}.items()}
     sm = {n[2:]: p for n, p in params.items() if n.startswith("m.")}
     sf = {n[2:]: p for n, p in params.items() if n.startswith("f.")}
-    hidden = [None, None]
+    hidden = None  # ONE state shared by both views, as Full_layer.hidden is (models/rlmil.py:216,219)
     losses = []
-    for _ in range(T):
+    for t in range(T):
         # RNG order of train_MuRCL.py:235-239 / :256-268: both action draws, then per view rand+randperm
         acts = [torch.rand(b, k, generator=generator) for _ in range(2)]
         views = [get_feats(feat_list, clusters_list, a, feat_size)[0] for a in acts]
@@ -301,7 +301,10 @@ def pretrain_step(feat_list, clusters_list, sd_model: StateDict, sd_fc: StateDic
             else:
                 kw = clam_kwargs or {}
                 pooled = torch.cat([clam_sb_bag(xb, sm, **kw)[0] for xb in x], 0)
-            z, hidden[v] = full_layer_step(pooled, hidden[v], sf)
+            # train_MuRCL.py:243,272 call the same Full_layer object for view 0 then view 1: with
+            # restart=True both start from zeros; afterwards each call continues from the hidden state
+            # the PREVIOUS CALL left behind (the other view's), not from its own view's history.
+            z, hidden = full_layer_step(pooled, None if t == 0 else hidden, sf)
             outs.append(z)
         losses.append(nt_xent(outs[0], outs[1], temperature))
     loss = sum(losses) / T
