@@ -1,0 +1,212 @@
+/*
+ * murcl_b200.h - C ABI of libmurcl_b200.so, the B200 (sm_100a) implementation of MuRCL's
+ * per-slide MIL hot path.
+ *
+ * The reference (wwu98934/MuRCL) has no FFI of its own: its operator surface is Python
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it replaces
+ * (file:line relative to the upstream repository).  The Python drop-ins under
+ * murcl_b200/dropin/ bind these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (e.g. torch.Tensor.data_ptr());
+ *     the library never allocates persistent device memory and never synchronises;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: MURCL_OK or a negative MURCL_E* code; murcl_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - matrices are row-major and dense unless a leading dimension is given;
+ *   - `dtype` arguments take MURCL_F32 or MURCL_BF16 and describe the storage type of the
+ *     large activation tensors; all reductions and accumulators are fp32.
+ *   - "bags" are stored CSR style: rows of all bags concatenated, `offsets[B+1]` (int64)
+ *     gives each bag's row range.
+ */
+#ifndef MURCL_B200_H
+#define MURCL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MURCL_ABI_VERSION 1
+
+#define MURCL_OK 0
+#define MURCL_EINVAL (-1)       /* bad argument */
+#define MURCL_EUNSUPPORTED (-2) /* shape / dtype combination not implemented */
+#define MURCL_ECUDA (-3)        /* CUDA runtime or driver error */
+
+#define MURCL_F32 0
+#define MURCL_BF16 1
+
+#define MURCL_ACT_NONE 0
+#define MURCL_ACT_RELU 1
+#define MURCL_ACT_TANH 2
+#define MURCL_ACT_SIGMOID 3
+#define MURCL_ACT_TANH_SIGMOID 4 /* tanh on columns [0,N/2), sigmoid on [N/2,N): gated attention */
+
+#define MURCL_GEMM_AUTO 0  /* tcgen05 when dtype/shape allow, else SIMT */
+#define MURCL_GEMM_SIMT 1  /* fp32 FFMA path (exact fp32 accumulate, any shape) */
+#define MURCL_GEMM_TCGEN05 2 /* TMA + tcgen05.mma, bf16 operands, fp32 TMEM accumulators */
+
+/* ---- library ------------------------------------------------------------------------ */
+int murcl_version(void);
+const char* murcl_last_error(void);
+/* sm count and compute capability of the current device. */
+int murcl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernel launches issued by this library on the calling process so far. */
+int64_t murcl_launch_count(void);
+
+/* ---- (1) ragged-bag packer: utils/datasets.py:274-308 (get_feats), :263-271 (mixup) ---- */
+
+/* Ingest: per-patch rank inside its cluster and per-bag cluster sizes from the per-patch
+ * cluster label (`features_cluster_indices`, wsi_processing/features_clustering.py:10-25).
+ * patch_cluster[n_rows] (label in [0,K) or -1), offsets[B+1] -> patch_rank[n_rows],
+ * cluster_sizes[B*K].  Equivalent to the position of the patch in the JSON inverted list. */
+int murcl_csr_rank_patches(const int32_t* patch_cluster, const int64_t* offsets, int B, int K,
+                           int32_t* patch_rank, int32_t* cluster_sizes, void* stream);
+
+/* Selection (datasets.py:283-305): for output slot s reading bag slot_bag[s] with actions
+ * actions[s*K..], keep patch p iff its rank lies in the window the reference's Python slice
+ * selects, in ascending patch order, first FS survivors.  sel_idx[S*FS] receives GLOBAL row
+ * indices into the CSR buffer (-1 = zero pad row), sel_cnt[S] the number kept.  Bit-exact. */
+int murcl_pack_select(const int32_t* patch_cluster, const int32_t* patch_rank, const int64_t* offsets,
+                      const int32_t* cluster_sizes, const int32_t* slot_bag, const float* actions,
+                      int S, int K, int FS, int32_t* sel_idx, int32_t* sel_cnt, void* stream);
+
+/* Gather + zero pad (+ mixup when lam != NULL): out[s,r,:] = lam[s]*x(s,r) + (1-lam[s])*x(perm[s],r)
+ * with x(s,r) = feats[sel_idx[s,r]] or 0; products and sum rounded separately like the
+ * reference (datasets.py:268-270).  feats fp32 [n_rows,D]; out [S,FS,D] in out_dtype
+ * (MURCL_BF16 rounds the fp32 result to nearest-even). */
+int murcl_pack_gather(const float* feats, int D, const int32_t* sel_idx, int S, int FS,
+                      const float* lam, const int32_t* perm, void* out, int out_dtype, void* stream);
+
+/* ---- dense layers: every nn.Linear on the path (abmil.py:12-32, clam.py:18-77,
+ *      dsmil.py:9,54-59, rlmil.py:40-53,199-200) ----------------------------------------- */
+
+/* y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]).  x,w in `dtype`; y in `out_dtype`; bias fp32/NULL. */
+int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K,
+                     int act, int dtype, int out_dtype, int backend, void* stream);
+
+/* dx[M,K] = dy[M,N] . w[N,K]; when relu_src != NULL (shape [M,K], storage `dtype`) the result is
+ * multiplied by (relu_src > 0), i.e. it is the gradient w.r.t. the previous layer's
+ * pre-activation.  When row_scale != NULL: dx += row_scale[m] * row_vec[row_seg[m]][k] before
+ * masking (the direct softmax-pool term, see murcl_pool_bwd). */
+int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K,
+                           const void* relu_src, const float* row_scale, const float* row_vec,
+                           const int32_t* row_seg, int dtype, int backend, void* stream);
+
+/* dw[N,K] (fp32) = dy[M,N]^T . x[M,K], db[N] (fp32, may be NULL) = column sums of dy.
+ * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats. */
+int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K);
+int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K,
+                            int dtype, int backend, float* workspace, void* stream);
+
+/* ---- (2) attention pooling: abmil.py:38-42, clam.py:37-60,139-170 --------------------- */
+
+/* Raw attention score s[n] = sum_d wc[d]*g[n,d] + bc with g = u (gated=0, uv is [N,D]) or
+ * u*v (gated=1, uv is [N,2D]: tanh branch in columns [0,D), sigmoid branch in [D,2D)). */
+int murcl_attn_score_fwd(const void* uv, const float* wc, const float* bc, float* s, int64_t N, int D,
+                         int gated, int dtype, void* stream);
+
+/* Segmented softmax over the rows of each bag for C score columns: p[n,c] = post_scale_b *
+ * softmax_n(s[n,c]); post_scale_b = 1/sqrt(N_b) when inv_sqrt_n (abmil.py:41) else 1.
+ * stats[b,c,0..1] = (max, sum exp).  s,p fp32 [n_rows,C]. */
+int murcl_seg_softmax(const float* s, const int64_t* offsets, int B, int C, int inv_sqrt_n, float* p,
+                      float* stats, void* stream);
+
+/* Segmented weighted row sum: out[b,c,:] = sum_{n in bag b} p[n,c] * h[n,:]  (abmil.py:42,
+ * clam.py:170, dsmil.py:78).  h [n_rows,L] in dtype; out fp32 [B,C,L].  workspace fp32 of
+ * murcl_seg_wsum_workspace(...) floats. */
+int64_t murcl_seg_wsum_workspace(int64_t n_rows, int B, int C, int L);
+int murcl_seg_wsum(const float* p, const void* h, const int64_t* offsets, int64_t n_rows, int B, int C, int L,
+                   int dtype, float* out, float* workspace, void* stream);
+
+/* Backward of p = post_scale*softmax(s), M = p^T h w.r.t. s:  ds[n,c] = p[n,c]*(dM[b,c].h[n] - k[b,c])
+ * with k[b,c] = (dM[b,c].M[b,c]) / post_scale_b.  row_seg[n] = bag of row n. */
+int murcl_pool_bwd_scores(const float* p, const void* h, const float* dM, const float* M, const int64_t* offsets,
+                          const int32_t* row_seg, int64_t n_rows, int B, int C, int L, int inv_sqrt_n, int dtype,
+                          float* ds, float* kbuf /* [B*C] scratch */, void* stream);
+
+/* Direct term of the pooling backward: dh[n,:] (+)= sum_c p[n,c] * dM[b,c,:] (accumulate != 0 adds to
+ * the existing contents).  The C == 1 case is also available fused in murcl_linear_bwd_input. */
+int murcl_pool_bwd_direct(const float* p, const float* dM, const int32_t* row_seg, int64_t n_rows, int C, int L,
+                          int dtype, void* dh, int accumulate, void* stream);
+
+/* Backward through the score: given ds[N] and the saved activations uv, overwrites uv with the
+ * gradient w.r.t. the pre-activations (tanh' / sigmoid' applied) and accumulates dwc[D], dbc[1]
+ * (fp32, must be zeroed by the caller). */
+int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, int64_t N, int D,
+                         int gated, int dtype, void* stream);
+
+/* ---- (3) segmented reductions: clam.py:103-132 (top-k instance loss), dsmil.py:71-78 ---- */
+
+/* Indices (global rows) of the k largest and k smallest p within each bag, ordered like
+ * torch.topk (descending p / ascending p).  Fails with MURCL_EINVAL if a bag has < k rows
+ * (the reference raises there too). */
+int murcl_seg_topk_ends(const float* p, const int64_t* offsets, int B, int k, int32_t* top_idx, int32_t* bot_idx,
+                        void* stream);
+
+/* Per bag and class: global row of the first maximum of c[n,cls] (dsmil.py:71-73: row 0 of the
+ * descending sort == arg-max). */
+int murcl_seg_argmax(const float* c, const int64_t* offsets, int B, int C, int32_t* idx, void* stream);
+
+/* DSMIL attention logits a[n,c] = q[n,:].q[crit[b,c],:] / sqrt(Dq) (dsmil.py:74-77). q fp32 [n_rows,Dq]. */
+int murcl_dsmil_scores_fwd(const float* q, const int32_t* crit, const int32_t* row_seg, int64_t n_rows, int C, int Dq,
+                           float* a, void* stream);
+/* Backward: dq[n,:] = sum_c da[n,c]*q[crit]/sqrt(Dq), and dq[crit[b,c],:] += sum_n da[n,c]*q[n,:]/sqrt(Dq).
+ * dq must be zeroed by the caller. */
+int murcl_dsmil_scores_bwd(const float* q, const float* da, const int32_t* crit, const int32_t* row_seg,
+                           const int64_t* offsets, int64_t n_rows, int B, int C, int Dq, float* dq, void* stream);
+
+/* Gather rows: out[i,:] = h[idx[i],:] as fp32 (index_select, clam.py:108,110; dsmil.py:73). */
+int murcl_gather_rows(const void* h, const int32_t* idx, int n_idx, int L, int dtype, float* out, void* stream);
+/* Scatter-add fp32 rows into a gradient buffer of storage `dtype`: dh[idx[i],:] += rows[i,:]. */
+int murcl_scatter_add_rows(void* dh, const int32_t* idx, int n_idx, int L, int dtype, const float* rows, void* stream);
+
+/* CLAM instance-classifier tail (clam.py:112-118,126-131).  rows fp32 [R,L] are the gathered top-k
+ * (+ bottom-k) instances; group g = rows [group_off[g], group_off[g+1]) scored by classifier
+ * group_cls[g] (w [n_cls,2,L], bias [n_cls,2]); targets[R] in {0,1}.  loss[g] = mean CE of the group,
+ * preds[R] = arg-max, dlogits[R,2] = (softmax - onehot)/rows_in_group (saved for the backward). */
+int murcl_clam_inst_ce_fwd(const float* rows, const int32_t* targets, const int32_t* group_off, const int32_t* group_cls,
+                           int G, const float* w, const float* bias, int L, float* loss, int32_t* preds, float* dlogits,
+                           void* stream);
+/* Given gloss[g] = d/d loss[g]: drows[R,L]; dw, db are ACCUMULATED (caller zeroes them). */
+int murcl_clam_inst_ce_bwd(const float* rows, const float* dlogits, const float* gloss, const int32_t* group_off,
+                           const int32_t* group_cls, int G, const float* w, int L, float* drows, float* dw, float* db,
+                           void* stream);
+
+/* ---- (4) NT-Xent: utils/losses.py:5-41, train_MuRCL.py:253,282 ------------------------- */
+
+/* z fp32 [2B,d]: rows [0,B) view i, [B,2B) view j.  loss[1] = mean_a(LSE_{b!=a} s_ab - s_a,pos(a)),
+ * s = cos/tau; dz[2B,d] = d loss / d z (NULL to skip); cos_pair[B] = cos(z_i[b], z_j[b]) (NULL to
+ * skip).  workspace: 2B*d + 4*2B floats. */
+int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
+                         float* workspace, void* stream);
+
+/* ---- (5) recurrent heads: rlmil.py:66-97 (actor), :187-220 (Full_layer) --------------- */
+
+/* GRU cell from the two gate pre-activations gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh
+ * (both [B,3H], gate order r,z,n).  gates_out [B,3H] saves (r,z,n) for the backward (may be NULL). */
+int murcl_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, float* h_new, float* gates_out, int B,
+                       int H, void* stream);
+/* Given dh_new: dgi, dgh [B,3H] and dh_prev [B,H] (the direct z*dh term; the caller adds dgh.W_hh). */
+int murcl_gru_cell_bwd(const float* dh_new, const float* gates, const float* gh, const float* h_prev, float* dgi,
+                       float* dgh, float* dh_prev, int B, int H, void* stream);
+/* Actor head: mean = sigmoid(logits); a = clip(mean + std*eps, 0, 1); logprob of a under
+ * N(mean, std^2 I) (rlmil.py:82-90). */
+int murcl_actor_head(const float* logits, const float* eps, float std, float* action, float* logprob, float* mean,
+                     int B, int K, void* stream);
+
+/* ---- helpers ---------------------------------------------------------------------------- */
+int murcl_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* row_seg[n] = bag id of row n, from offsets. */
+int murcl_row_segments(const int64_t* offsets, int B, int32_t* row_seg, void* stream);
+/* out[n] = (fp32) column sums of a[M,N] (storage dtype). */
+int murcl_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* stream);
+/* dz = dy * (y > 0) elementwise (ReLU backward), same storage dtype. */
+int murcl_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MURCL_B200_H */

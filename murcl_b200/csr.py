@@ -1,0 +1,150 @@
+"""Device-resident ragged-bag store (CSR) and the packer calls on it.
+
+Replaces the per-step Python list handling of ``get_feats`` (utils/datasets.py:274-308): all slides
+of a batch (or of the whole dataset - Camelyon16 is ~4.4 GB) live in ONE
+feature buffer ``feats[n_rows, D]`` with ``offsets[B+1]``; every patch carries its cluster label and
+its rank inside that cluster, which is all the selection rule needs.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, MurclError, check
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class BagStore:
+    """CSR store of B slides on one CUDA device."""
+
+    def __init__(self, feats: torch.Tensor, offsets_host: Sequence[int], patch_cluster: torch.Tensor,
+                 patch_rank: torch.Tensor, cluster_sizes: torch.Tensor, num_clusters: int):
+        self.feats = feats                      # [n_rows, D] fp32 cuda
+        self.offsets_host = [int(o) for o in offsets_host]
+        self.offsets = torch.tensor(self.offsets_host, dtype=torch.int64, device=feats.device)
+        self.patch_cluster = patch_cluster      # [n_rows] int32
+        self.patch_rank = patch_rank            # [n_rows] int32
+        self.cluster_sizes = cluster_sizes      # [B, K] int32
+        self.K = int(num_clusters)
+
+    # -- construction ---------------------------------------------------------------------------
+    @staticmethod
+    def _stack_feats(feat_list, device) -> tuple:
+        sizes = [int(f.shape[-2]) for f in feat_list]
+        d = int(feat_list[0].shape[-1])
+        offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        feats = torch.empty((int(offsets[-1]), d), dtype=torch.float32, device=device)
+        for f, lo, hi in zip(feat_list, offsets[:-1], offsets[1:]):
+            # host (ideally pinned) or device source: one copy straight into the CSR slot
+            feats[lo:hi].copy_(f.reshape(-1, d), non_blocking=True)
+        return feats, offsets
+
+    @classmethod
+    def from_cluster_lists(cls, feat_list: List[torch.Tensor], clusters_list: List[List[List[int]]], device=None):
+        """From the reference's in-memory format: per slide a ``[N,D]`` (or ``[1,N,D]``) tensor and the
+        JSON inverted lists ``clusters[j] = [patch ids]`` (datasets.py:145-165).  The rank of a patch
+        is its POSITION in its list, so non-ascending lists behave as in the reference's slicing."""
+        device = torch.device(device) if device is not None else (
+            feat_list[0].device if feat_list[0].is_cuda else torch.device("cuda"))
+        if device.type != "cuda":
+            raise MurclError("BagStore needs a CUDA device (libmurcl_b200 has no CPU path)")
+        feats, offsets = cls._stack_feats(feat_list, device)
+        K = len(clusters_list[0])
+        n_rows = int(offsets[-1])
+        cluster = np.full(n_rows, -1, dtype=np.int32)
+        rank = np.full(n_rows, -1, dtype=np.int32)
+        sizes = np.zeros((len(feat_list), K), dtype=np.int32)
+        for b, clusters in enumerate(clusters_list):
+            if len(clusters) != K:
+                raise MurclError("all slides must use the same number of clusters")
+            lo = offsets[b]
+            for j, c in enumerate(clusters):
+                if len(c):
+                    ids = np.asarray(c, dtype=np.int64) + lo
+                    cluster[ids] = j
+                    rank[ids] = np.arange(len(c), dtype=np.int32)
+                sizes[b, j] = len(c)
+        return cls(feats, offsets, torch.from_numpy(cluster).to(device), torch.from_numpy(rank).to(device),
+                   torch.from_numpy(sizes).to(device), K)
+
+    @classmethod
+    def from_labels(cls, feat_list: List[torch.Tensor], labels_list: List[torch.Tensor], num_clusters: int, device=None):
+        """From the on-disk format: per slide ``img_features [N,D]`` and ``features_cluster_indices [N]``
+        (features_clustering.py:10-16).  Ranks and cluster sizes are computed on the device."""
+        device = torch.device(device) if device is not None else torch.device("cuda")
+        feats, offsets = cls._stack_feats(feat_list, device)
+        n_rows, B = int(offsets[-1]), len(feat_list)
+        labels = torch.empty((n_rows,), dtype=torch.int32, device=device)
+        for l, lo, hi in zip(labels_list, offsets[:-1], offsets[1:]):
+            labels[lo:hi].copy_(torch.as_tensor(l).reshape(-1).to(torch.int32), non_blocking=True)
+        rank = torch.empty_like(labels)
+        sizes = torch.empty((B, num_clusters), dtype=torch.int32, device=device)
+        off_dev = torch.tensor(offsets, dtype=torch.int64, device=device)
+        check(_lib.load().murcl_csr_rank_patches(labels.data_ptr(), off_dev.data_ptr(), B, num_clusters, rank.data_ptr(),
+                                                 sizes.data_ptr(), _s()), "murcl_csr_rank_patches")
+        return cls(feats, offsets, labels, rank, sizes, num_clusters)
+
+    # -- properties -------------------------------------------------------------------------------
+    @property
+    def num_bags(self) -> int:
+        return len(self.offsets_host) - 1
+
+    @property
+    def dim(self) -> int:
+        return int(self.feats.shape[1])
+
+    @property
+    def device(self):
+        return self.feats.device
+
+    # -- packer -----------------------------------------------------------------------------------
+    def select(self, actions: torch.Tensor, feat_size: int, slot_bag: Optional[torch.Tensor] = None):
+        """Selection only: ``sel_idx [S, FS]`` int32 global CSR rows (-1 = pad) and ``sel_cnt [S]``."""
+        if not actions.is_cuda:
+            raise MurclError("BagStore.select: actions must be a CUDA tensor")
+        actions = actions.detach().to(torch.float32).contiguous()
+        S, K = actions.shape
+        if K != self.K:
+            raise MurclError(f"actions have {K} columns but the store has {self.K} clusters")
+        if slot_bag is None and S != self.num_bags:
+            raise MurclError(f"{S} action rows for {self.num_bags} bags (pass slot_bag to map slots to bags)")
+        sel_idx = torch.empty((S, feat_size), dtype=torch.int32, device=self.device)
+        sel_cnt = torch.empty((S,), dtype=torch.int32, device=self.device)
+        check(_lib.load().murcl_pack_select(self.patch_cluster.data_ptr(), self.patch_rank.data_ptr(), self.offsets.data_ptr(),
+                                            self.cluster_sizes.data_ptr(), None if slot_bag is None else slot_bag.data_ptr(),
+                                            actions.data_ptr(), S, K, feat_size, sel_idx.data_ptr(), sel_cnt.data_ptr(), _s()),
+              "murcl_pack_select")
+        return sel_idx, sel_cnt
+
+    def gather(self, sel_idx: torch.Tensor, lam: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
+               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """Gather + zero pad (+ mixup) -> ``[S, FS, D]``."""
+        return gather_rows_padded(self.feats, sel_idx, lam, perm, out_dtype)
+
+    def pack(self, actions, feat_size, lam=None, perm=None, out_dtype=torch.float32, slot_bag=None):
+        sel_idx, _ = self.select(actions, feat_size, slot_bag)
+        return self.gather(sel_idx, lam, perm, out_dtype)
+
+
+def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, perm=None, out_dtype=torch.float32):
+    if not feats.is_cuda or feats.dtype != torch.float32 or not feats.is_contiguous():
+        raise MurclError("gather: feats must be a contiguous fp32 CUDA tensor")
+    S, FS = sel_idx.shape
+    D = feats.shape[1]
+    out = torch.empty((S, FS, D), dtype=out_dtype, device=feats.device)
+    if lam is not None:
+        lam = lam.detach().reshape(-1).to(torch.float32).contiguous()
+        perm = perm.detach().reshape(-1).to(torch.int32).contiguous()
+        if lam.numel() != S or perm.numel() != S:
+            raise MurclError("gather: lam / perm must have one entry per output slot")
+    code = {torch.float32: F32, torch.bfloat16: BF16}[out_dtype]
+    check(_lib.load().murcl_pack_gather(feats.data_ptr(), D, sel_idx.data_ptr(), S, FS,
+                                        None if lam is None else lam.data_ptr(), None if perm is None else perm.data_ptr(),
+                                        out.data_ptr(), code, _s()), "murcl_pack_gather")
+    return out

@@ -1,0 +1,242 @@
+// fp32-accumulate SIMT GEMM family behind murcl_linear_{fwd,bwd_input,bwd_weight}.
+//
+// This is the exact-fp32 path (1e-5 relative budget against the reference; tensor cores cannot
+// meet it without split precision) and the any-shape path for operands the tcgen05 kernels in
+// gemm_tc.cu do not take.  Roofline: FFMA pipe (148 SM x 128 lanes x 2 x clk), ridge ~11 FLOP/B.
+//
+// C[m,n] = sum_k A(m,k) * B(n,k).  Operand storage is described by two flags:
+//   A_KC: A stored [M,K] row-major (k contiguous)   else stored [K,M] row-major (m contiguous)
+//   B_KC: B stored [N,K] row-major (k contiguous)   else stored [K,N] row-major (n contiguous)
+// 128x128x16 CTA tile, 256 threads, 8x8 register tile per thread, double-buffered smem with
+// register prefetch.  gridDim.z splits K (used for the weight gradient where K = #rows).
+#include "common.cuh"
+
+namespace murcl {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+struct GemmParams {
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t M;      // rows of C
+  int N;          // cols of C
+  int64_t K;      // reduction length
+  int64_t lda, ldb, ldc;
+  const float* bias;        // [N] or null
+  int act;
+  const void* relu_src;     // [M,N] (ld = ldc) or null: multiply by (relu_src > 0)
+  const float* row_scale;   // [M] or null: C += row_scale[m] * row_vec[row_seg[m]*N + n]
+  const float* row_vec;
+  const int32_t* row_seg;
+  int64_t k_chunk;          // K range per blockIdx.z
+  int64_t split_stride;     // elements between split outputs (C is fp32 workspace when gridDim.z > 1)
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* base, int64_t ld, int64_t major, int64_t minor, int64_t major_lim,
+                                      int64_t minor_lim, bool vec_ok, float (&v)[8]) {
+  // 8 consecutive elements along the contiguous ("minor") direction of row `major`.
+  if (major < major_lim && vec_ok && minor + 8 <= minor_lim) {
+    const T* p = base + major * ld + minor;
+    float4 a = load4(p), b = load4(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (major < major_lim && minor + j < minor_lim) ? Store<T>::load(base + major * ld + minor + j) : 0.f;
+  }
+}
+
+template <typename TA, typename TB, typename TC, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  const TA* A = static_cast<const TA*>(p.A);
+  const TB* B = static_cast<const TB*>(p.B);
+  const int t = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t k_begin = (int64_t)blockIdx.z * p.k_chunk;
+  const int64_t k_end = min(p.K, k_begin + p.k_chunk);
+  const bool a_vec = (p.lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool b_vec = (p.ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+  // loader coordinates
+  const int a_r = A_KC ? (t & 127) : (t >> 4);          // KC: row in tile | MC: k in tile
+  const int a_c = A_KC ? (t >> 7) * 8 : (t & 15) * 8;   // KC: k offset    | MC: m offset
+  const int b_r = B_KC ? (t & 127) : (t >> 4);
+  const int b_c = B_KC ? (t >> 7) * 8 : (t & 15) * 8;
+
+  float ra[8], rb[8];
+  auto fetch = [&](int64_t k0) {
+    if (A_KC) load8<TA>(A, p.lda, m0 + a_r, k0 + a_c, p.M, k_end, a_vec, ra);
+    else load8<TA>(A, p.lda, k0 + a_r, m0 + a_c, k_end, p.M, a_vec, ra);
+    if (B_KC) load8<TB>(B, p.ldb, n0 + b_r, k0 + b_c, p.N, k_end, b_vec, rb);
+    else load8<TB>(B, p.ldb, k0 + b_r, n0 + b_c, k_end, p.N, b_vec, rb);
+  };
+  auto stash = [&](int buf) {
+    if (A_KC) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[buf][a_c + j][a_r] = ra[j];
+    } else {
+      *reinterpret_cast<float4*>(&As[buf][a_r][a_c]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+      *reinterpret_cast<float4*>(&As[buf][a_r][a_c + 4]) = make_float4(ra[4], ra[5], ra[6], ra[7]);
+    }
+    if (B_KC) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Bs[buf][b_c + j][b_r] = rb[j];
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][b_r][b_c]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+      *reinterpret_cast<float4*>(&Bs[buf][b_r][b_c + 4]) = make_float4(rb[4], rb[5], rb[6], rb[7]);
+    }
+  };
+
+  const int tx = t & 15, ty = t >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stash(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // epilogue
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= p.M) continue;
+    float rs = 0.f;
+    const float* rv = nullptr;
+    if (p.row_scale) {
+      rs = p.row_scale[m];
+      rv = p.row_vec + (int64_t)p.row_seg[m] * p.N;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (split) {
+        static_cast<float*>(p.C)[(int64_t)blockIdx.z * p.split_stride + m * p.ldc + n] = v;
+        continue;
+      }
+      if (p.bias) v += p.bias[n];
+      v = apply_act(v, p.act, n, p.N);
+      if (rv) v = fmaf(rs, rv[n], v);
+      if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) v = 0.f;
+      Store<TC>::store(static_cast<TC*>(p.C) + m * p.ldc + n, v);
+    }
+  }
+}
+
+// Sum split-K partials: out[i] = sum_z ws[z*stride + i].
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t stride,
+                                                            float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[z * stride + i];
+  out[i] = s;
+}
+
+template <typename TA, typename TB, typename TC, bool A_KC, bool B_KC>
+static int launch(const GemmParams& p, int splits, cudaStream_t st) {
+  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN), splits);
+  gemm_simt_kernel<TA, TB, TC, A_KC, B_KC><<<grid, 256, 0, st>>>(p);
+  return check_launch("gemm_simt_kernel");
+}
+
+int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act,
+                    int dtype, int out_dtype, cudaStream_t st) {
+  GemmParams p{};
+  p.A = x; p.B = w; p.C = y; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldb = K; p.ldc = N;
+  p.bias = bias; p.act = act; p.k_chunk = K;
+  if (dtype == MURCL_F32 && out_dtype == MURCL_F32) return launch<float, float, float, true, true>(p, 1, st);
+  if (dtype == MURCL_BF16 && out_dtype == MURCL_BF16)
+    return launch<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, true>(p, 1, st);
+  if (dtype == MURCL_BF16 && out_dtype == MURCL_F32)
+    return launch<__nv_bfloat16, __nv_bfloat16, float, true, true>(p, 1, st);
+  set_error("linear_fwd(simt): unsupported dtype pair %d -> %d", dtype, out_dtype);
+  return MURCL_EUNSUPPORTED;
+}
+
+int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
+                          const float* row_scale, const float* row_vec, const int32_t* row_seg, int dtype,
+                          cudaStream_t st) {
+  GemmParams p{};
+  // C = dx [M, K]; reduction over N; A = dy [M,N] k-contiguous; B(n'=k_in, k'=n) = w[n, k_in] n'-contiguous.
+  p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
+  p.relu_src = relu_src; p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.k_chunk = N;
+  if (dtype == MURCL_F32) return launch<float, float, float, true, false>(p, 1, st);
+  return launch<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, false>(p, 1, st);
+}
+
+static int bwd_weight_splits(int64_t M, int N, int K) {
+  const int tiles = ceil_div(N, BM) * ceil_div(K, BN);
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  const int max_by_rows = (int)((M + 4 * BK - 1) / (4 * BK));
+  if (splits > max_by_rows) splits = max_by_rows;
+  if (splits < 1) splits = 1;
+  if (splits > 512) splits = 512;
+  return splits;
+}
+
+int64_t simt_linear_bwd_weight_workspace(int64_t M, int N, int K) {
+  const int s = bwd_weight_splits(M, N, K);
+  return s > 1 ? (int64_t)s * N * K : 0;
+}
+
+int simt_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, int N, int K, int dtype,
+                           float* workspace, cudaStream_t st) {
+  const int splits = bwd_weight_splits(M, N, K);
+  GemmParams p{};
+  // C = dw [N, K]; reduction over rows M; A(m'=n, k'=m) = dy[m, n]; B(n'=k_in, k'=m) = x[m, k_in].
+  p.A = dy; p.B = x; p.M = N; p.N = K; p.K = M; p.lda = N; p.ldb = K; p.ldc = K;
+  int64_t chunk = (M + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  p.k_chunk = chunk;
+  p.split_stride = (int64_t)N * K;
+  p.C = splits > 1 ? (void*)workspace : (void*)dw;
+  if (splits > 1 && workspace == nullptr) {
+    set_error("linear_bwd_weight: workspace required (%d splits)", splits);
+    return MURCL_EINVAL;
+  }
+  int rc = (dtype == MURCL_F32) ? launch<float, float, float, false, false>(p, splits, st)
+                                : launch<__nv_bfloat16, __nv_bfloat16, float, false, false>(p, splits, st);
+  if (rc != MURCL_OK || splits == 1) return rc;
+  const int64_t n = (int64_t)N * K;
+  splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(workspace, splits, n, dw, n);
+  return check_launch("splitk_reduce_kernel");
+}
+
+}  // namespace murcl

@@ -1,0 +1,230 @@
+// Small recurrent-head kernels (GRU cell of Full_layer / the PPO actor, rlmil.py:47,76-90,199,213-220)
+// and elementwise helpers (cast, column sums, ReLU backward, CSR row -> bag map).
+#include "common.cuh"
+
+namespace murcl {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// h' = (1 - z) * n + z * h,  r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n)
+__global__ void __launch_bounds__(256) gru_cell_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                                           const float* __restrict__ h_prev, float* __restrict__ h_new,
+                                                           float* __restrict__ gates, int B, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * H) return;
+  const int b = (int)(i / H), j = (int)(i % H);
+  const float* a = gi + (int64_t)b * 3 * H;
+  const float* c = gh + (int64_t)b * 3 * H;
+  const float r = sigmoidf_(a[j] + c[j]);
+  const float z = sigmoidf_(a[H + j] + c[H + j]);
+  const float n = tanhf(a[2 * H + j] + r * c[2 * H + j]);
+  const float hp = h_prev ? h_prev[i] : 0.f;
+  h_new[i] = (1.f - z) * n + z * hp;
+  if (gates) {
+    float* g = gates + (int64_t)b * 3 * H;
+    g[j] = r;
+    g[H + j] = z;
+    g[2 * H + j] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256) gru_cell_bwd_kernel(const float* __restrict__ dh_new, const float* __restrict__ gates,
+                                                           const float* __restrict__ gh, const float* __restrict__ h_prev,
+                                                           float* __restrict__ dgi, float* __restrict__ dgh,
+                                                           float* __restrict__ dh_prev, int B, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * H) return;
+  const int b = (int)(i / H), j = (int)(i % H);
+  const float* g = gates + (int64_t)b * 3 * H;
+  const float r = g[j], z = g[H + j], n = g[2 * H + j];
+  const float hn = gh[(int64_t)b * 3 * H + 2 * H + j];
+  const float hp = h_prev ? h_prev[i] : 0.f;
+  const float dh = dh_new[i];
+  const float dn = dh * (1.f - z);
+  const float dz = dh * (hp - n);
+  const float dan = dn * (1.f - n * n);
+  const float dar = dan * hn * r * (1.f - r);
+  const float daz = dz * z * (1.f - z);
+  float* o = dgi + (int64_t)b * 3 * H;
+  float* q = dgh + (int64_t)b * 3 * H;
+  o[j] = dar;
+  o[H + j] = daz;
+  o[2 * H + j] = dan;
+  q[j] = dar;
+  q[H + j] = daz;
+  q[2 * H + j] = dan * r;
+  if (dh_prev) dh_prev[i] = dh * z;
+}
+
+__global__ void __launch_bounds__(128) actor_head_kernel(const float* __restrict__ logits, const float* __restrict__ eps,
+                                                         float std, float* __restrict__ action, float* __restrict__ logprob,
+                                                         float* __restrict__ mean, int B, int K) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float q = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float mu = sigmoidf_(logits[(int64_t)b * K + k]);
+    float a = mu + std * eps[(int64_t)b * K + k];
+    a = fminf(fmaxf(a, 0.f), 1.f);
+    const float t = (a - mu) / std;
+    q = fmaf(t, t, q);
+    action[(int64_t)b * K + k] = a;
+    if (mean) mean[(int64_t)b * K + k] = mu;
+  }
+  logprob[b] = -0.5f * q - (float)K * logf(std) - 0.5f * (float)K * 1.8378770664093453f;  // log(2 pi)
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    store4(dst + i, load4(src + i));
+  } else {
+    for (int64_t j = i; j < n; ++j) Store<TD>::store(dst + j, Store<TS>::load(src + j));
+  }
+}
+
+__global__ void __launch_bounds__(256) row_segments_kernel(const int64_t* __restrict__ offsets, int32_t* __restrict__ row_seg) {
+  const int b = blockIdx.x;
+  const int64_t lo = offsets[b], hi = offsets[b + 1];
+  for (int64_t n = lo + threadIdx.x; n < hi; n += blockDim.x) row_seg[n] = b;
+}
+
+// Column sums: grid (column tiles of 32, row slices); each warp walks rows, lanes own columns.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, int64_t M, int N, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float acc = 0.f;
+  if (col < N)
+    for (int64_t r = r0 + w; r < r1; r += 8) acc += Store<T>::load(a + r * N + col);
+  sm[w][lane] = acc;
+  __syncthreads();
+  if (w == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i][lane];
+    if (col < N) atomicAdd(&out[col], t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz,
+                                                       int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    float4 g = load4(dy + i);
+    const float4 v = load4(y + i);
+    g.x = v.x > 0.f ? g.x : 0.f;
+    g.y = v.y > 0.f ? g.y : 0.f;
+    g.z = v.z > 0.f ? g.z : 0.f;
+    g.w = v.w > 0.f ? g.w : 0.f;
+    store4(dz + i, g);
+  } else {
+    for (int64_t j = i; j < n; ++j)
+      Store<T>::store(dz + j, Store<T>::load(y + j) > 0.f ? Store<T>::load(dy + j) : 0.f);
+  }
+}
+
+int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st);
+  if (e != cudaSuccess) {
+    set_error("colsum: memset failed: %s", cudaGetErrorString(e));
+    return MURCL_ECUDA;
+  }
+  const int col_tiles = ceil_div(N, 32);
+  int slices = (4 * sm_count() + col_tiles - 1) / col_tiles;
+  const int by_rows = (int)((M + 63) / 64);
+  if (slices > by_rows) slices = by_rows;
+  if (slices < 1) slices = 1;
+  if (slices > 65535) slices = 65535;
+  dim3 grid(col_tiles, slices);
+  if (dtype == MURCL_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)a, M, N, out);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, M, N, out);
+  return check_launch("colsum_kernel");
+}
+
+}  // namespace murcl
+
+using namespace murcl;
+
+extern "C" {
+
+int murcl_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, float* h_new, float* gates_out, int B, int H,
+                       void* stream) {
+  MURCL_REQUIRE(gi && gh && h_new, "gru_cell_fwd: null pointer");
+  MURCL_REQUIRE(B >= 0 && H > 0, "gru_cell_fwd: bad shape");
+  if (B == 0) return MURCL_OK;
+  gru_cell_fwd_kernel<<<ceil_div((int64_t)B * H, 256), 256, 0, as_stream(stream)>>>(gi, gh, h_prev, h_new, gates_out, B, H);
+  return check_launch("gru_cell_fwd_kernel");
+}
+
+int murcl_gru_cell_bwd(const float* dh_new, const float* gates, const float* gh, const float* h_prev, float* dgi, float* dgh,
+                       float* dh_prev, int B, int H, void* stream) {
+  MURCL_REQUIRE(dh_new && gates && gh && dgi && dgh, "gru_cell_bwd: null pointer");
+  MURCL_REQUIRE(B >= 0 && H > 0, "gru_cell_bwd: bad shape");
+  if (B == 0) return MURCL_OK;
+  gru_cell_bwd_kernel<<<ceil_div((int64_t)B * H, 256), 256, 0, as_stream(stream)>>>(dh_new, gates, gh, h_prev, dgi, dgh,
+                                                                                     dh_prev, B, H);
+  return check_launch("gru_cell_bwd_kernel");
+}
+
+int murcl_actor_head(const float* logits, const float* eps, float std, float* action, float* logprob, float* mean, int B,
+                     int K, void* stream) {
+  MURCL_REQUIRE(logits && eps && action && logprob, "actor_head: null pointer");
+  MURCL_REQUIRE(B >= 0 && K > 0 && std > 0.f, "actor_head: bad B=%d K=%d std=%g", B, K, (double)std);
+  if (B == 0) return MURCL_OK;
+  actor_head_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(logits, eps, std, action, logprob, mean, B, K);
+  return check_launch("actor_head_kernel");
+}
+
+int murcl_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+  MURCL_REQUIRE(src && dst, "cast: null pointer");
+  MURCL_REQUIRE(n >= 0, "cast: negative length");
+  if (n == 0) return MURCL_OK;
+  cudaStream_t st = as_stream(stream);
+  const int grid = ceil_div((n + 3) / 4, 256);
+  if (src_dtype == MURCL_F32 && dst_dtype == MURCL_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == MURCL_BF16 && dst_dtype == MURCL_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == MURCL_F32 && dst_dtype == MURCL_F32)
+    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == MURCL_BF16 && dst_dtype == MURCL_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else MURCL_REQUIRE(false, "cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  return check_launch("cast_kernel");
+}
+
+int murcl_row_segments(const int64_t* offsets, int B, int32_t* row_seg, void* stream) {
+  MURCL_REQUIRE(offsets && row_seg, "row_segments: null pointer");
+  if (B <= 0) return MURCL_OK;
+  row_segments_kernel<<<B, 256, 0, as_stream(stream)>>>(offsets, row_seg);
+  return check_launch("row_segments_kernel");
+}
+
+int murcl_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* stream) {
+  MURCL_REQUIRE(a && out, "colsum: null pointer");
+  MURCL_REQUIRE(M >= 0 && N > 0 && (dtype == MURCL_F32 || dtype == MURCL_BF16), "colsum: bad arguments");
+  if (M == 0) {
+    MURCL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, as_stream(stream)));
+    return MURCL_OK;
+  }
+  return colsum_impl(a, M, N, dtype, out, as_stream(stream));
+}
+
+int murcl_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, int dtype, void* stream) {
+  MURCL_REQUIRE(dy && y && dz, "relu_bwd: null pointer");
+  if (n <= 0) return MURCL_OK;
+  cudaStream_t st = as_stream(stream);
+  const int grid = ceil_div((n + 3) / 4, 256);
+  if (dtype == MURCL_F32) relu_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, (float*)dz, n);
+  else if (dtype == MURCL_BF16)
+    relu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dz, n);
+  else MURCL_REQUIRE(false, "relu_bwd: bad dtype %d", dtype);
+  return check_launch("relu_bwd_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// C-ABI dispatch for the dense layers: picks the tcgen05 path (gemm_tc.cu) when the operands are
+// bf16 and the shape fits its tiles, otherwise the exact-fp32 SIMT path (gemm_simt.cu).
+#include "common.cuh"
+
+namespace murcl {
+int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t);
+int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
+                          const int32_t*, int, cudaStream_t);
+int64_t simt_linear_bwd_weight_workspace(int64_t, int, int);
+int simt_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, float*, cudaStream_t);
+
+bool tc_fwd_supported(int64_t M, int N, int K, int dtype, int out_dtype);
+bool tc_bwd_input_supported(int64_t M, int N, int K, int dtype);
+bool tc_bwd_weight_supported(int64_t M, int N, int K, int dtype);
+int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, cudaStream_t);
+int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
+                        const int32_t*, cudaStream_t);
+int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
+int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t);
+
+int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st);
+}  // namespace murcl
+
+using namespace murcl;
+
+static bool valid_dtype(int d) { return d == MURCL_F32 || d == MURCL_BF16; }
+
+extern "C" {
+
+int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act,
+                     int dtype, int out_dtype, int backend, void* stream) {
+  MURCL_REQUIRE(x && w && y, "linear_fwd: null pointer");
+  MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  MURCL_REQUIRE(valid_dtype(dtype) && valid_dtype(out_dtype), "linear_fwd: bad dtype");
+  MURCL_REQUIRE(act >= MURCL_ACT_NONE && act <= MURCL_ACT_TANH_SIGMOID, "linear_fwd: bad activation %d", act);
+  MURCL_REQUIRE(act != MURCL_ACT_TANH_SIGMOID || (N % 2) == 0, "linear_fwd: gated activation needs even N");
+  if (M == 0) return MURCL_OK;
+  const bool tc_ok = tc_fwd_supported(M, N, K, dtype, out_dtype);
+  if (backend == MURCL_GEMM_TCGEN05 && !tc_ok) {
+    set_error("linear_fwd: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d->%d", (long long)M, N, K, dtype, out_dtype);
+    return MURCL_EUNSUPPORTED;
+  }
+  if (backend != MURCL_GEMM_SIMT && tc_ok) return tc_linear_fwd(x, w, bias, y, M, N, K, act, out_dtype, as_stream(stream));
+  return simt_linear_fwd(x, w, bias, y, M, N, K, act, dtype, out_dtype, as_stream(stream));
+}
+
+int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
+                           const float* row_scale, const float* row_vec, const int32_t* row_seg, int dtype, int backend,
+                           void* stream) {
+  MURCL_REQUIRE(dy && w && dx, "linear_bwd_input: null pointer");
+  MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_input: bad shape");
+  MURCL_REQUIRE(valid_dtype(dtype), "linear_bwd_input: bad dtype");
+  MURCL_REQUIRE((row_scale == nullptr) == (row_vec == nullptr) && (row_scale == nullptr) == (row_seg == nullptr),
+                "linear_bwd_input: row_scale, row_vec and row_seg must be given together");
+  if (M == 0) return MURCL_OK;
+  const bool tc_ok = tc_bwd_input_supported(M, N, K, dtype);
+  if (backend == MURCL_GEMM_TCGEN05 && !tc_ok) {
+    set_error("linear_bwd_input: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d", (long long)M, N, K, dtype);
+    return MURCL_EUNSUPPORTED;
+  }
+  if (backend != MURCL_GEMM_SIMT && tc_ok)
+    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, as_stream(stream));
+  return simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, dtype, as_stream(stream));
+}
+
+int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K) {
+  const int64_t a = simt_linear_bwd_weight_workspace(M, N, K), b = tc_linear_bwd_weight_workspace(M, N, K);
+  return a > b ? a : b;
+}
+
+int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K, int dtype,
+                            int backend, float* workspace, void* stream) {
+  MURCL_REQUIRE(dy && x && dw, "linear_bwd_weight: null pointer");
+  MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_weight: bad shape");
+  MURCL_REQUIRE(valid_dtype(dtype), "linear_bwd_weight: bad dtype");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) {
+    MURCL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    if (db) MURCL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+    return MURCL_OK;
+  }
+  if (db) {
+    int rc = colsum_impl(dy, M, N, dtype, db, st);
+    if (rc != MURCL_OK) return rc;
+  }
+  const bool tc_ok = tc_bwd_weight_supported(M, N, K, dtype);
+  if (backend == MURCL_GEMM_TCGEN05 && !tc_ok) {
+    set_error("linear_bwd_weight: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d", (long long)M, N, K, dtype);
+    return MURCL_EUNSUPPORTED;
+  }
+  if (backend != MURCL_GEMM_SIMT && tc_ok) return tc_linear_bwd_weight(dy, x, dw, M, N, K, workspace, st);
+  return simt_linear_bwd_weight(dy, x, dw, M, N, K, dtype, workspace, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// Ragged-bag packer: cluster-wise window selection, stream compaction, row gather, zero pad and
+// mixup.  Replaces utils/datasets.py:274-308 (get_feats) and :263-271 (mixup).
+//
+// HBM layout: all bags concatenated row-wise (CSR): feats[n_rows, D] fp32, offsets[B+1] int64,
+// per patch (cluster label, rank inside its cluster) int32, per bag cluster sizes [B, K] int32.
+// The kernels are pure HBM movers: 16-byte vector accesses, one warp per gathered row.
+#include "common.cuh"
+
+namespace murcl {
+
+// ---- ingest: rank of each patch inside its cluster -------------------------------------------
+// One CTA per bag walks the bag in patch order; warp-level match + cross-warp prefix in smem.
+__global__ void __launch_bounds__(256) rank_patches_kernel(const int32_t* __restrict__ patch_cluster,
+                                                           const int64_t* __restrict__ offsets, int K,
+                                                           int32_t* __restrict__ patch_rank,
+                                                           int32_t* __restrict__ cluster_sizes) {
+  extern __shared__ int32_t sm[];
+  const int nw = blockDim.x >> 5;
+  int32_t* base = sm;           // [K] running count per cluster
+  int32_t* wcnt = sm + K;       // [nw][K] per-warp counts of the current chunk
+  const int bag = blockIdx.x;
+  const int64_t lo = offsets[bag], hi = offsets[bag + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < K * (nw + 1); i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+  for (int64_t start = lo; start < hi; start += blockDim.x) {
+    const int64_t p = start + threadIdx.x;
+    int c = (p < hi) ? patch_cluster[p] : -1;
+    if (c >= K) c = -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (c >= 0 && in_warp == 0) wcnt[w * K + c] = __popc(peers);
+    __syncthreads();
+    if (c >= 0) {
+      int r = base[c] + in_warp;
+      for (int ww = 0; ww < w; ++ww) r += wcnt[ww * K + c];
+      patch_rank[p] = r;
+    } else if (p < hi) {
+      patch_rank[p] = -1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      int add = 0;
+      for (int ww = 0; ww < nw; ++ww) {
+        add += wcnt[ww * K + k];
+        wcnt[ww * K + k] = 0;
+      }
+      base[k] += add;
+    }
+    __syncthreads();
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) cluster_sizes[(int64_t)bag * K + k] = base[k];
+}
+
+// ---- selection ---------------------------------------------------------------------------------
+// Window arithmetic restated from datasets.py:285-291 in the float32 / int32 types torch uses
+// there, plus Python's slice clamping (:294).  No FMA contraction is possible: every expression
+// is a single multiply followed by rint/floor.
+__device__ __forceinline__ void cluster_window(int n, float ratio, float a, int& start, int& stop) {
+  const int size = (int)rintf(__fmul_rn((float)n, ratio));
+  const int l = (int)floorf(__fmul_rn(a, (float)(n - size)));
+  const int r = l + size;
+  start = (l >= 0) ? min(l, n) : max(n + l, 0);
+  stop = (r >= 0) ? min(r, n) : max(n + r, 0);
+  stop = max(stop, start);
+}
+
+__global__ void __launch_bounds__(512) pack_select_kernel(const int32_t* __restrict__ patch_cluster,
+                                                          const int32_t* __restrict__ patch_rank,
+                                                          const int64_t* __restrict__ offsets,
+                                                          const int32_t* __restrict__ cluster_sizes,
+                                                          const int32_t* __restrict__ slot_bag,
+                                                          const float* __restrict__ actions, int K, int FS,
+                                                          int32_t* __restrict__ sel_idx, int32_t* __restrict__ sel_cnt) {
+  extern __shared__ int32_t sm[];
+  int32_t* w_start = sm;        // [K]
+  int32_t* w_stop = sm + K;     // [K]
+  __shared__ int32_t warp_tot[16];
+  __shared__ int32_t s_base;
+  const int slot = blockIdx.x;
+  const int bag = slot_bag ? slot_bag[slot] : slot;
+  const int64_t lo = offsets[bag], hi = offsets[bag + 1];
+  const int64_t n_patch = hi - lo;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float ratio = (float)((double)FS / (double)n_patch);   // python double division, cast to f32
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    int s, e;
+    cluster_window(cluster_sizes[(int64_t)bag * K + k], ratio, actions[(int64_t)slot * K + k], s, e);
+    w_start[k] = s;
+    w_stop[k] = e;
+  }
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  int32_t* out = sel_idx + (int64_t)slot * FS;
+  for (int64_t start = lo; start < hi; start += blockDim.x) {
+    const int base = s_base;
+    if (base >= FS) break;                       // uniform: s_base is read after a barrier
+    const int64_t p = start + threadIdx.x;
+    bool keep = false;
+    if (p < hi) {
+      const int c = patch_cluster[p];
+      if (c >= 0 && c < K) {
+        const int r = patch_rank[p];
+        keep = (r >= w_start[c]) && (r < w_stop[c]);
+      }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[w] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int ww = 0; ww < nw; ++ww) {
+      const int t = warp_tot[ww];
+      before += (ww < w) ? t : 0;
+      total += t;
+    }
+    const int pos = base + before + __popc(ballot & ((1u << lane) - 1u));
+    if (keep && pos < FS) out[pos] = (int32_t)p;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  const int kept = min((int)s_base, FS);
+  for (int i = kept + threadIdx.x; i < FS; i += blockDim.x) out[i] = -1;
+  if (threadIdx.x == 0) sel_cnt[slot] = kept;
+}
+
+// ---- gather + pad + mixup ----------------------------------------------------------------------
+template <typename TO, bool MIX>
+__global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restrict__ feats, int D,
+                                                          const int32_t* __restrict__ sel_idx, int64_t n_out_rows,
+                                                          int FS, const float* __restrict__ lam,
+                                                          const int32_t* __restrict__ perm, TO* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_out_rows) return;
+  const int slot = (int)(row / FS), r = (int)(row % FS);
+  const int32_t ia = sel_idx[row];
+  const float* pa = (ia >= 0) ? feats + (int64_t)ia * D : nullptr;
+  const float* pb = nullptr;
+  float l0 = 1.f, l1 = 0.f;
+  if (MIX) {
+    const int32_t ib = sel_idx[(int64_t)perm[slot] * FS + r];
+    pb = (ib >= 0) ? feats + (int64_t)ib * D : nullptr;
+    l0 = lam[slot];
+    l1 = __fsub_rn(1.f, l0);
+  }
+  TO* po = out + row * D;
+  if ((D & 3) == 0) {
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 a = pa ? __ldg(reinterpret_cast<const float4*>(pa + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MIX) {
+        float4 b = pb ? __ldg(reinterpret_cast<const float4*>(pb + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a.x = __fadd_rn(__fmul_rn(l0, a.x), __fmul_rn(l1, b.x));
+        a.y = __fadd_rn(__fmul_rn(l0, a.y), __fmul_rn(l1, b.y));
+        a.z = __fadd_rn(__fmul_rn(l0, a.z), __fmul_rn(l1, b.z));
+        a.w = __fadd_rn(__fmul_rn(l0, a.w), __fmul_rn(l1, b.w));
+      }
+      store4(po + c, a);
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) {
+      float a = pa ? pa[c] : 0.f;
+      if (MIX) a = __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, pb ? pb[c] : 0.f));
+      Store<TO>::store(po + c, a);
+    }
+  }
+}
+
+}  // namespace murcl
+
+using namespace murcl;
+
+extern "C" {
+
+int murcl_csr_rank_patches(const int32_t* patch_cluster, const int64_t* offsets, int B, int K, int32_t* patch_rank,
+                           int32_t* cluster_sizes, void* stream) {
+  MURCL_REQUIRE(patch_cluster && offsets && patch_rank && cluster_sizes, "csr_rank_patches: null pointer");
+  MURCL_REQUIRE(B >= 0 && K > 0 && K <= 2048, "csr_rank_patches: B=%d K=%d out of range", B, K);
+  if (B == 0) return MURCL_OK;
+  const size_t smem = sizeof(int32_t) * (size_t)K * (256 / 32 + 1);
+  rank_patches_kernel<<<B, 256, smem, as_stream(stream)>>>(patch_cluster, offsets, K, patch_rank, cluster_sizes);
+  return check_launch("rank_patches_kernel");
+}
+
+int murcl_pack_select(const int32_t* patch_cluster, const int32_t* patch_rank, const int64_t* offsets,
+                      const int32_t* cluster_sizes, const int32_t* slot_bag, const float* actions, int S, int K, int FS,
+                      int32_t* sel_idx, int32_t* sel_cnt, void* stream) {
+  MURCL_REQUIRE(patch_cluster && patch_rank && offsets && cluster_sizes && actions && sel_idx && sel_cnt,
+                "pack_select: null pointer");
+  MURCL_REQUIRE(S >= 0 && K > 0 && K <= 4096 && FS > 0, "pack_select: S=%d K=%d FS=%d out of range", S, K, FS);
+  if (S == 0) return MURCL_OK;
+  pack_select_kernel<<<S, 512, sizeof(int32_t) * 2 * (size_t)K, as_stream(stream)>>>(
+      patch_cluster, patch_rank, offsets, cluster_sizes, slot_bag, actions, K, FS, sel_idx, sel_cnt);
+  return check_launch("pack_select_kernel");
+}
+
+int murcl_pack_gather(const float* feats, int D, const int32_t* sel_idx, int S, int FS, const float* lam,
+                      const int32_t* perm, void* out, int out_dtype, void* stream) {
+  MURCL_REQUIRE(feats && sel_idx && out, "pack_gather: null pointer");
+  MURCL_REQUIRE(S >= 0 && FS > 0 && D > 0, "pack_gather: S=%d FS=%d D=%d out of range", S, FS, D);
+  MURCL_REQUIRE((lam == nullptr) == (perm == nullptr), "pack_gather: lam and perm must be given together");
+  MURCL_REQUIRE(out_dtype == MURCL_F32 || out_dtype == MURCL_BF16, "pack_gather: bad out_dtype %d", out_dtype);
+  if (S == 0) return MURCL_OK;
+  const int64_t rows = (int64_t)S * FS;
+  const int grid = ceil_div(rows, 8);
+  cudaStream_t st = as_stream(stream);
+  const bool mix = lam != nullptr;
+  if (out_dtype == MURCL_F32) {
+    if (mix) pack_gather_kernel<float, true><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (float*)out);
+    else pack_gather_kernel<float, false><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (float*)out);
+  } else {
+    if (mix) pack_gather_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (__nv_bfloat16*)out);
+    else pack_gather_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (__nv_bfloat16*)out);
+  }
+  return check_launch("pack_gather_kernel");
+}
+
+}  // extern "C"

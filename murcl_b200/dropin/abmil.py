@@ -1,0 +1,68 @@
+"""``ABMIL`` of models/abmil.py:7-63 on the fused MIL aggregator kernels.
+
+Same constructor, parameter names (``encoder.{0,3,6}``, ``attention.{0,2}``, ``decoder.0``, ``fc``) and
+forward contract.  All bags of a call are processed together as CSR rows: the reference's Python loop
+over bags (abmil.py:47-51) becomes one batched encoder GEMM chain plus segmented softmax pooling.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from ..bags import to_rows
+
+
+class ABMIL(nn.Module):
+    def __init__(self, dim_in, L=512, D=128, K=1, dim_out=2, dropout=0., precision=None):
+        super(ABMIL, self).__init__()
+        self.L, self.D, self.K = L, D, K
+        if K != 1:
+            raise NotImplementedError("ABMIL drop-in supports K=1 attention heads (the reference default)")
+        self.dropout_p = float(dropout)
+        self.precision = precision          # None -> MURCL_PRECISION env (fp32 | bf16)
+
+        # parameter containers only: layout mirrors the reference so checkpoints load unchanged
+        self.encoder = nn.Sequential(
+            nn.Linear(dim_in, L), nn.ReLU(), nn.Dropout(dropout),
+            nn.Linear(L, L), nn.ReLU(), nn.Dropout(dropout),
+            nn.Linear(L, L), nn.ReLU(),
+        )
+        self.attention = nn.Sequential(nn.Linear(L, D), nn.Tanh(), nn.Linear(D, K))
+        self.decoder = nn.Sequential(nn.Linear(L, L), nn.ReLU())
+        self.fc = nn.Linear(L, dim_out)     # defined but never applied upstream (abmil.py:33)
+
+    # ------------------------------------------------------------------------------------------
+    def _meta(self, rows):
+        prec = self.precision or ops.default_precision()
+        return {"B": rows.B, "gated": False, "inv_sqrt_n": True, "dtype": ops.storage_dtype(prec)}
+
+    def _aggregate(self, x):
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError("train-mode dropout inside the fused encoder is not implemented; "
+                                      "use dropout=0 (the reference default) or eval()")
+        rows = to_rows(x)
+        enc = [p for i in (0, 3, 6) for p in (self.encoder[i].weight, self.encoder[i].bias)]
+        M, p, _s, _il, _pr = ops.mil_aggregate(rows.rows, rows.offsets, rows.row_seg, self._meta(rows),
+                                               self.attention[0].weight, self.attention[0].bias,
+                                               self.attention[2].weight, self.attention[2].bias, None, None, enc)
+        out = ops.linear(M, self.decoder[0].weight, self.decoder[0].bias, ops.ACT_RELU)
+        return out, p
+
+    def bag_forward(self, bag):
+        """One bag ``[N, dim_in]`` -> ``[1, L]`` (abmil.py:35-45)."""
+        return self._aggregate([bag])[0]
+
+    def batch_forward(self, batch):
+        """Sequence of bags -> ``[B, L]`` (abmil.py:47-51), batched instead of looped."""
+        return self._aggregate(list(batch) if not isinstance(batch, torch.Tensor) else batch)[0]
+
+    def forward(self, x):  # B x N x dim_in, a bag
+        if isinstance(x, list):
+            outputs = self.batch_forward(x)
+        elif isinstance(x, torch.Tensor):
+            if x.shape[0] == 1:
+                outputs = self.bag_forward(x.squeeze(0))
+            else:
+                outputs = self.batch_forward(x)
+        else:
+            raise TypeError
+        return outputs, outputs.detach()

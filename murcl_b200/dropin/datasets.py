@@ -1,0 +1,53 @@
+"""``get_feats`` and ``mixup`` of utils/datasets.py:263-308 on the CSR packer kernels."""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import List, Tuple, Union
+
+import torch
+
+from ..csr import BagStore, gather_rows_padded
+
+_store_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+_STORE_CACHE_SIZE = 4
+
+
+def bag_store_for(feat_list: List[torch.Tensor], clusters_list: List[List[List[int]]], device) -> BagStore:
+    """The CSR store of a batch, built once and reused by the 2 x T ``get_feats`` calls that
+    train_MuRCL.py:237,266 makes on the same ``feat_list`` / ``cluster_list`` objects."""
+    key = (tuple(id(f) for f in feat_list), tuple(id(c) for c in clusters_list), str(device))
+    hit = _store_cache.get(key)
+    if hit is not None:
+        _store_cache.move_to_end(key)
+        return hit[0]
+    store = BagStore.from_cluster_lists(feat_list, clusters_list, device)
+    # keep the source objects alive so their ids cannot be recycled while the entry exists
+    _store_cache[key] = (store, list(feat_list), list(clusters_list))
+    while len(_store_cache) > _STORE_CACHE_SIZE:
+        _store_cache.popitem(last=False)
+    return store
+
+
+def get_feats(feat_list: List[torch.Tensor],
+              clusters_list: List[List[List[int]]],
+              action_sequence: torch.Tensor,
+              feat_size: int = 1024) -> torch.Tensor:
+    """Construct the WSI-Fset batch ``[B, feat_size, D]`` (utils/datasets.py:274-308): per cluster keep
+    the rank window the action selects, in ascending patch order, zero pad / truncate to ``feat_size``.
+    Selection and gather are bit-exact with the reference."""
+    device = action_sequence.device
+    store = bag_store_for(feat_list, clusters_list, device)
+    return store.pack(action_sequence, feat_size)
+
+
+def mixup(inputs: torch.Tensor, alpha: Union[float, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Mix-up a batch tensor (utils/datasets.py:263-271).  Same RNG calls in the same order on the same
+    device as the reference (``rand`` then ``randperm``); the mix itself is one fused kernel."""
+    batch_size = inputs.shape[0]
+    lambda_ = alpha + torch.rand(size=(batch_size, 1), device=inputs.device) * (1 - alpha)
+    rand_idx = torch.randperm(batch_size, device=inputs.device)
+    flat = inputs.detach().to(torch.float32).contiguous().reshape(-1, inputs.shape[-1])
+    rows = flat.shape[0] // batch_size
+    ident = torch.arange(flat.shape[0], dtype=torch.int32, device=inputs.device).reshape(batch_size, rows)
+    out = gather_rows_padded(flat, ident, lambda_, rand_idx)
+    return out.reshape(inputs.shape), lambda_, rand_idx

@@ -1,0 +1,192 @@
+"""``Memory``, ``ActorCritic``, ``PPO`` and ``Full_layer`` of models/rlmil.py:7-239.
+
+Same constructors, state-dict keys (``state_encoder.{0,2}``, ``gru.*_l0``, ``actor.0``, ``critic.0``;
+``rnn.*_l0``, ``fc``) and call contracts.  The ``nn.GRU`` / ``nn.Linear`` members are parameter containers
+(identical initialisation and checkpoint layout); the math runs on libmurcl_b200's dense-layer, GRU-cell
+and actor-head kernels.  Hard-coded ``.cuda()`` calls of the reference become "the device of the input".
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class Memory:
+    def __init__(self):
+        self.actions = []
+        self.states = []
+        self.logprobs = []
+        self.rewards = []
+        self.is_terminals = []
+        self.hidden = []
+
+    def clear_memory(self):
+        del self.actions[:]
+        del self.states[:]
+        del self.logprobs[:]
+        del self.rewards[:]
+        del self.is_terminals[:]
+        del self.hidden[:]
+
+
+def _gru_params(gru: nn.GRU):
+    return gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, feature_dim, state_dim, hidden_state_dim=1024, policy_conv=False, action_std=0.1, action_size=2):
+        super(ActorCritic, self).__init__()
+        if policy_conv:
+            raise NotImplementedError("policy_conv=True (conv state encoder) is unused by the reference's run scripts")
+        self.state_encoder = nn.Sequential(
+            nn.Linear(state_dim, 2048), nn.ReLU(),
+            nn.Linear(2048, hidden_state_dim), nn.ReLU())
+        self.gru = nn.GRU(hidden_state_dim, hidden_state_dim, batch_first=False)
+        self.actor = nn.Sequential(nn.Linear(hidden_state_dim, action_size), nn.Sigmoid())
+        self.critic = nn.Sequential(nn.Linear(hidden_state_dim, 1))
+        self.action_std = float(action_std)        # the reference stores it as `action_var` but uses it as a std
+        self.action_size = action_size
+        self.hidden_state_dim = hidden_state_dim
+        self.policy_conv = policy_conv
+        self.feature_dim = feature_dim
+        self.feature_ratio = int(math.sqrt(state_dim / feature_dim))
+
+    def forward(self):
+        raise NotImplementedError
+
+    def _encode(self, state):
+        s = ops.linear(state, self.state_encoder[0].weight, self.state_encoder[0].bias, ops.ACT_RELU)
+        return ops.linear(s, self.state_encoder[2].weight, self.state_encoder[2].bias, ops.ACT_RELU)
+
+    def act(self, state_ini, memory, restart_batch=False, training=False, eps=None):
+        """rlmil.py:66-97.  ``eps`` optionally supplies the standard-normal draw (parity tests); by default it
+        is drawn with ``torch.randn`` on the state's device."""
+        with torch.no_grad():
+            if restart_batch:
+                del memory.hidden[:]
+                memory.hidden.append(torch.zeros(1, state_ini.size(0), self.hidden_state_dim, device=state_ini.device))
+            state = state_ini.flatten(1).float().contiguous()
+            enc = self._encode(state)
+            h = ops.gru_step(enc, memory.hidden[-1][0].contiguous(), *_gru_params(self.gru))
+            memory.hidden.append(h.unsqueeze(0))
+            logits = ops.linear(h, self.actor[0].weight, self.actor[0].bias)
+            if eps is None:
+                eps = torch.randn(logits.shape, device=logits.device, dtype=torch.float32)
+            action, logprob, mean = ops.actor_head(logits, eps, self.action_std)
+            if training:
+                memory.states.append(state_ini)
+                memory.actions.append(action)
+                memory.logprobs.append(logprob)
+            else:
+                action = mean
+        return action.detach()
+
+    def evaluate(self, state, action):
+        """rlmil.py:99-127: log-prob, value and entropy of stored (state, action) sequences ``[T, B, ...]``."""
+        seq_l, batch_size = state.size(0), state.size(1)
+        flat = state.flatten(2).reshape(seq_l * batch_size, -1).float().contiguous()
+        enc = self._encode(flat).reshape(seq_l, batch_size, -1)
+        h = torch.zeros(batch_size, self.hidden_state_dim, device=state.device)
+        outs = []
+        for t in range(seq_l):
+            h = ops.gru_step(enc[t].contiguous(), h, *_gru_params(self.gru))
+            outs.append(h)
+        feat = torch.cat(outs, 0)
+        mean = ops.linear(feat, self.actor[0].weight, self.actor[0].bias, ops.ACT_SIGMOID)
+        value = ops.linear(feat, self.critic[0].weight, self.critic[0].bias)
+        k, std = self.action_size, self.action_std
+        a = action.reshape(seq_l * batch_size, -1)
+        logprob = (-0.5 * (((a - mean) / std) ** 2).sum(1) - k * math.log(std) - 0.5 * k * math.log(2 * math.pi))
+        entropy = torch.full_like(logprob, 0.5 * k * (1.0 + math.log(2 * math.pi)) + k * math.log(std))
+        return logprob.view(seq_l, batch_size), value.view(seq_l, batch_size), entropy.view(seq_l, batch_size)
+
+
+class PPO:
+    def __init__(self, feature_dim, state_dim, hidden_state_dim, policy_conv,
+                 action_std=0.1, lr=0.0003, betas=(0.9, 0.999), gamma=0.7, K_epochs=1, eps_clip=0.2, action_size=2):
+        self.lr = lr
+        self.betas = betas
+        self.gamma = gamma
+        self.eps_clip = eps_clip
+        self.K_epochs = K_epochs
+
+        self.policy = ActorCritic(feature_dim, state_dim, hidden_state_dim, policy_conv, action_std, action_size).cuda()
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr, betas=betas)
+        self.policy_old = ActorCritic(feature_dim, state_dim, hidden_state_dim, policy_conv, action_std,
+                                      action_size).cuda()
+        self.policy_old.load_state_dict(self.policy.state_dict())
+        self.MseLoss = nn.MSELoss()
+
+    def select_action(self, state, memory, restart_batch=False, training=True):
+        return self.policy_old.act(state, memory, restart_batch, training)
+
+    def update(self, memory):
+        """PPO-clip update of rlmil.py:152-184 (discounted rewards, K epochs, policy_old <- policy)."""
+        rewards = []
+        discounted_reward = 0
+        for reward in reversed(memory.rewards):
+            discounted_reward = reward + (self.gamma * discounted_reward)
+            rewards.insert(0, discounted_reward)
+        rewards = torch.cat(rewards, 0).cuda()
+        rewards = (rewards - rewards.mean()) / (rewards.std() + 1e-5)
+
+        old_states = torch.stack(memory.states, 0).cuda().detach()
+        old_actions = torch.stack(memory.actions, 0).cuda().detach()
+        old_logprobs = torch.stack(memory.logprobs, 0).cuda().detach()
+
+        for _ in range(self.K_epochs):
+            logprobs, state_values, dist_entropy = self.policy.evaluate(old_states, old_actions)
+            ratios = torch.exp(logprobs - old_logprobs.detach())
+            advantages = rewards - state_values.detach()
+            surr1 = ratios * advantages
+            surr2 = torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages
+            loss = -torch.min(surr1, surr2) + 0.5 * self.MseLoss(state_values, rewards) - 0.01 * dist_entropy
+            self.optimizer.zero_grad()
+            loss.mean().backward()
+            self.optimizer.step()
+
+        self.policy_old.load_state_dict(self.policy.state_dict())
+
+
+class Full_layer(torch.nn.Module):
+    def __init__(self, feature_num, hidden_state_dim=1024, fc_rnn=True, class_num=1000):
+        super(Full_layer, self).__init__()
+        self.class_num = class_num
+        self.feature_num = feature_num
+        self.hidden_state_dim = hidden_state_dim
+        self.hidden = None
+        self.fc_rnn = fc_rnn
+        if fc_rnn:
+            self.rnn = nn.GRU(feature_num, self.hidden_state_dim)
+            self.fc = nn.Linear(self.hidden_state_dim, class_num)
+        else:
+            self.fc_2 = nn.Linear(self.feature_num * 2, class_num)
+            self.fc_3 = nn.Linear(self.feature_num * 3, class_num)
+            self.fc_4 = nn.Linear(self.feature_num * 4, class_num)
+            self.fc_5 = nn.Linear(self.feature_num * 5, class_num)
+
+    def forward(self, x, restart=False):
+        if self.fc_rnn:
+            # ``self.hidden`` is ONE state shared by every caller (both views of train_MuRCL.py:243,272 run
+            # through it in turn) and is carried with its graph across the T patch-steps, as upstream.
+            if restart:
+                h_prev = torch.zeros(x.size(0), self.hidden_state_dim, device=x.device)
+            else:
+                h_prev = self.hidden[0]
+            h = ops.gru_step(x.float().contiguous(), h_prev, *_gru_params(self.rnn))
+            self.hidden = h.unsqueeze(0)
+            return ops.linear(h, self.fc.weight, self.fc.bias)
+        else:
+            if restart:
+                self.hidden = x
+            else:
+                self.hidden = torch.cat([self.hidden, x], 1)
+            width = self.hidden.size(1)
+            if width == self.feature_num:
+                return None
+            for mult, layer in ((2, self.fc_2), (3, self.fc_3), (4, self.fc_4), (5, self.fc_5)):
+                if width == self.feature_num * mult:
+                    return ops.linear(self.hidden.float().contiguous(), layer.weight, layer.bias)
+            raise RuntimeError(f"Full_layer(fc_rnn=False): unexpected accumulated width {width}")

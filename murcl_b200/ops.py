@@ -1,0 +1,547 @@
+"""Tensor-level wrappers over the C ABI (include/murcl_b200.h).
+
+PyTorch supplies device memory, streams and autograd bookkeeping; every computation below is a
+call into libmurcl_b200.so on the caller's current CUDA stream.  There is no CPU path: a CPU
+tensor raises ``MurclError``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_TANH_SIGMOID, BF16, F32, GEMM_AUTO, GEMM_SIMT,
+                   GEMM_TCGEN05, MurclError, check)
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def default_precision() -> str:
+    """'fp32' (exact, FFMA) or 'bf16' (tcgen05, fp32 accumulate).  Env var MURCL_PRECISION."""
+    p = os.environ.get("MURCL_PRECISION", "fp32").lower()
+    if p not in ("fp32", "bf16"):
+        raise MurclError(f"MURCL_PRECISION must be fp32 or bf16, got {p!r}")
+    return p
+
+
+def storage_dtype(precision: str) -> torch.dtype:
+    return torch.bfloat16 if precision == "bf16" else torch.float32
+
+
+def _backend() -> int:
+    return {"auto": GEMM_AUTO, "simt": GEMM_SIMT, "tcgen05": GEMM_TCGEN05}[os.environ.get("MURCL_GEMM", "auto").lower()]
+
+
+def _chk(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise MurclError(f"{name}: expected a CUDA tensor (libmurcl_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise MurclError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise MurclError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise MurclError(f"unsupported storage dtype {t.dtype}") from None
+
+
+# ------------------------------------------------------------------------------------------------
+# raw (non-differentiable) wrappers
+# ------------------------------------------------------------------------------------------------
+def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _chk(src, "cast.src")
+    if src.dtype == dtype:
+        return src
+    dst = torch.empty_like(src, dtype=dtype)
+    check(_lib.load().murcl_cast(_p(src), _dt(src), _p(dst), _DT[dtype], src.numel(), _s()), "murcl_cast")
+    return dst
+
+
+def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Storage-dtype copy of a parameter.  The copy is cached ON the parameter object together with its
+    autograd version counter, so weights are cast once per optimiser update, not once per forward."""
+    if w.dtype == dtype:
+        d = w.detach()
+        return d if d.is_contiguous() else d.contiguous()
+    hit = getattr(w, "_murcl_cast", None)
+    if hit is not None and hit[0] == w._version and hit[1] == dtype and hit[2].shape == w.shape:
+        return hit[2]
+    out = cast(w.detach().contiguous(), dtype)
+    try:
+        w._murcl_cast = (w._version, dtype, out)
+    except AttributeError:
+        pass
+    return out
+
+
+def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
+    _chk(x, "linear_fwd.x"); _chk(w, "linear_fwd.w")
+    if x.dtype != w.dtype:
+        raise MurclError(f"linear_fwd: x is {x.dtype} but w is {w.dtype}")
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise MurclError(f"linear_fwd: shape mismatch x{tuple(x.shape)} w{tuple(w.shape)}")
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    if bias is not None:
+        _chk(bias, "linear_fwd.bias", torch.float32)
+    check(_lib.load().murcl_linear_fwd(_p(x), _p(w), _p(bias), _p(y), M, N, K, act, _dt(x), _DT[out_dtype], _backend(),
+                                       _s()), "murcl_linear_fwd")
+    return y
+
+
+def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None):
+    _chk(dy, "linear_bwd_input.dy"); _chk(w, "linear_bwd_input.w")
+    if dy.dtype != w.dtype:
+        raise MurclError(f"linear_bwd_input: dy is {dy.dtype} but w is {w.dtype}")
+    M, N = dy.shape
+    K = w.shape[1]
+    if w.shape[0] != N:
+        raise MurclError(f"linear_bwd_input: shape mismatch dy{tuple(dy.shape)} w{tuple(w.shape)}")
+    dx = torch.empty((M, K), device=dy.device, dtype=dy.dtype)
+    if relu_src is not None:
+        _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
+    check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
+                                             _p(row_seg), _dt(dy), _backend(), _s()), "murcl_linear_bwd_input")
+    return dx
+
+
+def linear_bwd_weight(dy, x, want_bias=True):
+    _chk(dy, "linear_bwd_weight.dy"); _chk(x, "linear_bwd_weight.x", dy.dtype)
+    M, N = dy.shape
+    K = x.shape[1]
+    lib = _lib.load()
+    dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
+    db = torch.empty((N,), device=dy.device, dtype=torch.float32) if want_bias else None
+    nws = int(lib.murcl_linear_bwd_weight_workspace(M, N, K))
+    ws = torch.empty((max(nws, 1),), device=dy.device, dtype=torch.float32)
+    check(lib.murcl_linear_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), M, N, K, _dt(dy), _backend(), _p(ws), _s()),
+          "murcl_linear_bwd_weight")
+    return dw, db
+
+
+def relu_bwd(dy, y):
+    _chk(dy, "relu_bwd.dy"); _chk(y, "relu_bwd.y", dy.dtype)
+    dz = torch.empty_like(dy)
+    check(_lib.load().murcl_relu_bwd(_p(dy), _p(y), _p(dz), dy.numel(), _dt(dy), _s()), "murcl_relu_bwd")
+    return dz
+
+
+def row_segments(offsets: torch.Tensor, n_rows: int) -> torch.Tensor:
+    _chk(offsets, "row_segments.offsets", torch.int64)
+    seg = torch.empty((n_rows,), device=offsets.device, dtype=torch.int32)
+    check(_lib.load().murcl_row_segments(_p(offsets), offsets.numel() - 1, _p(seg), _s()), "murcl_row_segments")
+    return seg
+
+
+def attn_score_fwd(uv, wc, bc, D, gated):
+    n = uv.shape[0]
+    s = torch.empty((n,), device=uv.device, dtype=torch.float32)
+    check(_lib.load().murcl_attn_score_fwd(_p(uv), _p(wc), _p(bc), _p(s), n, D, int(gated), _dt(uv), _s()),
+          "murcl_attn_score_fwd")
+    return s
+
+
+def seg_softmax(s, offsets, B, C, inv_sqrt_n):
+    _chk(s, "seg_softmax.s", torch.float32)
+    p = torch.empty_like(s)
+    stats = torch.empty((B, C, 2), device=s.device, dtype=torch.float32)
+    check(_lib.load().murcl_seg_softmax(_p(s), _p(offsets), B, C, int(inv_sqrt_n), _p(p), _p(stats), _s()),
+          "murcl_seg_softmax")
+    return p, stats
+
+
+def seg_wsum(p, h, offsets, B, C):
+    _chk(p, "seg_wsum.p", torch.float32); _chk(h, "seg_wsum.h")
+    n_rows, L = h.shape
+    lib = _lib.load()
+    out = torch.empty((B, C, L), device=h.device, dtype=torch.float32)
+    ws = torch.empty((max(int(lib.murcl_seg_wsum_workspace(n_rows, B, C, L)), 1),), device=h.device, dtype=torch.float32)
+    check(lib.murcl_seg_wsum(_p(p), _p(h), _p(offsets), n_rows, B, C, L, _dt(h), _p(out), _p(ws), _s()), "murcl_seg_wsum")
+    return out
+
+
+def pool_bwd_scores(p, h, dM, M, offsets, row_seg, B, C, inv_sqrt_n):
+    n_rows, L = h.shape
+    _chk(dM, "pool_bwd_scores.dM", torch.float32); _chk(M, "pool_bwd_scores.M", torch.float32)
+    ds = torch.empty((n_rows, C) if C > 1 else (n_rows,), device=h.device, dtype=torch.float32)
+    kbuf = torch.empty((B * C,), device=h.device, dtype=torch.float32)
+    check(_lib.load().murcl_pool_bwd_scores(_p(p), _p(h), _p(dM), _p(M), _p(offsets), _p(row_seg), n_rows, B, C, L,
+                                            int(inv_sqrt_n), _dt(h), _p(ds), _p(kbuf), _s()), "murcl_pool_bwd_scores")
+    return ds
+
+
+def pool_bwd_direct(p, dM, row_seg, C, L, out, accumulate):
+    n_rows = out.shape[0]
+    check(_lib.load().murcl_pool_bwd_direct(_p(p), _p(dM), _p(row_seg), n_rows, C, L, _dt(out), _p(out), int(accumulate),
+                                            _s()), "murcl_pool_bwd_direct")
+    return out
+
+
+def attn_score_bwd_(uv, wc, ds, D, gated):
+    """In place: uv becomes the gradient w.r.t. the pre-activations.  Returns (dwc [D], dbc [1])."""
+    dwc = torch.zeros((D,), device=uv.device, dtype=torch.float32)
+    dbc = torch.zeros((1,), device=uv.device, dtype=torch.float32)
+    check(_lib.load().murcl_attn_score_bwd(_p(uv), _p(wc), _p(ds), _p(dwc), _p(dbc), uv.shape[0], D, int(gated), _dt(uv),
+                                           _s()), "murcl_attn_score_bwd")
+    return dwc, dbc
+
+
+def seg_topk_ends(p, offsets, B, k):
+    top = torch.empty((B, k), device=p.device, dtype=torch.int32)
+    bot = torch.empty((B, k), device=p.device, dtype=torch.int32)
+    check(_lib.load().murcl_seg_topk_ends(_p(p), _p(offsets), B, k, _p(top), _p(bot), _s()), "murcl_seg_topk_ends")
+    return top, bot
+
+
+def seg_argmax(c, offsets, B, C):
+    idx = torch.empty((B, C), device=c.device, dtype=torch.int32)
+    check(_lib.load().murcl_seg_argmax(_p(c), _p(offsets), B, C, _p(idx), _s()), "murcl_seg_argmax")
+    return idx
+
+
+def gather_rows(h, idx):
+    _chk(idx, "gather_rows.idx", torch.int32)
+    out = torch.empty((idx.numel(), h.shape[1]), device=h.device, dtype=torch.float32)
+    check(_lib.load().murcl_gather_rows(_p(h), _p(idx), idx.numel(), h.shape[1], _dt(h), _p(out), _s()), "murcl_gather_rows")
+    return out
+
+
+def scatter_add_rows_(dh, idx, rows):
+    _chk(rows, "scatter_add_rows.rows", torch.float32)
+    check(_lib.load().murcl_scatter_add_rows(_p(dh), _p(idx), idx.numel(), dh.shape[1], _dt(dh), _p(rows), _s()),
+          "murcl_scatter_add_rows")
+    return dh
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: small dense heads (fp32 storage; decoder, GRU gates, actor MLP, classifier heads)
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """y = act(x w^T + b).  Operands are stored in ``dtype`` for the GEMMs (fp32 or bf16); y is fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, dtype):
+        xs = cast(x.detach().contiguous(), dtype)
+        ws = weight_as(w, dtype)
+        bs = None if b is None else b.detach().contiguous().float()
+        y = linear_fwd(xs, ws, bs, act, torch.float32)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.dtype = dtype
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(xs, ws, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, ws, y = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        if ctx.act == ACT_RELU:
+            dz = relu_bwd(dy, y)
+        elif ctx.act == ACT_TANH:
+            dz = dy * (1 - y * y)
+        elif ctx.act == ACT_SIGMOID:
+            dz = dy * y * (1 - y)
+        else:
+            dz = dy
+        dz = cast(dz.contiguous(), ctx.dtype)
+        dx = linear_bwd_input(dz, ws).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = linear_bwd_weight(dz, xs, want_bias=ctx.has_bias)
+        return dx, dw, db, None, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+           dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """act(x @ w.T + b) on libmurcl_b200 kernels, differentiable; x [M,K] CUDA, result fp32."""
+    if not x.is_cuda:
+        raise MurclError("linear: expected a CUDA tensor (libmurcl_b200 has no CPU path)")
+    return _Linear.apply(x, w, b, act, dtype)
+
+
+class _GRUCell(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gi, gh, h_prev):
+        gi, gh, h_prev = gi.contiguous(), gh.contiguous(), h_prev.contiguous()
+        B, H = h_prev.shape
+        h_new = torch.empty_like(h_prev)
+        gates = torch.empty_like(gi)
+        check(_lib.load().murcl_gru_cell_fwd(_p(gi), _p(gh), _p(h_prev), _p(h_new), _p(gates), B, H, _s()),
+              "murcl_gru_cell_fwd")
+        ctx.save_for_backward(gates, gh, h_prev)
+        return h_new
+
+    @staticmethod
+    def backward(ctx, dh_new):
+        gates, gh, h_prev = ctx.saved_tensors
+        B, H = h_prev.shape
+        dh_new = dh_new.contiguous()
+        dgi, dgh, dh_prev = torch.empty_like(gates), torch.empty_like(gates), torch.empty_like(h_prev)
+        check(_lib.load().murcl_gru_cell_bwd(_p(dh_new), _p(gates), _p(gh), _p(h_prev), _p(dgi), _p(dgh), _p(dh_prev), B, H,
+                                             _s()), "murcl_gru_cell_bwd")
+        return dgi, dgh, dh_prev
+
+
+def gru_step(x, h_prev, w_ih, w_hh, b_ih, b_hh):
+    """One nn.GRU time step (gate order r,z,n) built from two dense layers and the fused cell kernel."""
+    gi = linear(x, w_ih, b_ih)
+    gh = linear(h_prev, w_hh, b_hh)
+    return _GRUCell.apply(gi, gh, h_prev)
+
+
+def actor_head(logits, eps, std):
+    logits, eps = _chk(logits.contiguous(), "actor_head.logits", torch.float32), _chk(eps.contiguous(), "actor_head.eps", torch.float32)
+    B, K = logits.shape
+    action, mean = torch.empty_like(logits), torch.empty_like(logits)
+    logprob = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    check(_lib.load().murcl_actor_head(_p(logits), _p(eps), float(std), _p(action), _p(logprob), _p(mean), B, K, _s()),
+          "murcl_actor_head")
+    return action, logprob, mean
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: NT-Xent
+# ------------------------------------------------------------------------------------------------
+def ntxent_raw(z: torch.Tensor, B: int, temperature: float, want_grad=True):
+    _chk(z, "ntxent.z", torch.float32)
+    R, d = z.shape
+    loss = torch.empty((1,), device=z.device, dtype=torch.float32)
+    dz = torch.empty_like(z) if want_grad else None
+    cos = torch.empty((B,), device=z.device, dtype=torch.float32)
+    ws = torch.empty((R * d + 4 * R,), device=z.device, dtype=torch.float32)
+    check(_lib.load().murcl_ntxent_fwd_bwd(_p(z), B, d, float(temperature), _p(loss), _p(dz), _p(cos), _p(ws), _s()),
+          "murcl_ntxent_fwd_bwd")
+    return loss, dz, cos
+
+
+class _NTXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_i, z_j, temperature):
+        B = z_i.shape[0]
+        z = torch.cat([z_i.detach(), z_j.detach()], 0).float().contiguous()
+        loss, dz, cos = ntxent_raw(z, B, temperature, True)
+        ctx.save_for_backward(dz)
+        ctx.B = B
+        ctx.mark_non_differentiable(cos)
+        return loss.reshape(()), cos
+
+    @staticmethod
+    def backward(ctx, g, _gcos):
+        (dz,) = ctx.saved_tensors
+        dz = dz * g
+        return dz[: ctx.B], dz[ctx.B:], None
+
+
+def ntxent(z_i, z_j, temperature):
+    """(loss, cos_pair): fused NT-Xent forward+gradient; cos_pair[b] = cos(z_i[b], z_j[b]) (the reward signal)."""
+    if not z_i.is_cuda:
+        raise MurclError("ntxent: expected CUDA tensors (libmurcl_b200 has no CPU path)")
+    return _NTXent.apply(z_i, z_j, temperature)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: the MIL aggregator (encoder -> attention -> segmented softmax pooling)
+# ------------------------------------------------------------------------------------------------
+class _MILAggregate(torch.autograd.Function):
+    """x [n_rows, D_in] (CSR rows of all bags) -> M [B, L].
+
+    args: x, offsets, row_seg, meta, wab, bab, wc, bc, inst_w, inst_b, *enc (w0, b0, w1, b1, ...)
+    meta: dict(B, gated, inv_sqrt_n, dtype, inst=None | dict(groups...))
+    Also returns p [n_rows] (attention weights incl. post-scale), raw scores s, inst loss per group.
+    """
+
+    @staticmethod
+    def forward(ctx, x, offsets, row_seg, meta, wab, bab, wc, bc, inst_w, inst_b, *enc):
+        dt = meta["dtype"]
+        B, gated = meta["B"], meta["gated"]
+        D = wc.numel()
+        hs = [cast(x.detach().contiguous(), dt)]
+        enc_w = []
+        for i in range(0, len(enc), 2):
+            w = weight_as(enc[i], dt)
+            enc_w.append(w)
+            hs.append(linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU))
+        H = hs[-1]
+        wab_s = weight_as(wab, dt)
+        uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
+        wc_f = wc.detach().reshape(-1).contiguous().float()
+        bc_f = bc.detach().reshape(-1).contiguous().float()
+        s = attn_score_fwd(uv, wc_f, bc_f, D, gated)
+        p, _ = seg_softmax(s, offsets, B, 1, meta["inv_sqrt_n"])
+        M = seg_wsum(p, H, offsets, B, 1).reshape(B, -1)
+        inst = meta.get("inst")
+        inst_loss = s.new_zeros((0,))
+        preds = s.new_zeros((0,), dtype=torch.int32)
+        saved_inst = ()
+        if inst is not None:
+            k = inst["k"]
+            top, bot = seg_topk_ends(p, offsets, B, k)
+            # per-group row index lists; layout decided on the host (tiny), data stays on device
+            both = torch.cat([top, bot], 1)                                   # [B, 2k]
+            idx_parts = [(both if in_cls else top)[b] for (b, _c, in_cls) in inst["groups"]]
+            idx = torch.cat(idx_parts).contiguous()
+            rows = gather_rows(H, idx)
+            G = len(inst["groups"])
+            inst_loss = torch.empty((G,), device=x.device, dtype=torch.float32)
+            preds = torch.empty((idx.numel(),), device=x.device, dtype=torch.int32)
+            dlogits = torch.empty((idx.numel(), 2), device=x.device, dtype=torch.float32)
+            iw = inst_w.detach().contiguous().float()
+            ib = inst_b.detach().contiguous().float()
+            check(_lib.load().murcl_clam_inst_ce_fwd(_p(rows), _p(inst["targets"]), _p(inst["group_off"]), _p(inst["group_cls"]),
+                                                     G, _p(iw), _p(ib), rows.shape[1], _p(inst_loss), _p(preds), _p(dlogits),
+                                                     _s()), "murcl_clam_inst_ce_fwd")
+            saved_inst = (idx, rows, dlogits, iw)
+        ctx.meta = meta
+        ctx.n_enc = len(enc) // 2
+        ctx.D = D
+        ctx.consumed = False
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(offsets, row_seg, wab_s, wc_f, uv, p, M, *hs, *enc_w, *saved_inst)
+        ctx.mark_non_differentiable(p, s, preds)
+        return M, p, s, inst_loss, preds
+
+    @staticmethod
+    def backward(ctx, dM, _dp, _ds, dinst, _dpreds):
+        if ctx.consumed:
+            raise MurclError("MIL aggregate: backward called twice (saved activations are consumed in place)")
+        ctx.consumed = True
+        meta = ctx.meta
+        B, gated, D, n_enc = meta["B"], meta["gated"], ctx.D, ctx.n_enc
+        sv = ctx.saved_tensors
+        offsets, row_seg, wab_s, wc_f, uv, p, M = sv[:7]
+        hs = sv[7:7 + n_enc + 1]
+        enc_w = sv[7 + n_enc + 1:7 + 2 * n_enc + 1]
+        rest = sv[7 + 2 * n_enc + 1:]
+        H = hs[-1]
+        L = H.shape[1]
+        dM = dM.contiguous().float()
+        ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, meta["inv_sqrt_n"])
+        dwc, dbc = attn_score_bwd_(uv, wc_f, ds, D, gated)          # uv now holds d(pre-activation)
+        dwab, dbab = linear_bwd_weight(uv, H)
+        relu_src = H if n_enc > 0 else None
+        dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg)     # + p_n dM[b] direct term, ReLU mask
+        d_inst_w = d_inst_b = None
+        inst = meta.get("inst")
+        if inst is not None:
+            idx, rows, dlogits, iw = rest
+            G = len(inst["groups"])
+            drows = torch.empty_like(rows)
+            d_inst_w = torch.zeros_like(iw)
+            d_inst_b = torch.zeros((iw.shape[0], 2), device=iw.device, dtype=torch.float32)
+            gl = dinst.contiguous().float()
+            check(_lib.load().murcl_clam_inst_ce_bwd(_p(rows), _p(dlogits), _p(gl), _p(inst["group_off"]), _p(inst["group_cls"]),
+                                                     G, _p(iw), L, _p(drows), _p(d_inst_w), _p(d_inst_b), _s()),
+                  "murcl_clam_inst_ce_bwd")
+            if n_enc > 0:
+                drows = drows * (rows > 0)                              # same ReLU mask as the fused epilogue
+            scatter_add_rows_(dz, idx, drows.contiguous())
+        grads_enc = []
+        for l in range(n_enc, 0, -1):
+            dw, db = linear_bwd_weight(dz, hs[l - 1])
+            grads_enc = [dw, db] + grads_enc
+            if l > 1:
+                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1])
+            elif ctx.needs_input_grad[0]:
+                dz = linear_bwd_input(dz, enc_w[0])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = dz.to(ctx.x_dtype)
+        return (dx, None, None, None, dwab, dbab, dwc.reshape(1, -1), dbc, d_inst_w, d_inst_b, *grads_enc)
+
+
+@torch.no_grad()
+def mil_attention_scores(x, meta, wab, bab, wc, bc, enc_params):
+    """Raw (pre-softmax) attention scores [n_rows] of every instance: CLAM's ``attention_only`` path
+    (clam.py:141-142) used by the heat-map script.  Not differentiable."""
+    if not x.is_cuda:
+        raise MurclError("mil_attention_scores: expected CUDA tensors (libmurcl_b200 has no CPU path)")
+    dt = meta["dtype"]
+    h = cast(x.detach().contiguous(), dt)
+    for i in range(0, len(enc_params), 2):
+        h = linear_fwd(h, weight_as(enc_params[i], dt), enc_params[i + 1].detach().contiguous(), ACT_RELU)
+    uv = linear_fwd(h, weight_as(wab, dt), bab.detach().contiguous(), ACT_TANH_SIGMOID if meta["gated"] else ACT_TANH)
+    return attn_score_fwd(uv, wc.detach().reshape(-1).contiguous().float(), bc.detach().reshape(-1).contiguous().float(),
+                          wc.numel(), meta["gated"])
+
+
+def mil_aggregate(x, offsets, row_seg, meta, wab, bab, wc, bc, inst_w, inst_b, enc_params):
+    if not x.is_cuda:
+        raise MurclError("mil_aggregate: expected CUDA tensors (libmurcl_b200 has no CPU path)")
+    return _MILAggregate.apply(x, offsets, row_seg, meta, wab, bab, wc, bc, inst_w, inst_b, *enc_params)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: DSMIL critical-instance attention
+# ------------------------------------------------------------------------------------------------
+class _DSMILAggregate(torch.autograd.Function):
+    """BClassifier (dsmil.py:64-81): x [n_rows, D], instance scores c [n_rows, C] (used for the arg-max
+    only) -> bag [B, C, D] fp32.  V is applied AFTER pooling: A^T (X Wv^T + bv) = (A^T X) Wv^T + bv because
+    every softmax column sums to 1, which removes 89% of the reference's FLOPs."""
+
+    @staticmethod
+    def forward(ctx, x, classes, offsets, row_seg, meta, wq, bq, wv, bv):
+        dt, B = meta["dtype"], meta["B"]
+        xs = cast(x.detach().contiguous(), dt)
+        classes = classes.detach().contiguous().float()
+        C = classes.shape[1]
+        wq_s = weight_as(wq, dt)
+        crit = seg_argmax(classes, offsets, B, C)
+        q = linear_fwd(xs, wq_s, bq.detach().contiguous().float(), ACT_NONE, torch.float32)
+        n_rows, Dq = q.shape
+        a = torch.empty((n_rows, C), device=x.device, dtype=torch.float32)
+        check(_lib.load().murcl_dsmil_scores_fwd(_p(q), _p(crit), _p(row_seg), n_rows, C, Dq, _p(a), _s()),
+              "murcl_dsmil_scores_fwd")
+        p, _ = seg_softmax(a, offsets, B, C, False)
+        mx = seg_wsum(p, xs, offsets, B, C)                               # [B, C, D]
+        wv_f = wv.detach().contiguous().float()
+        bag = linear_fwd(mx.reshape(B * C, -1), wv_f, bv.detach().contiguous().float(), ACT_NONE).reshape(B, C, -1)
+        ctx.meta = meta
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(offsets, row_seg, xs, wq_s, wv_f, q, crit, p, mx)
+        return bag
+
+    @staticmethod
+    def backward(ctx, dbag):
+        meta = ctx.meta
+        dt, B = meta["dtype"], meta["B"]
+        offsets, row_seg, xs, wq_s, wv_f, q, crit, p, mx = ctx.saved_tensors
+        n_rows, D = xs.shape
+        C, Dq = p.shape[1], q.shape[1]
+        dbag2 = dbag.contiguous().float().reshape(B * C, D)
+        dmx = linear_bwd_input(dbag2, wv_f).reshape(B, C, D)
+        dwv, dbv = linear_bwd_weight(dbag2, mx.reshape(B * C, D))
+        da = pool_bwd_scores(p, xs, dmx, mx, offsets, row_seg, B, C, False).reshape(n_rows, C)
+        dq = torch.empty_like(q)
+        check(_lib.load().murcl_dsmil_scores_bwd(_p(q), _p(da), _p(crit), _p(row_seg), _p(offsets), n_rows, B, C, Dq, _p(dq),
+                                                 _s()), "murcl_dsmil_scores_bwd")
+        dq_s = cast(dq, dt)
+        dwq, dbq = linear_bwd_weight(dq_s, xs)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_bwd_input(dq_s, wq_s)
+            pool_bwd_direct(p, dmx.contiguous(), row_seg, C, D, dx, True)
+            dx = dx.to(ctx.x_dtype)
+        return dx, None, None, None, None, dwq, dbq, dwv, dbv
+
+
+def dsmil_aggregate(x, classes, offsets, row_seg, meta, wq, bq, wv, bv):
+    if not x.is_cuda:
+        raise MurclError("dsmil_aggregate: expected CUDA tensors (libmurcl_b200 has no CPU path)")
+    return _DSMILAggregate.apply(x, classes, offsets, row_seg, meta, wq, bq, wv, bv)

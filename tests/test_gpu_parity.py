@@ -1,0 +1,491 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances are the north-star's: indices / gathers bit-exact; fp32 mode 1e-5 relative on attention
+weights, bag vectors and losses (gradients 1e-4, they sum thousands of fp32 terms in a different order);
+bf16 mode 2e-2 relative.  Run with ``pytest -m gpu`` on a B200.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from murcl_b200 import synth
+from oracle import murcl_oracle as O
+from tests.helpers import assert_close, leaf_state, sample
+
+pytestmark = pytest.mark.gpu
+
+FP32_OUT, FP32_GRAD = 1e-5, 1e-4
+BF16_OUT, BF16_GRAD = 2e-2, 6e-2
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    from murcl_b200 import _lib
+    _lib.load()
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _load(module, sd):
+    module.load_state_dict(sd, strict=True)
+    return module.to(DEV)
+
+
+def _grads(module):
+    return {n: p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(p).cpu() for n, p in module.named_parameters()}
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) packer
+# ------------------------------------------------------------------------------------------------
+def test_get_feats_golden(golden):
+    from murcl_b200.dropin import datasets
+    g = golden("get_feats")
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), int(g["d"]), int(g["k"]), seed=int(g["seed_bags"]))
+    b, src, dst = g["merged_cluster"].tolist()
+    clusters[b][src] = sorted(clusters[b][src] + clusters[b][dst])
+    clusters[b][dst] = []
+    feat_list = [f.unsqueeze(0).to(DEV) for f in feats]
+    out = datasets.get_feats(feat_list, clusters, torch.from_numpy(g["actions"]).to(DEV), feat_size=int(g["fs"]))
+    assert out.shape == g["out"].shape
+    assert np.array_equal(out.cpu().numpy(), g["out"])
+
+
+@pytest.mark.parametrize("fs,k,d", [(64, 5, 8), (1024, 10, 512), (100, 3, 20)])
+def test_get_feats_random(fs, k, d):
+    from murcl_b200.csr import BagStore
+    sizes = [3 * fs, fs // 2, fs, fs + 3, 7, 2 * fs + 1, 5000]
+    feats, clusters, labels = synth.make_bags(sizes, d, k, seed=5)
+    g = synth.gen(6)
+    actions = torch.rand(len(sizes), k, generator=g)
+    actions[0, 0], actions[1, 1], actions[2, 0], actions[3, 2] = 0.0, 1.0, 1.0, 0.0
+    want, kept = O.get_feats(feats, clusters, actions, fs)
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    sel_idx, sel_cnt = store.select(actions.to(DEV), fs)
+    out = store.gather(sel_idx)
+    assert torch.equal(out.cpu(), want)
+    assert sel_cnt.cpu().tolist() == [len(x) for x in kept]
+    offs = store.offsets_host
+    for b, idx in enumerate(kept):
+        got = sel_idx[b, : len(idx)].cpu().numpy().astype(np.int64) - offs[b]
+        assert np.array_equal(got, idx)
+        assert bool((sel_idx[b, len(idx):] == -1).all())
+    # the on-disk ingest path (per-patch labels -> ranks on the device) builds the same store
+    store2 = BagStore.from_labels(feats, labels, k, DEV)
+    assert torch.equal(store2.patch_rank, store.patch_rank)
+    assert torch.equal(store2.cluster_sizes, store.cluster_sizes)
+    assert torch.equal(store2.pack(actions.to(DEV), fs).cpu(), want)
+    # bf16 output is the fp32 result rounded to nearest even
+    assert torch.equal(store.gather(sel_idx, out_dtype=torch.bfloat16).cpu(), want.to(torch.bfloat16))
+
+
+def test_selection_sweep_on_device(golden):
+    """The brute-force selection fixture, one single-cluster bag per case."""
+    from murcl_b200.csr import BagStore
+    g = golden("selection_sweep")
+    cases, acts = g["cases"][:1500], g["actions"][:1500]
+    for fs in sorted(set(cases[:, 0].tolist())):
+        sel = np.nonzero(cases[:, 0] == fs)[0]
+        feats, clusters = [], []
+        for i in sel:
+            n = cases[i][2]
+            feats.append(torch.zeros(int(cases[i][1]), 1))
+            clusters.append([list(range(int(n)))])
+        store = BagStore.from_cluster_lists(feats, clusters, DEV)
+        a = torch.from_numpy(acts[sel]).reshape(-1, 1).to(DEV)
+        sel_idx, sel_cnt = store.select(a, int(fs))
+        cnt = sel_cnt.cpu().numpy()
+        first = sel_idx[:, 0].cpu().numpy()
+        for j, i in enumerate(sel):
+            want_cnt = min(int(cases[i][4]), int(fs))
+            assert cnt[j] == want_cnt, cases[i]
+            if want_cnt:
+                assert first[j] - store.offsets_host[j] == cases[i][3], cases[i]
+
+
+def test_mixup_bit_exact(golden):
+    from murcl_b200.dropin import datasets
+    x = torch.randn(6, 40, 24, generator=synth.gen(3)).to(DEV)
+    torch.manual_seed(11)
+    out, lam, perm = datasets.mixup(x, 0.9)
+    want = O.mixup_apply(x.cpu(), lam.cpu(), perm.cpu())
+    assert torch.equal(out.cpu(), want)
+    assert float(lam.min()) >= 0.9 and float(lam.max()) < 1.0
+    assert sorted(perm.cpu().tolist()) == list(range(6))
+    # fused select + gather + mixup == get_feats then mixup
+    from murcl_b200.csr import BagStore
+    feats, clusters, _ = synth.make_bags([300, 90, 64, 200], 16, 4, seed=8)
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    actions = torch.rand(4, 4, generator=synth.gen(9))
+    lam = 0.9 + 0.1 * torch.rand(4, 1, generator=synth.gen(10))
+    perm = torch.randperm(4, generator=synth.gen(12))
+    fused = store.pack(actions.to(DEV), 64, lam.to(DEV), perm.to(DEV))
+    dense, _ = O.get_feats(feats, clusters, actions, 64)
+    assert torch.equal(fused.cpu(), O.mixup_apply(dense, lam, perm))
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(300, 64, 48), (1000, 512, 512), (129, 130, 70), (5, 2, 1024), (2048, 128, 512)])
+def test_linear_simt(M, N, K):
+    from murcl_b200 import ops
+    g = synth.gen(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    mask_src = torch.randn(M, K, generator=g)
+    y_ref = torch.relu(x.double() @ w.double().t() + b.double())
+    xd, wd, bd, dyd = x.to(DEV), w.to(DEV), b.to(DEV), dy.to(DEV)
+    os.environ["MURCL_GEMM"] = "simt"
+    try:
+        y = ops.linear_fwd(xd, wd, bd, ops.ACT_RELU)
+        assert_close(y, y_ref.float(), 2e-6, "fwd")
+        dx = ops.linear_bwd_input(dyd, wd, mask_src.to(DEV))
+        dx_ref = (dy.double() @ w.double()) * (mask_src > 0)
+        assert_close(dx, dx_ref.float(), 2e-6, "bwd_input")
+        dw, db = ops.linear_bwd_weight(dyd, xd)
+        assert_close(dw, (dy.double().t() @ x.double()).float(), 5e-6, "bwd_weight")
+        assert_close(db, dy.double().sum(0).float(), 5e-6, "bias grad")
+        # bf16 storage through the same kernels (fp32 accumulate)
+        xb, wb = xd.bfloat16(), wd.bfloat16()
+        yb = ops.linear_fwd(xb, wb, bd, ops.ACT_NONE, torch.float32)
+        ref = xb.float().double().cpu() @ wb.float().double().cpu().t() + b.double()
+        assert_close(yb, ref.float(), 2e-6, "bf16 storage fwd")
+    finally:
+        os.environ.pop("MURCL_GEMM", None)
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) ABMIL / CLAM_SB
+# ------------------------------------------------------------------------------------------------
+def test_abmil_golden_small(golden):
+    from murcl_b200.dropin import abmil
+    g = golden("abmil_small")
+    dim_in, L, D = g["dims"].tolist()
+    m = _load(abmil.ABMIL(dim_in, L=L, D=D, dim_out=2, precision="fp32"), synth.abmil_state(dim_in, L, D, 2, seed=31))
+    feats, _, _ = synth.make_bags(g["sizes"].tolist(), dim_in, 3, seed=32)
+    bags = [f.to(DEV).requires_grad_(True) for f in feats]
+    out, det = m(bags)
+    assert not det.requires_grad
+    assert_close(out, g["out"], FP32_OUT, "out")
+    (out * torch.from_numpy(g["cot"]).to(DEV)).sum().backward()
+    gr = _grads(m)
+    for k, v in g.items():
+        if k.startswith("grad."):
+            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-4)
+    for i, b in enumerate(bags):
+        assert_close(b.grad, g[f"grad_input.{i}"], FP32_GRAD, f"dx{i}")
+    with torch.no_grad():
+        xb = torch.stack([feats[0][:40], feats[1][:40]]).to(DEV)
+        assert_close(m(xb)[0], g["out_dense"], FP32_OUT, "dense batch")
+        assert_close(m(feats[0].unsqueeze(0).to(DEV))[0], g["out_single"], FP32_OUT, "single")
+    with pytest.raises(TypeError):
+        m("not a tensor")
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", FP32_OUT, FP32_GRAD), ("bf16", BF16_OUT, BF16_GRAD)])
+def test_abmil_full_size(golden, precision, tol_out, tol_grad):
+    """Camelyon16-shaped: D_in=512, L=512, D=128; ragged bags incl. cfg1's N~2000."""
+    from murcl_b200.dropin import abmil
+    sd = synth.abmil_state(512, 512, 128, 2, seed=31)
+    m = _load(abmil.ABMIL(512, precision=precision), sd)
+    if precision == "fp32":
+        g = golden("abmil_full")
+        feats, _, _ = synth.make_bags(g["sizes"].tolist(), 512, 3, seed=32)
+        with torch.no_grad():
+            assert_close(m([f.to(DEV) for f in feats])[0], g["out"], tol_out, "golden full")
+    feats, _, _ = synth.make_bags([2000, 333, 1024], 512, 3, seed=77)
+    sdl = leaf_state(sd)
+    want = O.abmil_forward(feats, sdl)
+    cot = torch.randn(want.shape, generator=synth.gen(78))
+    (want * cot).sum().backward()
+    out, _ = m([f.to(DEV) for f in feats])
+    assert_close(out, want, tol_out, "out")
+    (out * cot.to(DEV)).sum().backward()
+    gr = _grads(m)
+    for k, p in sdl.items():
+        if k.startswith("fc."):
+            continue
+        assert_close(gr[k], p.grad, tol_grad, k, floor=1e-4 if "attention.2.bias" in k else 1e-7)
+
+
+@pytest.mark.parametrize("gate", [True, False])
+@pytest.mark.parametrize("dropout", [False, True])
+@pytest.mark.parametrize("subtyping", [False, True])
+def test_clam_golden(golden, gate, dropout, subtyping):
+    from murcl_b200.dropin import clam
+    g = golden(f"clam_g{int(gate)}_d{int(dropout)}_s{int(subtyping)}")
+    in_dim, n_classes = int(g["in_dim"]), int(g["n_classes"])
+    m = clam.CLAM_SB(gate=gate, size_arg="small", dropout=dropout, k_sample=8, n_classes=n_classes, subtyping=subtyping,
+                     in_dim=in_dim, precision="fp32")
+    m = _load(m, synth.clam_state(in_dim, "small", gate, dropout, n_classes, seed=41)).eval()
+    feats, _, _ = synth.make_bags(g["sizes"].tolist(), in_dim, 3, seed=42)
+    labels = g["labels"].tolist()
+    tot = 0.0
+    x0 = feats[0].to(DEV).requires_grad_(True)
+    for i, f in enumerate(feats):
+        x = x0 if i == 0 else f.to(DEV)
+        out, det, res = m(x.unsqueeze(0), label=torch.tensor([labels[i]]), instance_eval=True)
+        assert isinstance(res, dict)
+        assert_close(out, g[f"out{i}"], FP32_OUT, f"M{i}")
+        assert_close(res["instance_loss"], g[f"inst_loss{i}"], FP32_OUT, f"inst{i}")
+        assert np.array_equal(res["inst_labels"], g[f"inst_labels{i}"])
+        assert np.array_equal(res["inst_preds"], g[f"inst_preds{i}"])
+        raw = m.bag_forward(f.to(DEV), attention_only=True)
+        assert_close(raw, g[f"raw_scores{i}"], FP32_OUT, f"raw{i}")
+        tot = tot + (out * torch.from_numpy(g[f"cot{i}"]).to(DEV)).sum() + 0.3 * res["instance_loss"]
+    tot.backward()
+    gr = _grads(m)
+    for k, v in g.items():
+        if k.startswith("grad."):
+            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-4)
+    assert_close(x0.grad, g["grad_input.0"], FP32_GRAD, "dx0")
+    with torch.no_grad():
+        outs, det = m([f.to(DEV) for f in feats])
+        assert_close(outs, g["out_list"], FP32_OUT, "list batch")
+        # batch + instance_eval returns a LIST of dicts (clam.py:183-195)
+        o3 = m([f.to(DEV) for f in feats], label=torch.tensor(labels), instance_eval=True)
+        assert isinstance(o3[2], list) and len(o3[2]) == len(feats)
+        for i in range(len(feats)):
+            assert_close(o3[2][i]["instance_loss"], g[f"inst_loss{i}"], FP32_OUT, f"batched inst{i}")
+
+
+def test_clam_big_and_errors(golden):
+    from murcl_b200.dropin import clam
+    g = golden("clam_big")
+    m = _load(clam.CLAM_SB(gate=True, size_arg="big", in_dim=int(g["in_dim"]), precision="fp32"),
+              synth.clam_state(int(g["in_dim"]), "big", True, False, 2, seed=44)).eval()
+    feats, _, _ = synth.make_bags([60, 33, 100], int(g["in_dim"]), 3, seed=42)
+    with torch.no_grad():
+        assert_close(m(feats[0].unsqueeze(0).to(DEV))[0], g["out"], FP32_OUT, "big")
+    with pytest.raises(RuntimeError):       # fewer than k_sample instances: torch.topk raises upstream
+        m(feats[0][:5].unsqueeze(0).to(DEV), label=torch.tensor([1]), instance_eval=True)
+    with pytest.raises(TypeError):
+        m(3.0)
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", FP32_OUT, FP32_GRAD), ("bf16", BF16_OUT, BF16_GRAD)])
+def test_clam_ragged_cfg2(precision, tol_out, tol_grad):
+    """BASELINE config 2 shape: CLAM_SB small + instance loss on ragged bags x 512-d."""
+    from murcl_b200.dropin import clam
+    sd = synth.clam_state(512, "small", True, False, 2, seed=45)
+    m = _load(clam.CLAM_SB(gate=True, size_arg="small", k_sample=8, n_classes=2, subtyping=True, in_dim=512,
+                           precision=precision), sd).eval()
+    sizes = [2000, 3111, 5000]
+    feats, _, _ = synth.make_bags(sizes, 512, 3, seed=46)
+    labels = [1, 0, 1]
+    sdl = leaf_state(sd)
+    tot_ref, wants = 0.0, []
+    cots = [torch.randn(1, 512, generator=synth.gen(50 + i)) for i in range(3)]
+    for i, f in enumerate(feats):
+        mm, res = O.clam_sb_bag(f, sdl, gate=True, label=labels[i], instance_eval=True, n_classes=2, k_sample=8, subtyping=True)
+        wants.append((mm, res))
+        tot_ref = tot_ref + (mm * cots[i]).sum() + 0.3 * res["instance_loss"]
+    tot_ref.backward()
+    out, det, res = m([f.to(DEV) for f in feats], label=torch.tensor(labels), instance_eval=True)
+    tot = 0.0
+    for i in range(3):
+        assert_close(out[i:i + 1], wants[i][0], tol_out, f"M{i}")
+        if precision == "fp32":
+            assert_close(res[i]["instance_loss"], wants[i][1]["instance_loss"], tol_out, f"inst{i}")
+            assert np.array_equal(res[i]["inst_preds"], wants[i][1]["inst_preds"])
+        tot = tot + (out[i:i + 1] * cots[i].to(DEV)).sum() + 0.3 * res[i]["instance_loss"]
+    tot.backward()
+    if precision == "fp32":
+        gr = _grads(m)
+        for k, p in sdl.items():
+            if k.startswith("classifiers") or p.grad is None:
+                continue
+            assert_close(gr[k], p.grad, tol_grad, k, floor=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) DSMIL
+# ------------------------------------------------------------------------------------------------
+def test_dsmil_golden(golden):
+    from murcl_b200.dropin import dsmil
+    g = golden("dsmil")
+    dim, c = int(g["dim"]), int(g["c"])
+    m = dsmil.build_dsmil(dim, c, precision="fp32")
+    m.load_state_dict(synth.dsmil_state(dim, c, seed=51), strict=True)
+    feats, _, _ = synth.make_bags(g["sizes"].tolist(), dim, 3, seed=52)
+    tot, xs = 0.0, []
+    for i, f in enumerate(feats):
+        x = f.to(DEV).requires_grad_(True)
+        xs.append(x)
+        classes, bag, bag_det = m(x.unsqueeze(0))
+        assert_close(classes, g[f"classes{i}"], FP32_OUT, "classes")
+        assert_close(bag, g[f"bag{i}"], FP32_OUT, "bag")
+        tot = tot + (bag * torch.from_numpy(g[f"cot_b{i}"]).to(DEV)).sum() + (classes * torch.from_numpy(g[f"cot_c{i}"]).to(DEV)).sum()
+    tot.backward()
+    gr = _grads(m)
+    for k, v in g.items():
+        if k.startswith("grad."):
+            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-4)
+    for i, x in enumerate(xs):
+        assert_close(x.grad, g[f"grad_input.{i}"], FP32_GRAD, f"dx{i}")
+    # batch form: lists of per-bag outputs, bags concatenated (dsmil.py:26-36,83-91)
+    with torch.no_grad():
+        classes, bag, _ = m([f.unsqueeze(0).to(DEV) for f in feats])
+        assert isinstance(classes, list) and bag.shape == (2, c, dim)
+        assert_close(bag[1:2], g["bag1"], FP32_OUT, "batched bag")
+    with pytest.raises(TypeError):
+        m(1.0)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", BF16_OUT)])
+def test_dsmil_tcga_shape(precision, tol):
+    """BASELINE config 4 shape: N=10k x 1024-d (V applied after pooling: 1e-6-level reassociation)."""
+    from murcl_b200.dropin import dsmil
+    sd = synth.dsmil_state(1024, 2, seed=55)
+    m = dsmil.build_dsmil(1024, 2, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    feats, _, _ = synth.make_bags([10000], 1024, 3, seed=56)
+    with torch.no_grad():
+        want_c, want_b = O.dsmil_bag(feats[0], sd)
+        classes, bag, _ = m(feats[0].unsqueeze(0).to(DEV))
+    assert_close(classes, want_c, tol, "classes")
+    assert_close(bag, want_b, tol, "bag")
+
+
+# ------------------------------------------------------------------------------------------------
+# (4) NT-Xent
+# ------------------------------------------------------------------------------------------------
+def test_ntxent_golden(golden):
+    from murcl_b200.dropin import losses
+    g = golden("ntxent")
+    for i in range(3):
+        b, d, tau = g[f"cfg{i}"].tolist()
+        zi = torch.from_numpy(g[f"zi{i}"]).to(DEV).requires_grad_(True)
+        zj = torch.from_numpy(g[f"zj{i}"]).to(DEV).requires_grad_(True)
+        crit = losses.NT_Xent(int(b), tau)
+        loss = crit(zi, zj)
+        assert loss.dim() == 0
+        assert_close(loss, g[f"loss{i}"], FP32_OUT, "loss")
+        loss.backward()
+        assert_close(zi.grad, g[f"gzi{i}"], FP32_GRAD, "gzi")
+        assert_close(zj.grad, g[f"gzj{i}"], FP32_GRAD, "gzj")
+        assert_close(crit.last_cosine, g[f"cos{i}"], FP32_OUT, "cos")
+    same = torch.randn(1, 8, generator=synth.gen(69)).repeat(6, 1).to(DEV)
+    assert abs(float(losses.NT_Xent(6, 1.0)(same, same.clone())) - math.log(11.0)) < 1e-5
+    with pytest.raises(RuntimeError):
+        losses.NT_Xent(4, 1.0)(same, same)
+
+
+@pytest.mark.parametrize("B,d,tau", [(128, 128, 1.0), (128, 128, 0.07), (1024, 128, 0.5)])
+def test_ntxent_pretrain_shape(B, d, tau):
+    from murcl_b200 import ops
+    g = synth.gen(B + d)
+    zi = torch.randn(B, d, generator=g, dtype=torch.float64)
+    zj = 0.7 * zi + torch.randn(B, d, generator=g, dtype=torch.float64)
+    zi32, zj32 = zi.float().requires_grad_(True), zj.float().requires_grad_(True)
+    zi.requires_grad_(True); zj.requires_grad_(True)
+    want = O.nt_xent(zi, zj, tau)          # fp64 evaluation of the same formula
+    want.backward()
+    a, b = zi32.detach().to(DEV).requires_grad_(True), zj32.detach().to(DEV).requires_grad_(True)
+    loss, cos = ops.ntxent(a, b, tau)
+    loss.backward()
+    assert_close(loss, want.float(), FP32_OUT, "loss")
+    assert_close(a.grad, zi.grad.float(), FP32_GRAD, "gzi")
+    assert_close(b.grad, zj.grad.float(), FP32_GRAD, "gzj")
+
+
+# ------------------------------------------------------------------------------------------------
+# (5) heads
+# ------------------------------------------------------------------------------------------------
+def test_full_layer_golden(golden):
+    from murcl_b200.dropin import rlmil
+    g = golden("full_layer")
+    fnum, hid, cls, b = g["dims"].tolist()
+    m = _load(rlmil.Full_layer(fnum, hid, True, cls), synth.full_layer_state(fnum, hid, cls, seed=71))
+    tot, xs = 0.0, []
+    for t in range(3):
+        x = torch.from_numpy(g[f"x{t}"]).to(DEV).requires_grad_(True)
+        xs.append(x)
+        out = m(x, restart=(t == 0))
+        assert_close(out, g[f"out{t}"], FP32_OUT, f"out{t}")
+        tot = tot + (out * torch.from_numpy(g[f"cot{t}"]).to(DEV)).sum()
+    tot.backward()
+    gr = _grads(m)
+    for k, v in g.items():
+        if k.startswith("grad."):
+            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-4)
+    for t, x in enumerate(xs):
+        assert_close(x.grad, g[f"grad_input.{t}"], FP32_GRAD, f"dx{t}")
+
+
+def test_actor_golden(golden):
+    from murcl_b200.dropin import rlmil
+    g = golden("actor")
+    sdim, hid, k, b = g["dims"].tolist()
+    ppo = rlmil.PPO(sdim, sdim, hid, False, action_std=float(g["std"]), action_size=k)
+    ppo.policy_old.load_state_dict(synth.actor_state(sdim, hid, k, seed=81), strict=True)
+    mem = rlmil.Memory()
+    for t in range(3):
+        state = torch.from_numpy(g[f"state{t}"]).to(DEV)
+        action = ppo.policy_old.act(state, mem, restart_batch=(t == 0), training=True, eps=torch.from_numpy(g[f"eps{t}"]).to(DEV))
+        assert_close(action, g[f"action{t}"], FP32_OUT, "action")
+        assert_close(mem.logprobs[-1], g[f"logprob{t}"], FP32_OUT, "logprob")
+        assert_close(mem.hidden[-1][0], g[f"hidden{t}"], FP32_OUT, "hidden")
+    assert len(mem.states) == 3 and len(mem.actions) == 3
+    # PPO.update runs end to end on the kernels (rewards as train_MuRCL.py:283-288 stores them)
+    for _ in range(2):
+        mem.rewards.append(torch.randn(1, b, device=DEV))
+    mem.states, mem.actions, mem.logprobs = mem.states[:2], mem.actions[:2], mem.logprobs[:2]
+    before = ppo.policy.actor[0].weight.detach().clone()
+    ppo.update(mem)
+    assert not torch.equal(before, ppo.policy.actor[0].weight.detach())
+    assert torch.equal(ppo.policy.actor[0].weight, ppo.policy_old.actor[0].weight)
+
+
+# ------------------------------------------------------------------------------------------------
+# composition: one miniature pre-training step against the reference-generated fixture
+# ------------------------------------------------------------------------------------------------
+def _mini_step_draws(g_cfg, seed):
+    b, k = g_cfg[0], g_cfg[1]
+    gen = synth.gen(seed)
+    draws = []
+    for _ in range(g_cfg[4]):
+        acts = [torch.rand((b, k), generator=gen) for _ in range(2)]
+        lams, perms = [], []
+        for _ in range(2):
+            lams.append(0.9 + torch.rand(b, 1, generator=gen) * (1 - 0.9))
+            perms.append(torch.randperm(b, generator=gen))
+        draws.append((acts, lams, perms))
+    return draws
+
+
+def test_pretrain_step_golden(golden):
+    from murcl_b200 import pretrain
+    from murcl_b200.csr import BagStore
+    from murcl_b200.dropin import abmil, cl, losses, rlmil
+    g = golden("pretrain_step")
+    cfg = g["cfg"].tolist()
+    b, k, d, fs, T, L, D, hid, proj = cfg
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), d, k, seed=91)
+    enc = _load(abmil.ABMIL(d, L=L, D=D, dim_out=proj, precision="fp32"), synth.abmil_state(d, L, D, proj, seed=92))
+    model = cl.CL(enc, projection_dim=proj, n_features=L)
+    fc = _load(rlmil.Full_layer(L, hid, True, proj), synth.full_layer_state(L, hid, proj, seed=93))
+    crit = losses.NT_Xent(b, float(g["tau"]))
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    draws = [([a.to(DEV) for a in acts], [l.to(DEV) for l in lams], [p.to(DEV) for p in perms])
+             for acts, lams, perms in _mini_step_draws(cfg, 94)]
+    loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=float(g["alpha"]), draws=draws,
+                                     precision="fp32")
+    assert_close(loss, g["loss"], FP32_OUT, "loss")
+    gm, gf = _grads(enc), _grads(fc)
+    n = 0
+    for key, v in g.items():
+        if key.startswith("grad.m."):
+            assert_close(sample(gm[key[7:]].numpy()), v, 3e-4, key, floor=1e-5)
+            n += 1
+        elif key.startswith("grad.f."):
+            assert_close(sample(gf[key[7:]].numpy()), v, 3e-4, key, floor=1e-5)
+            n += 1
+    assert n >= 10

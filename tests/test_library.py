@@ -1,0 +1,104 @@
+"""CPU checks: the shared object builds/loads and exports every symbol the header declares; the drop-in
+modules keep the reference's state-dict layout; the product path refuses CPU tensors (no fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from murcl_b200 import _lib, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    hdr = (ROOT / "include" / "murcl_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(murcl_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_header_symbols():
+    from murcl_b200 import build
+    build.build()
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/murcl_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header drifted"
+    loaded = _lib.load()
+    assert loaded.murcl_version() == 1
+    assert loaded.murcl_launch_count() >= 0
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call, with a message."""
+    lib = _lib.load()
+    rc = lib.murcl_pack_gather(None, 8, None, 1, 4, None, None, None, 0, None)
+    assert rc == -1 and b"null" in lib.murcl_last_error()
+    rc = lib.murcl_linear_fwd(1, 1, None, 1, 4, 0, 4, 0, 0, 0, 0, None)
+    assert rc == -1
+    rc = lib.murcl_ntxent_fwd_bwd(1, 0, 4, 1.0, 1, None, None, 1, None)
+    assert rc == -1
+    with pytest.raises(_lib.MurclError):
+        _lib.check(rc, "murcl_ntxent_fwd_bwd")
+
+
+def test_state_dict_layout_matches_reference_names():
+    from murcl_b200.dropin import abmil, clam, dsmil, rlmil
+    abmil.ABMIL(24, L=32, D=16).load_state_dict(synth.abmil_state(24, 32, 16, 2), strict=True)
+    for gate in (True, False):
+        for dropout in (True, False):
+            m = clam.CLAM_SB(gate=gate, dropout=dropout, n_classes=3, in_dim=24)
+            m.load_state_dict(synth.clam_state(24, "small", gate, dropout, 3), strict=True)
+    clam.CLAM_SB(size_arg="big", in_dim=24).load_state_dict(synth.clam_state(24, "big"), strict=True)
+    net = dsmil.MILNet(dsmil.FCLayer(40, 2), dsmil.BClassifier(40, 2))
+    net.load_state_dict(synth.dsmil_state(40, 2), strict=True)
+    rlmil.Full_layer(24, 40, True, 12).load_state_dict(synth.full_layer_state(24, 40, 12), strict=True)
+    ac = rlmil.ActorCritic(32, 32, 24, False, 0.5, 6)
+    ac.load_state_dict(synth.actor_state(32, 24, 6), strict=True)
+
+
+def test_no_cpu_fallback():
+    from murcl_b200 import ops
+    from murcl_b200.dropin import abmil, clam, datasets, losses
+    with pytest.raises(_lib.MurclError):
+        abmil.ABMIL(16, L=16, D=8)(torch.randn(2, 5, 16))
+    with pytest.raises(_lib.MurclError):
+        clam.CLAM_SB(in_dim=16)(torch.randn(1, 20, 16))
+    with pytest.raises(_lib.MurclError):
+        losses.NT_Xent(2, 1.0)(torch.randn(2, 4), torch.randn(2, 4))
+    with pytest.raises(_lib.MurclError):
+        ops.linear(torch.randn(2, 4), torch.randn(3, 4))
+    with pytest.raises(_lib.MurclError):
+        datasets.get_feats([torch.randn(1, 9, 4)], [[[0, 1, 2], [3, 4, 5, 6, 7, 8]]], torch.rand(1, 2), 4)
+
+
+def test_product_does_not_import_oracle():
+    for path in (ROOT / "murcl_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_clam_instance_plan_layout():
+    """Host-side group layout of the instance loss (clam.py:146-166): label -> targets."""
+    from murcl_b200.dropin import clam
+
+    class R:
+        B = 2
+        sizes = [20, 30]
+
+        class rows:
+            device = "cpu"
+
+    m = clam.CLAM_SB(n_classes=2, subtyping=True, in_dim=16)
+    plan = m._instance_plan(R, [1, 0])
+    assert plan["targets"].tolist() == [0] * 8 + [1] * 8 + [0] * 8 + [1] * 8 + [0] * 8 + [0] * 8
+    assert plan["group_cls"].tolist() == [0, 1, 0, 1]
+    assert plan["groups"] == [(0, 0, False), (0, 1, True), (1, 0, True), (1, 1, False)]
+    m2 = clam.CLAM_SB(n_classes=2, subtyping=False, in_dim=16)
+    assert m2._instance_plan(R, [1, 0])["group_cls"].tolist() == [1, 0]
+    R.sizes = [5, 30]
+    with pytest.raises(RuntimeError):
+        m._instance_plan(R, [1, 0])
