@@ -90,6 +90,26 @@ class BagStore:
                                                  sizes.data_ptr(), _s()), "murcl_csr_rank_patches")
         return cls(feats, offsets, labels, rank, sizes, num_clusters)
 
+    @classmethod
+    def empty_like_host(cls, host: "HostBags", device=None):
+        """Device buffers sized for ``host`` (contents undefined until ``copy_from_host``)."""
+        device = torch.device(device) if device is not None else torch.device("cuda")
+        n_rows, d = host.feats.shape
+        return cls(torch.empty((n_rows, d), dtype=torch.float32, device=device), host.offsets,
+                   torch.empty((n_rows,), dtype=torch.int32, device=device),
+                   torch.empty((n_rows,), dtype=torch.int32, device=device),
+                   torch.empty(tuple(host.cluster_sizes.shape), dtype=torch.int32, device=device), host.K)
+
+    def copy_from_host(self, host: "HostBags") -> int:
+        """Asynchronous H2D of a whole batch from pinned memory on the current stream.  Returns bytes moved."""
+        if tuple(host.feats.shape) != tuple(self.feats.shape) or list(host.offsets) != self.offsets_host:
+            raise MurclError("copy_from_host: host batch does not match the device buffers")
+        self.feats.copy_(host.feats, non_blocking=True)
+        self.patch_cluster.copy_(host.patch_cluster, non_blocking=True)
+        self.patch_rank.copy_(host.patch_rank, non_blocking=True)
+        self.cluster_sizes.copy_(host.cluster_sizes, non_blocking=True)
+        return host.nbytes
+
     # -- properties -------------------------------------------------------------------------------
     @property
     def num_bags(self) -> int:
@@ -148,3 +168,36 @@ def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, per
                                         None if lam is None else lam.data_ptr(), None if perm is None else perm.data_ptr(),
                                         out.data_ptr(), code, _s()), "murcl_pack_gather")
     return out
+
+
+class HostBags:
+    """A batch of slides staged in PINNED host memory in the CSR layout (what a data loader hands over)."""
+
+    def __init__(self, feat_list, labels_list, num_clusters: int, pin: bool = True):
+        sizes = [int(f.shape[-2]) for f in feat_list]
+        d = int(feat_list[0].shape[-1])
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64).tolist()
+        n_rows = self.offsets[-1]
+        self.K = int(num_clusters)
+        self.feats = torch.empty((n_rows, d), dtype=torch.float32)
+        self.patch_cluster = torch.empty((n_rows,), dtype=torch.int32)
+        self.patch_rank = torch.empty((n_rows,), dtype=torch.int32)
+        self.cluster_sizes = torch.zeros((len(sizes), self.K), dtype=torch.int32)
+        for b, (f, l) in enumerate(zip(feat_list, labels_list)):
+            lo, hi = self.offsets[b], self.offsets[b + 1]
+            self.feats[lo:hi] = f.reshape(-1, d)
+            lab = torch.as_tensor(l).reshape(-1).to(torch.int64)
+            self.patch_cluster[lo:hi] = lab.to(torch.int32)
+            # rank of a patch inside its cluster = number of earlier patches with the same label
+            onehot = torch.nn.functional.one_hot(lab, self.K)
+            self.patch_rank[lo:hi] = ((onehot.cumsum(0) - 1) * onehot).sum(1).to(torch.int32)
+            self.cluster_sizes[b] = onehot.sum(0).to(torch.int32)
+        if pin and torch.cuda.is_available():
+            self.feats = self.feats.pin_memory()
+            self.patch_cluster = self.patch_cluster.pin_memory()
+            self.patch_rank = self.patch_rank.pin_memory()
+            self.cluster_sizes = self.cluster_sizes.pin_memory()
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.feats, self.patch_cluster, self.patch_rank, self.cluster_sizes))

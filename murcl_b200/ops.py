@@ -60,6 +60,35 @@ def _dt(t: torch.Tensor) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
+# optional per-launch timing of the dense layers (bench.py's roofline probe)
+# ------------------------------------------------------------------------------------------------
+_profile = None
+
+
+def set_profile(log):
+    """``log`` (a list) receives ``(family, flops, start_event, end_event)`` per dense-layer launch; None = off."""
+    global _profile
+    _profile = log
+
+
+class _Timed:
+    def __init__(self, family, flops):
+        self.family, self.flops = family, flops
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None:
+            self.e1.record()
+            _profile.append((self.family, self.flops, self.e0, self.e1))
+        return False
+
+
+# ------------------------------------------------------------------------------------------------
 # raw (non-differentiable) wrappers
 # ------------------------------------------------------------------------------------------------
 def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -100,8 +129,9 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
     y = torch.empty((M, N), device=x.device, dtype=out_dtype)
     if bias is not None:
         _chk(bias, "linear_fwd.bias", torch.float32)
-    check(_lib.load().murcl_linear_fwd(_p(x), _p(w), _p(bias), _p(y), M, N, K, act, _dt(x), _DT[out_dtype], _backend(),
-                                       _s()), "murcl_linear_fwd")
+    with _Timed("linear_fwd", 2.0 * M * N * K):
+        check(_lib.load().murcl_linear_fwd(_p(x), _p(w), _p(bias), _p(y), M, N, K, act, _dt(x), _DT[out_dtype], _backend(),
+                                           _s()), "murcl_linear_fwd")
     return y
 
 
@@ -116,8 +146,9 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
     dx = torch.empty((M, K), device=dy.device, dtype=dy.dtype)
     if relu_src is not None:
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
-    check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
-                                             _p(row_seg), _dt(dy), _backend(), _s()), "murcl_linear_bwd_input")
+    with _Timed("linear_bwd_input", 2.0 * M * N * K):
+        check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
+                                                 _p(row_seg), _dt(dy), _backend(), _s()), "murcl_linear_bwd_input")
     return dx
 
 
@@ -130,8 +161,9 @@ def linear_bwd_weight(dy, x, want_bias=True):
     db = torch.empty((N,), device=dy.device, dtype=torch.float32) if want_bias else None
     nws = int(lib.murcl_linear_bwd_weight_workspace(M, N, K))
     ws = torch.empty((max(nws, 1),), device=dy.device, dtype=torch.float32)
-    check(lib.murcl_linear_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), M, N, K, _dt(dy), _backend(), _p(ws), _s()),
-          "murcl_linear_bwd_weight")
+    with _Timed("linear_bwd_weight", 2.0 * M * N * K):
+        check(lib.murcl_linear_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), M, N, K, _dt(dy), _backend(), _p(ws), _s()),
+              "murcl_linear_bwd_weight")
     return dw, db
 
 
