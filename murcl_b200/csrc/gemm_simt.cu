@@ -169,6 +169,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   out[i] = s;
 }
 
+int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st) {
+  splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws, splits, stride, out, n);
+  return check_launch("splitk_reduce_kernel");
+}
+
 template <typename TA, typename TB, typename TC, bool A_KC, bool B_KC>
 static int launch(const GemmParams& p, int splits, cudaStream_t st) {
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN), splits);
@@ -235,8 +240,7 @@ int simt_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, 
                                 : launch<__nv_bfloat16, __nv_bfloat16, float, false, false>(p, splits, st);
   if (rc != MURCL_OK || splits == 1) return rc;
   const int64_t n = (int64_t)N * K;
-  splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(workspace, splits, n, dw, n);
-  return check_launch("splitk_reduce_kernel");
+  return launch_splitk_reduce(workspace, splits, n, dw, n, st);
 }
 
 }  // namespace murcl

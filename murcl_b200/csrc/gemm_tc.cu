@@ -1,11 +1,546 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 / TMEM / TMA GEMM family for the bf16 mode of murcl_linear_{fwd,bwd_input,bwd_weight}.
+//
+//   C[m,n] = sum_k A(m,k) * B(n,k)      bf16 operands, fp32 accumulators in tensor memory
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0  TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (STAGES deep), mbarrier tx-count
+//   warp 1  MMA issuer     one lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16), tcgen05.commit frees
+//                          smem slots and publishes the accumulator; also owns tcgen05.alloc/dealloc
+//   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Operand majors (UMMA "K-major" = reduction index contiguous in memory, "MN-major" = output index contiguous):
+//   forward      y  = x   w^T        A = x  [M,K]  K-major      B = w [N,K]   K-major
+//   input grad   dx = dy  w          A = dy [M,N]  K-major      B = w [N,K]   MN-major (rows = reduction index n)
+//   weight grad  dw = dy^T x         A = dy [M,N]  MN-major     B = x [M,K]   MN-major (rows = reduction index m), split-K
+// so no operand is ever transposed in memory.
+//
+// Roofline: tensor pipe.  Algorithmic FLOPs = 2*M*N*K per launch.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace murcl {
-bool tc_fwd_supported(int64_t, int, int, int, int) { return false; }
-bool tc_bwd_input_supported(int64_t, int, int, int) { return false; }
-bool tc_bwd_weight_supported(int64_t, int, int, int) { return false; }
-int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, cudaStream_t) { return MURCL_EUNSUPPORTED; }
-int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*, const int32_t*, cudaStream_t) { return MURCL_EUNSUPPORTED; }
-int64_t tc_linear_bwd_weight_workspace(int64_t, int, int) { return 0; }
-int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t) { return MURCL_EUNSUPPORTED; }
+
+// defined in gemm_simt.cu
+int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st);
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_SPLIT = 2 };
+
+struct Params {
+  int64_t M;          // rows of C
+  int N;              // cols of C
+  int64_t K;          // reduction length
+  int64_t ldc;
+  void* C;
+  const float* bias;
+  int act;
+  const __nv_bfloat16* relu_src;
+  const float* row_scale;
+  const float* row_vec;
+  const int32_t* row_seg;
+  int splits;
+  int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
+  int64_t split_stride;
+  int m_tiles, n_tiles;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 layout: address>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64) with 2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), majors (bits 15, 16),
+// N>>3 (bits 17-22), M>>4 (bits 24-28).
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t bars = tiles + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);          // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  const int k_blocks_full = (int)((p.k_chunk + BLOCK_K - 1) / BLOCK_K);
+
+  auto tile_coords = [&](int64_t t, int& mb, int& nb, int& sp) {
+    nb = (int)(t % p.n_tiles);
+    const int64_t r = t / p.n_tiles;
+    mb = (int)(r % p.m_tiles);
+    sp = (int)(r / p.m_tiles);
+  };
+  auto k_range = [&](int sp, int64_t& k0, int& nkb) {
+    k0 = (int64_t)sp * p.k_chunk;
+    const int64_t k1 = (k0 + p.k_chunk < p.K) ? k0 + p.k_chunk : p.K;
+    nkb = (int)((k1 - k0 + BLOCK_K - 1) / BLOCK_K);
+    if (nkb > k_blocks_full) nkb = k_blocks_full;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mb, nb, sp, nkb;
+        int64_t k0;
+        tile_coords(t, mb, nb, sp);
+        k_range(sp, k0, nkb);
+        const int m0 = mb * BLOCK_M, n0 = nb * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t a_dst = tiles + s * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+          const int kk = (int)(k0 + (int64_t)kb * BLOCK_K);
+          if (!A_MN) {
+            tma_load_2d(a_dst, &map_a, full_bar(s), kk, m0);                    // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)                               // box {64 m, 64 k-rows}
+              tma_load_2d(a_dst + j * 8192, &map_a, full_bar(s), m0 + 64 * j, kk);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &map_b, full_bar(s), kk, n0);                    // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * 8192, &map_b, full_bar(s), n0 + 64 * j, kk);
+          }
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, A_MN, B_MN);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mb, nb, sp, nkb;
+        int64_t k0;
+        tile_coords(t, mb, nb, sp);
+        k_range(sp, k0, nkb);
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t a_src = tiles + s * C::STAGE_BYTES;
+          const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: 16 k-elements = 32 B inside the 128 B swizzle span; SBO = 1024 B between 8-row groups.
+            // MN-major: 16 k-rows = two 8-row groups of 1024 B; LBO = 8192 B between 64-wide MN blocks.
+            const uint64_t adesc = A_MN ? make_smem_desc(a_src + k * 2048, 8192, 1024) : make_smem_desc(a_src + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_src + k * 2048, 8192, 1024) : make_smem_desc(b_src + k * 32, 16, 1024);
+            tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(s));                    // smem slot reusable once these MMAs retire
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+        tcgen05_commit(tfull_bar(as));                     // accumulator complete
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue warps (2..5) =================
+    const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) belong to this warp
+    int as = 0;
+    uint32_t aph = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mb, nb, sp;
+      tile_coords(t, mb, nb, sp);
+      const int64_t row = (int64_t)mb * BLOCK_M + quarter * 32 + lane;
+      const int n0 = nb * BN;
+      mbar_wait(tfull_bar(as), aph);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+      float rs = 0.f;
+      const float* rv = nullptr;
+      if (EPI == EPI_DGRAD && p.row_scale != nullptr && row < p.M) {
+        rs = p.row_scale[row];
+        rv = p.row_vec + (int64_t)p.row_seg[row] * p.N;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);                // whole warp participates (.sync.aligned)
+        const int col0 = n0 + c0;
+        if (row < p.M && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (EPI == EPI_FWD) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = col0 + i;
+              float x = v[i];
+              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+              v[i] = apply_act(x, p.act, col, p.N);
+            }
+          } else if (EPI == EPI_DGRAD) {
+            if (rv != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] = fmaf(rs, __ldg(rv + col0 + i), v[i]);
+            }
+            if (p.relu_src != nullptr) {
+              const __nv_bfloat16* src = p.relu_src + row * p.ldc + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {                     // N % 8 == 0: whole 16-byte chunks
+                  const uint4 q = *reinterpret_cast<const uint4*>(src + i);
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h[j]);
+                    if (!(f.x > 0.f)) v[i + 2 * j] = 0.f;
+                    if (!(f.y > 0.f)) v[i + 2 * j + 1] = 0.f;
+                  }
+                }
+              }
+            }
+          }
+          TOUT* dst = static_cast<TOUT*>(p.C) + (EPI == EPI_SPLIT ? (int64_t)sp * p.split_stride : 0) + row * p.ldc + col0;
+          if (sizeof(TOUT) == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (col0 + i < p.N) {
+                uint4 q;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+                q.x = *reinterpret_cast<uint32_t*>(&h0);
+                q.y = *reinterpret_cast<uint32_t*>(&h1);
+                q.z = *reinterpret_cast<uint32_t*>(&h2);
+                q.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + i) = q;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N)                          // N % 8 == 0
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));          // this warp has drained its quarter of the accumulator
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous); box = {box_cols, box_rows}, 128B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MURCL_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] box {%d,%d}", (int)r, (long long)rows, (long long)cols,
+              box_cols, box_rows);
+    return MURCL_ECUDA;
+  }
+  return MURCL_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return MURCL_ECUDA;
+    }
+    configured = true;
+  }
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace tc
+
+using namespace tc;
+
+static bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MURCL_DISABLE_TCGEN05");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool tc_fwd_supported(int64_t M, int N, int K, int dtype, int out_dtype) {
+  (void)out_dtype;
+  return tc_enabled() && dtype == MURCL_BF16 && M >= 128 && N >= 128 && N % 8 == 0 && K >= 64 && K % 8 == 0;
+}
+bool tc_bwd_input_supported(int64_t M, int N, int K, int dtype) {
+  // C = dx [M, K]; reduction over N
+  return tc_enabled() && dtype == MURCL_BF16 && M >= 128 && K >= 128 && K % 8 == 0 && N >= 64 && N % 8 == 0;
+}
+bool tc_bwd_weight_supported(int64_t M, int N, int K, int dtype) {
+  // C = dw [N, K]; reduction over M rows
+  return tc_enabled() && dtype == MURCL_BF16 && M >= 64 && N >= 128 && N % 8 == 0 && K >= 128 && K % 8 == 0;
+}
+
+int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act, int out_dtype,
+                  cudaStream_t st) {
+  if (!aligned16(x) || !aligned16(w) || !aligned16(y)) {
+    set_error("linear_fwd(tcgen05): operands must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, x, M, K, BLOCK_K, BLOCK_M);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, w, N, K, BLOCK_K, BN);
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = y; p.bias = bias; p.act = act;
+  p.splits = 1; p.k_chunk = ((int64_t)K + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
+  if (out_dtype == MURCL_BF16)
+    return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, p, st)
+                     : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, p, st);
+  return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, p, st)
+                   : launch<128, false, false, EPI_FWD, float>(ma, mb, p, st);
+}
+
+int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
+                        const float* row_scale, const float* row_vec, const int32_t* row_seg, cudaStream_t st) {
+  if (!aligned16(dy) || !aligned16(w) || !aligned16(dx) || (relu_src && !aligned16(relu_src))) {
+    set_error("linear_bwd_input(tcgen05): operands must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  // C = dx [M, K_in]; A = dy [M, N] K-major (reduction over N); B(n'=k_in, k'=n) = w[n, k_in]: MN-major, rows = n.
+  const int BN = (K % 256 == 0) ? 256 : 128;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dy, M, N, BLOCK_K, BLOCK_M);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, w, N, K, 64, BLOCK_K);
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = M; p.N = K; p.K = N; p.ldc = K; p.C = dx;
+  p.relu_src = static_cast<const __nv_bfloat16*>(relu_src);
+  p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg;
+  p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, p, st)
+                   : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, p, st);
+}
+
+static void wgrad_plan(int64_t M, int N, int K, int& BN, int& splits, int64_t& k_chunk) {
+  BN = (K % 256 == 0) ? 256 : 128;
+  const int tiles = ceil_div(N, BLOCK_M) * ceil_div(K, BN);
+  splits = sm_count() / tiles;                                     // one wave
+  if (splits < 1) splits = 1;
+  const int64_t kb_total = (M + BLOCK_K - 1) / BLOCK_K;
+  if (splits > kb_total) splits = (int)kb_total;
+  const int64_t kb_per = (kb_total + splits - 1) / splits;
+  k_chunk = kb_per * BLOCK_K;
+  splits = (int)((kb_total + kb_per - 1) / kb_per);                // every split owns >= 1 k-block
+}
+
+int64_t tc_linear_bwd_weight_workspace(int64_t M, int N, int K) {
+  if (M < 64 || N < 128 || K < 128) return 0;
+  int BN, splits;
+  int64_t kc;
+  wgrad_plan(M, N, K, BN, splits, kc);
+  return (int64_t)splits * N * K;
+}
+
+int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, int N, int K, float* workspace, cudaStream_t st) {
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dw) || !aligned16(workspace)) {
+    set_error("linear_bwd_weight(tcgen05): operands must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  int BN, splits;
+  int64_t k_chunk;
+  wgrad_plan(M, N, K, BN, splits, k_chunk);
+  if (workspace == nullptr) {
+    set_error("linear_bwd_weight(tcgen05): workspace required");
+    return MURCL_EINVAL;
+  }
+  // C = dw [N, K_in]; reduction over the M rows.  A(m'=n, k'=m) = dy[m, n]; B(n'=k_in, k'=m) = x[m, k_in]; both MN-major.
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dy, M, N, 64, BLOCK_K);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, x, M, K, 64, BLOCK_K);
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
+  p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
+  p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, p, st) : launch<128, true, true, EPI_SPLIT, float>(ma, mb, p, st);
+  if (rc != MURCL_OK) return rc;
+  const int64_t n = (int64_t)N * K;
+  return launch_splitk_reduce(workspace, splits, n, dw, n, st);
+}
+
+}  // namespace murcl

@@ -35,6 +35,11 @@ def _load(module, sd):
     return module.to(DEV)
 
 
+def _zero_grad_key(k):
+    """Final attention bias: its gradient is analytically zero (softmax shift invariance), only noise remains."""
+    return k.endswith(("attention.2.bias", "attention_c.bias", "module.2.bias", "module.3.bias"))
+
+
 def _grads(module):
     return {n: p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(p).cpu() for n, p in module.named_parameters()}
 
@@ -178,7 +183,7 @@ def test_abmil_golden_small(golden):
     gr = _grads(m)
     for k, v in g.items():
         if k.startswith("grad."):
-            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-4)
+            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-1 if _zero_grad_key(k) else 1e-4)
     for i, b in enumerate(bags):
         assert_close(b.grad, g[f"grad_input.{i}"], FP32_GRAD, f"dx{i}")
     with torch.no_grad():
@@ -212,7 +217,7 @@ def test_abmil_full_size(golden, precision, tol_out, tol_grad):
     for k, p in sdl.items():
         if k.startswith("fc."):
             continue
-        assert_close(gr[k], p.grad, tol_grad, k, floor=1e-4 if "attention.2.bias" in k else 1e-7)
+        assert_close(gr[k], p.grad, tol_grad, k, floor=1e-1 if _zero_grad_key(k) else 1e-7)
 
 
 @pytest.mark.parametrize("gate", [True, False])
@@ -244,7 +249,7 @@ def test_clam_golden(golden, gate, dropout, subtyping):
     gr = _grads(m)
     for k, v in g.items():
         if k.startswith("grad."):
-            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-4)
+            assert_close(sample(gr[k[5:]].numpy()), v, FP32_GRAD, k, floor=1e-1 if _zero_grad_key(k) else 1e-4)
     assert_close(x0.grad, g["grad_input.0"], FP32_GRAD, "dx0")
     with torch.no_grad():
         outs, det = m([f.to(DEV) for f in feats])
@@ -302,7 +307,7 @@ def test_clam_ragged_cfg2(precision, tol_out, tol_grad):
         for k, p in sdl.items():
             if k.startswith("classifiers") or p.grad is None:
                 continue
-            assert_close(gr[k], p.grad, tol_grad, k, floor=1e-5)
+            assert_close(gr[k], p.grad, tol_grad, k, floor=1e-1 if _zero_grad_key(k) else 1e-5)
 
 
 # ------------------------------------------------------------------------------------------------
