@@ -287,6 +287,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the MIL hot path has no CPU fallback; use --impl reference)")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    os.environ["MURCL_PRECISION"] = a.precision          # heads (Full_layer, actor, decoder) follow the same mode
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from murcl_b200 import _lib

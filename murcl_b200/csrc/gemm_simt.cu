@@ -169,6 +169,22 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   out[i] = s;
 }
 
+// Split-K tail for the small-M dense layers: sum the partials, then the same fused epilogue as the main kernel.
+template <typename TC>
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __restrict__ ws, int splits, GemmParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.M * p.N) return;
+  const int64_t m = i / p.N;
+  const int n = (int)(i % p.N);
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += ws[z * p.split_stride + m * p.ldc + n];
+  if (p.bias) v += p.bias[n];
+  v = apply_act(v, p.act, n, p.N);
+  if (p.row_scale) v = fmaf(p.row_scale[m], p.row_vec[(int64_t)p.row_seg[m] * p.N + n], v);
+  if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) v = 0.f;
+  Store<TC>::store(static_cast<TC*>(p.C) + m * p.ldc + n, v);
+}
+
 int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st) {
   splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws, splits, stride, out, n);
   return check_launch("splitk_reduce_kernel");
@@ -181,16 +197,55 @@ static int launch(const GemmParams& p, int splits, cudaStream_t st) {
   return check_launch("gemm_simt_kernel");
 }
 
+// Forward / input-gradient launch.  When the output has too few 128x128 tiles to fill the GPU (the heads:
+// M = batch size) the reduction is split across gridDim.z into a stream-ordered scratch buffer.
+template <typename TA, typename TB, typename TC, bool A_KC, bool B_KC>
+static int launch_auto(GemmParams p, cudaStream_t st) {
+  const int ctas = ceil_div(p.M, BM) * ceil_div(p.N, BN);
+  int splits = 1;
+  if (ctas * 2 <= sm_count() && p.K >= 256) {
+    splits = (2 * sm_count()) / ctas;
+    const int by_k = (int)(p.K / 64);
+    if (splits > by_k) splits = by_k;
+    if (splits > 32) splits = 32;
+  }
+  if (splits <= 1) return launch<TA, TB, TC, A_KC, B_KC>(p, 1, st);
+  int64_t chunk = (p.K + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  splits = (int)((p.K + chunk - 1) / chunk);
+  float* ws = nullptr;
+  const size_t bytes = sizeof(float) * (size_t)splits * p.M * p.N;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st);
+  if (e != cudaSuccess) {
+    set_error("gemm_simt: cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return MURCL_ECUDA;
+  }
+  GemmParams q = p;
+  q.C = ws;
+  q.k_chunk = chunk;
+  q.split_stride = p.M * p.N;
+  q.ldc = p.N;
+  int rc = launch<TA, TB, float, A_KC, B_KC>(q, splits, st);
+  if (rc == MURCL_OK) {
+    GemmParams r = p;
+    r.split_stride = p.M * p.N;
+    splitk_epilogue_kernel<TC><<<ceil_div(p.M * p.N, 256), 256, 0, st>>>(ws, splits, r);
+    rc = check_launch("splitk_epilogue_kernel");
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
 int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act,
                     int dtype, int out_dtype, cudaStream_t st) {
   GemmParams p{};
   p.A = x; p.B = w; p.C = y; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldb = K; p.ldc = N;
   p.bias = bias; p.act = act; p.k_chunk = K;
-  if (dtype == MURCL_F32 && out_dtype == MURCL_F32) return launch<float, float, float, true, true>(p, 1, st);
+  if (dtype == MURCL_F32 && out_dtype == MURCL_F32) return launch_auto<float, float, float, true, true>(p, st);
   if (dtype == MURCL_BF16 && out_dtype == MURCL_BF16)
-    return launch<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, true>(p, 1, st);
+    return launch_auto<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, true>(p, st);
   if (dtype == MURCL_BF16 && out_dtype == MURCL_F32)
-    return launch<__nv_bfloat16, __nv_bfloat16, float, true, true>(p, 1, st);
+    return launch_auto<__nv_bfloat16, __nv_bfloat16, float, true, true>(p, st);
   set_error("linear_fwd(simt): unsupported dtype pair %d -> %d", dtype, out_dtype);
   return MURCL_EUNSUPPORTED;
 }
@@ -202,8 +257,8 @@ int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, in
   // C = dx [M, K]; reduction over N; A = dy [M,N] k-contiguous; B(n'=k_in, k'=n) = w[n, k_in] n'-contiguous.
   p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
   p.relu_src = relu_src; p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.k_chunk = N;
-  if (dtype == MURCL_F32) return launch<float, float, float, true, false>(p, 1, st);
-  return launch<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, false>(p, 1, st);
+  if (dtype == MURCL_F32) return launch_auto<float, float, float, true, false>(p, st);
+  return launch_auto<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, false>(p, st);
 }
 
 static int bwd_weight_splits(int64_t M, int N, int K) {

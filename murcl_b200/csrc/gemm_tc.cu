@@ -6,7 +6,9 @@
 //   warp 0  TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (STAGES deep), mbarrier tx-count
 //   warp 1  MMA issuer     one lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16), tcgen05.commit frees
 //                          smem slots and publishes the accumulator; also owns tcgen05.alloc/dealloc
-//   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+//   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> 128B-swizzled smem slab
+//                          (32 rows x 128 B per warp) -> cp.async.bulk.tensor store; the ReLU-mask operand of the
+//                          input-gradient epilogue arrives the same way (TMA load of the matching slab)
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Operand majors (UMMA "K-major" = reduction index contiguous in memory, "MN-major" = output index contiguous):
@@ -32,7 +34,7 @@ constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 224 * 1024;
 
 enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_SPLIT = 2 };
 
@@ -84,6 +86,52 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Activation over a register slab.  bf16 outputs use the MUFU tanh (error ~2^-11, below bf16's 2^-9 rounding);
+// fp32 outputs use the accurate libm versions.
+template <bool FAST, int N>
+__device__ __forceinline__ void act_slab(float (&v)[N], int act, int col0, int n_cols) {
+  if (act == MURCL_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == MURCL_ACT_TANH || (act == MURCL_ACT_TANH_SIGMOID && col0 + N <= (n_cols >> 1))) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = FAST ? tanh_fast(v[i]) : tanhf(v[i]);
+  } else if (act == MURCL_ACT_SIGMOID || (act == MURCL_ACT_TANH_SIGMOID && col0 >= (n_cols >> 1))) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = FAST ? fmaf(0.5f, tanh_fast(0.5f * v[i]), 0.5f) : 1.f / (1.f + expf(-v[i]));
+  } else if (act == MURCL_ACT_TANH_SIGMOID) {      // slab straddles the tanh | sigmoid boundary
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (col0 + i < (n_cols >> 1)) ? tanhf(v[i]) : 1.f / (1.f + expf(-v[i]));
+  }
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -130,28 +178,34 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a
          ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
+constexpr int SLAB_BYTES = 32 * 128;        // one epilogue warp's staging slab: 32 rows x 128 B
+constexpr int STAGING_BYTES = 4 * SLAB_BYTES * 2;   // per warp: output slab + mask slab
+
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_mask, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B atoms need 1024 B alignment
-  const uint32_t bars = tiles + C::STAGES * C::STAGE_BYTES;
+  const uint32_t staging = tiles + C::STAGES * C::STAGE_BYTES;        // 1024 B aligned (stage sizes are multiples of 1024)
+  const uint32_t bars = staging + STAGING_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
-  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  auto mask_bar = [&](int w) { return bars + 8u * (2 * C::STAGES + 4 + w); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 8);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);          // one arrival per epilogue warp
     }
+    for (int w = 0; w < 4; ++w) mbar_init(mask_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
@@ -266,85 +321,121 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ================= epilogue warps (2..5) =================
     const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) belong to this warp
+    const uint32_t out_slab = staging + (uint32_t)quarter * (2 * SLAB_BYTES);
+    const uint32_t mask_slab = out_slab + SLAB_BYTES;
+    const uint32_t my_row_off = (uint32_t)lane * 128u;
+    const uint32_t swz = (uint32_t)(lane & 7);             // 128B swizzle: 16-byte chunk index ^= row & 7
+    constexpr int SLAB_COLS = 128 / (int)sizeof(TOUT);      // 64 bf16 or 32 fp32 columns = 128 B per row
     int as = 0;
-    uint32_t aph = 0;
+    uint32_t aph = 0, mph = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int mb, nb, sp;
       tile_coords(t, mb, nb, sp);
-      const int64_t row = (int64_t)mb * BLOCK_M + quarter * 32 + lane;
+      const int64_t row0 = (int64_t)mb * BLOCK_M + quarter * 32;
+      const int64_t row = row0 + lane;
       const int n0 = nb * BN;
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
-      float rs = 0.f;
-      const float* rv = nullptr;
-      if (EPI == EPI_DGRAD && p.row_scale != nullptr && row < p.M) {
-        rs = p.row_scale[row];
-        rv = p.row_vec + (int64_t)p.row_seg[row] * p.N;
-      }
+      if (EPI == EPI_SPLIT) {
+        // fp32 partial sums straight to the split workspace (few tiles per launch: not worth staging)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)c0, r);                // whole warp participates (.sync.aligned)
-        const int col0 = n0 + c0;
-        if (row < p.M && col0 < p.N) {
-          float v[32];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + (uint32_t)c0, r);
+          const int col0 = n0 + c0;
+          if (row < p.M && col0 < p.N) {
+            float* dst = static_cast<float*>(p.C) + (int64_t)sp * p.split_stride + row * p.ldc + col0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; i += 4)
+              if (col0 + i < p.N)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          }
+        }
+      } else {
+        float rs = 0.f;
+        const float* rv = nullptr;
+        if (EPI == EPI_DGRAD && p.row_scale != nullptr && row < p.M) {
+          rs = p.row_scale[row];
+          rv = p.row_vec + (int64_t)p.row_seg[row] * p.N;
+        }
+        const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += SLAB_COLS) {
+          const int col0 = n0 + c0;
+          if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this slab is in range
+          if (has_mask && lane == 0) {                     // fetch the matching slab of the ReLU source
+            mbar_expect_tx(mask_bar(quarter), SLAB_BYTES);
+            tma_load_2d(mask_slab, &map_mask, mask_bar(quarter), col0, (int)row0);
+          }
+          float v[SLAB_COLS];
+#pragma unroll
+          for (int j = 0; j < SLAB_COLS / 32; ++j) {
+            uint32_t r[32];
+            tmem_ld32(t_row + (uint32_t)(c0 + 32 * j), r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[32 * j + i] = __uint_as_float(r[i]);
+          }
           if (EPI == EPI_FWD) {
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = col0 + i;
-              float x = v[i];
-              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-              v[i] = apply_act(x, p.act, col, p.N);
+              for (int i = 0; i < SLAB_COLS; i += 4) {
+                if (col0 + i < p.N) {                       // N % 8 == 0
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+              }
             }
-          } else if (EPI == EPI_DGRAD) {
+            act_slab<sizeof(TOUT) == 2, SLAB_COLS>(v, p.act, col0, p.N);
+          } else {
             if (rv != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] = fmaf(rs, __ldg(rv + col0 + i), v[i]);
+              for (int i = 0; i < SLAB_COLS; i += 4) {
+                if (col0 + i < p.N) {
+                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(rv + col0 + i));
+                  v[i] = fmaf(rs, g4.x, v[i]); v[i + 1] = fmaf(rs, g4.y, v[i + 1]);
+                  v[i + 2] = fmaf(rs, g4.z, v[i + 2]); v[i + 3] = fmaf(rs, g4.w, v[i + 3]);
+                }
+              }
             }
-            if (p.relu_src != nullptr) {
-              const __nv_bfloat16* src = p.relu_src + row * p.ldc + col0;
+            if (has_mask) {
+              mbar_wait(mask_bar(quarter), mph);
+              mph ^= 1u;
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (col0 + i < p.N) {                     // N % 8 == 0: whole 16-byte chunks
-                  const uint4 q = *reinterpret_cast<const uint4*>(src + i);
-                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+              for (int c = 0; c < 8; ++c) {                 // bf16 mask slab: 8 chunks of 8 columns per row
+                const uint4 q = ld_shared_v4(mask_slab + my_row_off + (((uint32_t)c ^ swz) << 4));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = __bfloat1622float2(h[j]);
-                    if (!(f.x > 0.f)) v[i + 2 * j] = 0.f;
-                    if (!(f.y > 0.f)) v[i + 2 * j + 1] = 0.f;
-                  }
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(h[j]);
+                  if (!(f.x > 0.f)) v[8 * c + 2 * j] = 0.f;
+                  if (!(f.y > 0.f)) v[8 * c + 2 * j + 1] = 0.f;
                 }
               }
             }
           }
-          TOUT* dst = static_cast<TOUT*>(p.C) + (EPI == EPI_SPLIT ? (int64_t)sp * p.split_stride : 0) + row * p.ldc + col0;
+          // stage the slab (swizzled like the TMA box) and hand it to the bulk-store engine
+          if (lane == 0) bulk_wait_read0();                 // previous store has finished reading the slab
+          __syncwarp();
           if (sizeof(TOUT) == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {
-                uint4 q;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                q.x = *reinterpret_cast<uint32_t*>(&h0);
-                q.y = *reinterpret_cast<uint32_t*>(&h1);
-                q.z = *reinterpret_cast<uint32_t*>(&h2);
-                q.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + i) = q;
-              }
-            }
+            for (int c = 0; c < 8; ++c)
+              st_shared_v4(out_slab + my_row_off + (((uint32_t)c ^ swz) << 4), pack_bf16(v[8 * c], v[8 * c + 1]),
+                           pack_bf16(v[8 * c + 2], v[8 * c + 3]), pack_bf16(v[8 * c + 4], v[8 * c + 5]),
+                           pack_bf16(v[8 * c + 6], v[8 * c + 7]));
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (col0 + i < p.N)                          // N % 8 == 0
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
+            for (int c = 0; c < 8; ++c)
+              st_shared_v4(out_slab + my_row_off + (((uint32_t)c ^ swz) << 4), __float_as_uint(v[4 * c % SLAB_COLS]),
+                           __float_as_uint(v[(4 * c + 1) % SLAB_COLS]), __float_as_uint(v[(4 * c + 2) % SLAB_COLS]),
+                           __float_as_uint(v[(4 * c + 3) % SLAB_COLS]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, out_slab, col0, (int)row0);   // rows >= M and cols >= N are clipped by the tensor map
+            bulk_commit();
           }
         }
       }
@@ -353,6 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar(as));          // this warp has drained its quarter of the accumulator
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
+    if (EPI != EPI_SPLIT && lane == 0) bulk_wait_all();     // all bulk stores of this warp have completed
   }
 
   tcgen05_fence_before();
@@ -380,20 +472,22 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major tensor [rows, cols] (cols contiguous); box = {box_cols, box_rows}, 128B swizzle, zero OOB fill.
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows) {
+// 2-D row-major tensor [rows, cols] (cols contiguous) of 2-byte (bf16) or 4-byte (fp32) elements;
+// box = {box_cols, box_rows}, 128B swizzle, zero OOB fill on loads / clipping on stores.
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                    int elem_bytes = 2) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return MURCL_ECUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] box {%d,%d}", (int)r, (long long)rows, (long long)cols,
               box_cols, box_rows);
@@ -403,7 +497,8 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mm, const Params& p,
+                  cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT>;
   static bool configured = false;
@@ -417,7 +512,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
   }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mc, mm, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -461,15 +556,23 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
   if (rc != MURCL_OK) return rc;
   rc = make_map(&mb, w, N, K, BLOCK_K, BN);
   if (rc != MURCL_OK) return rc;
+  CUtensorMap mc;
+  const int eb = out_dtype == MURCL_BF16 ? 2 : 4;
+  rc = make_map(&mc, y, M, N, 128 / eb, 32, eb);                 // store slab: 32 rows x 128 B
+  if (rc != MURCL_OK) return rc;
+  if (bias != nullptr && !aligned16(bias)) {
+    set_error("linear_fwd(tcgen05): bias must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
   Params p{};
   p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = y; p.bias = bias; p.act = act;
   p.splits = 1; p.k_chunk = ((int64_t)K + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
   if (out_dtype == MURCL_BF16)
-    return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, p, st)
-                     : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, p, st);
-  return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, p, st)
-                   : launch<128, false, false, EPI_FWD, float>(ma, mb, p, st);
+    return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st)
+                     : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st);
+  return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, mc, mc, p, st)
+                   : launch<128, false, false, EPI_FWD, float>(ma, mb, mc, mc, p, st);
 }
 
 int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
@@ -491,8 +594,17 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg;
   p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
-  return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, p, st)
-                   : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, p, st);
+  CUtensorMap mc, mm;
+  rc = make_map(&mc, dx, M, K, 64, 32);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mm, relu_src ? relu_src : dx, M, K, 64, 32);
+  if (rc != MURCL_OK) return rc;
+  if (row_vec != nullptr && !aligned16(row_vec)) {
+    set_error("linear_bwd_input(tcgen05): row_vec must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st)
+                   : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st);
 }
 
 static void wgrad_plan(int64_t M, int N, int K, int& BN, int& splits, int64_t& k_chunk) {
@@ -537,7 +649,8 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
   p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
-  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, p, st) : launch<128, true, true, EPI_SPLIT, float>(ma, mb, p, st);
+  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, ma, p, st)
+                 : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, ma, p, st);
   if (rc != MURCL_OK) return rc;
   const int64_t n = (int64_t)N * K;
   return launch_splitk_reduce(workspace, splits, n, dw, n, st);

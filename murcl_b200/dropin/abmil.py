@@ -44,7 +44,7 @@ class ABMIL(nn.Module):
         M, p, _s, _il, _pr = ops.mil_aggregate(rows.rows, rows.offsets, rows.row_seg, self._meta(rows),
                                                self.attention[0].weight, self.attention[0].bias,
                                                self.attention[2].weight, self.attention[2].bias, None, None, enc)
-        out = ops.linear(M, self.decoder[0].weight, self.decoder[0].bias, ops.ACT_RELU)
+        out = ops.linear(M, self.decoder[0].weight, self.decoder[0].bias, ops.ACT_RELU, self._meta(rows)["dtype"])
         return out, p
 
     def bag_forward(self, bag):

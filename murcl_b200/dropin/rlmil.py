@@ -35,6 +35,11 @@ def _gru_params(gru: nn.GRU):
     return gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0
 
 
+def _dtype(module):
+    """Operand storage of the dense layers: fp32 (exact) or bf16 (tcgen05); module.precision or MURCL_PRECISION."""
+    return ops.storage_dtype(getattr(module, "precision", None) or ops.default_precision())
+
+
 class ActorCritic(nn.Module):
     def __init__(self, feature_dim, state_dim, hidden_state_dim=1024, policy_conv=False, action_std=0.1, action_size=2):
         super(ActorCritic, self).__init__()
@@ -57,8 +62,9 @@ class ActorCritic(nn.Module):
         raise NotImplementedError
 
     def _encode(self, state):
-        s = ops.linear(state, self.state_encoder[0].weight, self.state_encoder[0].bias, ops.ACT_RELU)
-        return ops.linear(s, self.state_encoder[2].weight, self.state_encoder[2].bias, ops.ACT_RELU)
+        dt = _dtype(self)
+        s = ops.linear(state, self.state_encoder[0].weight, self.state_encoder[0].bias, ops.ACT_RELU, dt)
+        return ops.linear(s, self.state_encoder[2].weight, self.state_encoder[2].bias, ops.ACT_RELU, dt)
 
     def act(self, state_ini, memory, restart_batch=False, training=False, eps=None):
         """rlmil.py:66-97.  ``eps`` optionally supplies the standard-normal draw (parity tests); by default it
@@ -69,7 +75,7 @@ class ActorCritic(nn.Module):
                 memory.hidden.append(torch.zeros(1, state_ini.size(0), self.hidden_state_dim, device=state_ini.device))
             state = state_ini.flatten(1).float().contiguous()
             enc = self._encode(state)
-            h = ops.gru_step(enc, memory.hidden[-1][0].contiguous(), *_gru_params(self.gru))
+            h = ops.gru_step(enc, memory.hidden[-1][0].contiguous(), *_gru_params(self.gru), dtype=_dtype(self))
             memory.hidden.append(h.unsqueeze(0))
             logits = ops.linear(h, self.actor[0].weight, self.actor[0].bias)
             if eps is None:
@@ -91,7 +97,7 @@ class ActorCritic(nn.Module):
         h = torch.zeros(batch_size, self.hidden_state_dim, device=state.device)
         outs = []
         for t in range(seq_l):
-            h = ops.gru_step(enc[t].contiguous(), h, *_gru_params(self.gru))
+            h = ops.gru_step(enc[t].contiguous(), h, *_gru_params(self.gru), dtype=_dtype(self))
             outs.append(h)
         feat = torch.cat(outs, 0)
         mean = ops.linear(feat, self.actor[0].weight, self.actor[0].bias, ops.ACT_SIGMOID)
@@ -175,9 +181,9 @@ class Full_layer(torch.nn.Module):
                 h_prev = torch.zeros(x.size(0), self.hidden_state_dim, device=x.device)
             else:
                 h_prev = self.hidden[0]
-            h = ops.gru_step(x.float().contiguous(), h_prev, *_gru_params(self.rnn))
+            h = ops.gru_step(x.float().contiguous(), h_prev, *_gru_params(self.rnn), dtype=_dtype(self))
             self.hidden = h.unsqueeze(0)
-            return ops.linear(h, self.fc.weight, self.fc.bias)
+            return ops.linear(h, self.fc.weight, self.fc.bias, ops.ACT_NONE, _dtype(self))
         else:
             if restart:
                 self.hidden = x

@@ -331,10 +331,10 @@ class _GRUCell(torch.autograd.Function):
         return dgi, dgh, dh_prev
 
 
-def gru_step(x, h_prev, w_ih, w_hh, b_ih, b_hh):
+def gru_step(x, h_prev, w_ih, w_hh, b_ih, b_hh, dtype: torch.dtype = torch.float32):
     """One nn.GRU time step (gate order r,z,n) built from two dense layers and the fused cell kernel."""
-    gi = linear(x, w_ih, b_ih)
-    gh = linear(h_prev, w_hh, b_hh)
+    gi = linear(x, w_ih, b_ih, ACT_NONE, dtype)
+    gh = linear(h_prev, w_hh, b_hh, ACT_NONE, dtype)
     return _GRUCell.apply(gi, gh, h_prev)
 
 
