@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-bags", type=int, default=8, help="slides in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -143,8 +144,31 @@ class Job:
         else:
             self.crit = losses.NT_Xent(a.bags, 1.0)
         self.params = list(self.model.parameters()) + list(self.fc.parameters())
-        self.opt = torch.optim.Adam(self.params, lr=1e-4, weight_decay=1e-5)
+        self.opt = torch.optim.Adam(self.params, lr=1e-4, weight_decay=1e-5, capturable=True)
         self.mdist = mdist
+        self.graphs = {}
+        self.launches_per_step = None
+
+    def capture(self, stores):
+        """One CUDA graph per (double-buffered) store, sharing a memory pool.  Returns False if capture fails."""
+        from murcl_b200 import _lib, pretrain
+        try:
+            pool = None
+            for i, st in enumerate(stores):
+                g = pretrain.GraphedStep(lambda st=st: self.step(st), warmup=2 if i == 0 else 0, pool=pool)
+                pool = g.pool()
+                self.graphs[id(st)] = g
+                self.launches_per_step = g.launches
+            return True
+        except Exception as e:                                  # noqa: BLE001 - report and fall back to eager launches
+            sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
+            self.graphs = {}
+            torch.cuda.synchronize()
+            return False
+
+    def run(self, store):
+        g = self.graphs.get(id(store))
+        return g() if g is not None else self.step(store)
 
     def step(self, store):
         from murcl_b200 import pretrain
@@ -306,14 +330,15 @@ def main():
     job = Job(a, rank, world, device)
 
     # ---- device-resident throughput --------------------------------------------------------------
+    graphed = (not a.no_graph) and job.capture(stores)
     for i in range(a.warmup):
-        job.step(stores[i % 2])
+        job.run(stores[i % 2])
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
     l0 = _lib.launch_count()
-    ms = timed(lambda i: job.step(stores[i % 2]), a.steps, world, device)
-    launches = _lib.launch_count() - l0
+    ms = timed(lambda i: job.run(stores[i % 2]), a.steps, world, device)
+    launches = job.launches_per_step * a.steps if graphed else _lib.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     value = a.bags * world * a.steps / (ms * 1e-3)
 
@@ -338,7 +363,7 @@ def main():
             if i + 1 < a.e2e_steps:
                 prefetch(i + 1)                      # next batch's H2D overlaps this step's compute
             torch.cuda.current_stream().wait_event(ready[i % 2])
-            loss = job.step(stores[i % 2])
+            loss = job.run(stores[i % 2])
             freed[i % 2].record()
             losses.append(float(loss.item()))        # D2H read of the step's result
 
@@ -363,7 +388,7 @@ def main():
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
-               "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+               "config": dict(workload_config(a, world), cuda_graph=bool(graphed)), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roof, "cpu_baseline": cpu,
                "bag_passes_per_s": round(value * a.T * 2, 1)}
         print(json.dumps(out))

@@ -236,11 +236,98 @@ static int launch_auto(GemmParams p, cudaStream_t st) {
   return rc;
 }
 
+// ---- skinny outputs (N <= 16): instance classifiers, actor head -----------------------------------
+// One warp per row: x[m,:] is read once (HBM-bound for large M), the N weight rows stay in L1/L2.
+constexpr int SKINNY_N = 16;
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                         const float* __restrict__ bias, TO* __restrict__ y, int64_t M, int N,
+                                                         int K, int act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float acc[SKINNY_N];
+#pragma unroll
+  for (int n = 0; n < SKINNY_N; ++n) acc[n] = 0.f;
+  const T* xr = x + m * K;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 a = load4(xr + k);
+#pragma unroll
+      for (int n = 0; n < SKINNY_N; ++n) {
+        if (n < N) {
+          const float4 b = load4(w + (int64_t)n * K + k);
+          acc[n] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float a = Store<T>::load(xr + k);
+#pragma unroll
+      for (int n = 0; n < SKINNY_N; ++n)
+        if (n < N) acc[n] = fmaf(a, Store<T>::load(w + (int64_t)n * K + k), acc[n]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < SKINNY_N; ++n) {
+    if (n < N) {
+      float v = warp_sum(acc[n]);
+      if (lane == 0) {
+        if (bias) v += bias[n];
+        Store<TO>::store(y + m * N + n, apply_act(v, act, n, N));
+      }
+    }
+  }
+}
+
+// dx[m,k] = sum_n dy[m,n] * w[n,k] for a short reduction (N <= 16); same epilogue options as the tiled kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx,
+                                                           int64_t M, int N, int K, const T* __restrict__ relu_src,
+                                                           const float* __restrict__ row_scale, const float* __restrict__ row_vec,
+                                                           const int32_t* __restrict__ row_seg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float g[SKINNY_N];
+#pragma unroll
+  for (int n = 0; n < SKINNY_N; ++n) g[n] = n < N ? Store<T>::load(dy + m * N + n) : 0.f;
+  const float rs = row_scale ? row_scale[m] : 0.f;
+  const float* rv = row_scale ? row_vec + (int64_t)row_seg[m] * K : nullptr;
+  for (int k = lane; k < K; k += 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < SKINNY_N; ++n)
+      if (n < N) v = fmaf(g[n], Store<T>::load(w + (int64_t)n * K + k), v);
+    if (rv) v = fmaf(rs, rv[k], v);
+    if (relu_src && !(Store<T>::load(relu_src + m * K + k) > 0.f)) v = 0.f;
+    Store<T>::store(dx + m * K + k, v);
+  }
+}
+
 int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act,
                     int dtype, int out_dtype, cudaStream_t st) {
   GemmParams p{};
   p.A = x; p.B = w; p.C = y; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldb = K; p.ldc = N;
   p.bias = bias; p.act = act; p.k_chunk = K;
+  if (N <= SKINNY_N) {
+    const int grid = ceil_div(M, 8);
+    if (dtype == MURCL_F32 && out_dtype == MURCL_F32)
+      skinny_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (const float*)w, bias, (float*)y, M, N, K, act);
+    else if (dtype == MURCL_BF16 && out_dtype == MURCL_BF16)
+      skinny_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                                                                           (__nv_bfloat16*)y, M, N, K, act);
+    else if (dtype == MURCL_BF16 && out_dtype == MURCL_F32)
+      skinny_fwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                                                                   (float*)y, M, N, K, act);
+    else {
+      set_error("linear_fwd(simt): unsupported dtype pair %d -> %d", dtype, out_dtype);
+      return MURCL_EUNSUPPORTED;
+    }
+    return check_launch("skinny_fwd_kernel");
+  }
   if (dtype == MURCL_F32 && out_dtype == MURCL_F32) return launch_auto<float, float, float, true, true>(p, st);
   if (dtype == MURCL_BF16 && out_dtype == MURCL_BF16)
     return launch_auto<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, true>(p, st);
@@ -257,6 +344,17 @@ int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, in
   // C = dx [M, K]; reduction over N; A = dy [M,N] k-contiguous; B(n'=k_in, k'=n) = w[n, k_in] n'-contiguous.
   p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
   p.relu_src = relu_src; p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.k_chunk = N;
+  if (N <= SKINNY_N) {
+    const int grid = ceil_div(M, 8);
+    if (dtype == MURCL_F32)
+      skinny_dgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)w, (float*)dx, M, N, K,
+                                                       (const float*)relu_src, row_scale, row_vec, row_seg);
+    else
+      skinny_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w,
+                                                               (__nv_bfloat16*)dx, M, N, K, (const __nv_bfloat16*)relu_src,
+                                                               row_scale, row_vec, row_seg);
+    return check_launch("skinny_dgrad_kernel");
+  }
   if (dtype == MURCL_F32) return launch_auto<float, float, float, true, false>(p, st);
   return launch_auto<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, false>(p, st);
 }

@@ -90,23 +90,49 @@ __global__ void __launch_bounds__(256) row_segments_kernel(const int64_t* __rest
   for (int64_t n = lo + threadIdx.x; n < hi; n += blockDim.x) row_seg[n] = b;
 }
 
-// Column sums: grid (column tiles of 32, row slices); each warp walks rows, lanes own columns.
+// Column sums: each lane owns 4 consecutive columns (8/16-byte loads), a warp covers 128 columns of one row per
+// step; grid = (column tiles of 128, row slices); warps of a CTA walk interleaved rows, shared-memory reduce across
+// warps, one atomicAdd per column per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ a, int64_t M, int N, float* __restrict__ out) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[8][128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane;
+  const int col = blockIdx.x * 128 + lane * 4;
   const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  float acc = 0.f;
-  if (col < N)
-    for (int64_t r = r0 + w; r < r1; r += 8) acc += Store<T>::load(a + r * N + col);
-  sm[w][lane] = acc;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((N & 3) == 0) {
+    if (col < N) {
+      int64_t r = r0 + w;
+      for (; r + 24 < r1; r += 32) {            // 4 independent loads in flight per lane
+        const float4 v0 = load4(a + r * N + col), v1 = load4(a + (r + 8) * N + col);
+        const float4 v2 = load4(a + (r + 16) * N + col), v3 = load4(a + (r + 24) * N + col);
+        acc.x += (v0.x + v1.x) + (v2.x + v3.x);
+        acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+        acc.z += (v0.z + v1.z) + (v2.z + v3.z);
+        acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; r < r1; r += 8) {
+        const float4 v = load4(a + r * N + col);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+  } else {
+    for (int64_t r = r0 + w; r < r1; r += 8) {
+      if (col + 0 < N) acc.x += Store<T>::load(a + r * N + col + 0);
+      if (col + 1 < N) acc.y += Store<T>::load(a + r * N + col + 1);
+      if (col + 2 < N) acc.z += Store<T>::load(a + r * N + col + 2);
+      if (col + 3 < N) acc.w += Store<T>::load(a + r * N + col + 3);
+    }
+  }
+  sm[w][lane * 4 + 0] = acc.x; sm[w][lane * 4 + 1] = acc.y; sm[w][lane * 4 + 2] = acc.z; sm[w][lane * 4 + 3] = acc.w;
   __syncthreads();
-  if (w == 0) {
+  if (threadIdx.x < 128) {
     float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += sm[i][lane];
-    if (col < N) atomicAdd(&out[col], t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < N) atomicAdd(&out[c], t);
   }
 }
 
@@ -134,9 +160,9 @@ int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStre
     set_error("colsum: memset failed: %s", cudaGetErrorString(e));
     return MURCL_ECUDA;
   }
-  const int col_tiles = ceil_div(N, 32);
-  int slices = (4 * sm_count() + col_tiles - 1) / col_tiles;
-  const int by_rows = (int)((M + 63) / 64);
+  const int col_tiles = ceil_div(N, 128);
+  int slices = (8 * sm_count() + col_tiles - 1) / col_tiles;
+  const int by_rows = (int)((M + 255) / 256);
   if (slices > by_rows) slices = by_rows;
   if (slices < 1) slices = 1;
   if (slices > 65535) slices = 65535;

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .csr import BagStore
 
 Draw = Tuple[Sequence[torch.Tensor], Sequence[torch.Tensor], Sequence[torch.Tensor]]  # (actions, lams, perms) per view
@@ -29,8 +29,9 @@ def draw_patch_step(B: int, K: int, alpha: float, device, actions: Optional[List
     return actions, lams, perms
 
 
-def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dtype, slot_bag=None) -> List[torch.Tensor]:
-    """Both views of a patch-step through one packer pass: ``2B`` output slots over ``B`` bags."""
+def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dtype, slot_bag=None) -> torch.Tensor:
+    """Both views of a patch-step through one packer pass: ``2B`` output slots over ``B`` bags.  Returns the
+    ``[2B, feat_size, D]`` tensor; rows ``[0,B)`` are view 0, ``[B,2B)`` view 1."""
     actions, lams, perms = draw
     B = store.num_bags
     if slot_bag is None:
@@ -38,8 +39,20 @@ def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dty
     act = torch.cat([a.to(torch.float32) for a in actions], 0)
     lam = torch.cat([l.reshape(-1) for l in lams], 0)
     perm = torch.cat([perms[0].reshape(-1), perms[1].reshape(-1) + B], 0)     # each view mixes within itself
-    x = store.pack(act, feat_size, lam, perm, out_dtype, slot_bag)
-    return [x[:B], x[B:]]
+    return store.pack(act, feat_size, lam, perm, out_dtype, slot_bag)
+
+
+def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
+    """``model(x_views)`` of train_MuRCL.py:242,271 -> ``(outputs, detached states)``.  Bags are independent, so
+    when the model is the CL wrapper all views go through its encoder in ONE batched call (half the launches,
+    twice the rows per GEMM) and are split afterwards; any other model is called with the list of views."""
+    B = x_all.shape[0] // n_views
+    enc = getattr(model, "encoder", None)
+    if enc is not None:
+        out = enc(x_all)[0]
+        outs = [out[v * B:(v + 1) * B] for v in range(n_views)]
+        return outs, [o.detach() for o in outs]
+    return model([x_all[v * B:(v + 1) * B] for v in range(n_views)])
 
 
 def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_size: int = 1024, alpha: float = 0.9,
@@ -64,8 +77,8 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
             if stage == 3 and t >= 1:
                 actions = [ppo.select_action(s, m, restart_batch=(t == 1)) for s, m in zip(states, memories)]
             draw = draw_patch_step(B, K, alpha, dev, actions)
-        x_views = pack_views(store, draw, feat_size, dt, slot_bag)
-        outputs, states = model(x_views)
+        x_all = pack_views(store, draw, feat_size, dt, slot_bag)
+        outputs, states = encode_views(model, x_all)
         outputs = [fc(o, restart=(t == 0)) for o in outputs]
         loss = criterion(outputs[0], outputs[1])
         losses.append(loss)
@@ -82,3 +95,34 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         for m in memories:
             m.clear_memory()
     return total.detach(), [l.detach() for l in losses]
+
+
+class GraphedStep:
+    """Captures ``step_fn`` (zero_grad + pretrain_step + optimiser) into one CUDA graph and replays it.
+
+    One optimiser step issues ~700 short kernels; launched from Python they are CPU-bound (~40 us each).  All of
+    them - the C-ABI kernels, torch's RNG draws, autograd's accumulations, Adam(capturable=True), NCCL
+    collectives - are stream-ordered, so the whole step replays as a single graph launch.  The bag store and
+    every tensor the step touches keep fixed addresses (torch's graph-private pool)."""
+
+    def __init__(self, step_fn, warmup: int = 2, pool=None):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step_fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph, pool=pool):
+            self.loss = step_fn()
+        self.launches = _lib.launch_count() - n0          # libmurcl_b200 kernels per replay
+
+    def pool(self):
+        return self.graph.pool()
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss
