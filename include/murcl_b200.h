@@ -90,10 +90,12 @@ int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, i
 /* dx[M,K] = dy[M,N] . w[N,K]; when relu_src != NULL (shape [M,K], storage `dtype`) the result is
  * multiplied by (relu_src > 0), i.e. it is the gradient w.r.t. the previous layer's
  * pre-activation.  When row_scale != NULL: dx += row_scale[m] * row_vec[row_seg[m]][k] before
- * masking (the direct softmax-pool term, see murcl_pool_bwd). */
+ * masking (the direct softmax-pool term, see murcl_pool_bwd).  When col_sum != NULL (fp32 [K], zeroed by
+ * the caller) the column sums of the stored result are accumulated into it: dx is the next layer's dZ, so this
+ * is that layer's bias gradient, produced without another pass over dx. */
 int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K,
                            const void* relu_src, const float* row_scale, const float* row_vec,
-                           const int32_t* row_seg, int dtype, int backend, void* stream);
+                           const int32_t* row_seg, float* col_sum, int dtype, int backend, void* stream);
 
 /* dw[N,K] (fp32) = dy[M,N]^T . x[M,K], db[N] (fp32, may be NULL) = column sums of dy.
  * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats. */
@@ -133,10 +135,11 @@ int murcl_pool_bwd_direct(const float* p, const float* dM, const int32_t* row_se
                           int dtype, void* dh, int accumulate, void* stream);
 
 /* Backward through the score: given ds[N] and the saved activations uv, overwrites uv with the
- * gradient w.r.t. the pre-activations (tanh' / sigmoid' applied) and accumulates dwc[D], dbc[1]
- * (fp32, must be zeroed by the caller). */
-int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, int64_t N, int D,
-                         int gated, int dtype, void* stream);
+ * gradient w.r.t. the pre-activations (tanh' / sigmoid' applied) and accumulates dwc[D], dbc[1] and - when
+ * dpre_colsum != NULL - the column sums of the written gradient ([D] or [2D]: the bias gradient of the
+ * attention projection).  All three are fp32 and must be zeroed by the caller. */
+int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, float* dpre_colsum,
+                         int64_t N, int D, int gated, int dtype, void* stream);
 
 /* ---- (3) segmented reductions: clam.py:103-132 (top-k instance loss), dsmil.py:71-78 ---- */
 

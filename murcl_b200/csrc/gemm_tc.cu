@@ -50,6 +50,7 @@ struct Params {
   const float* row_scale;
   const float* row_vec;
   const int32_t* row_seg;
+  float* col_sum;     // EPI_DGRAD: accumulated column sums of the stored result (may be null)
   int splits;
   int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
   int64_t split_stride;
@@ -187,7 +188,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    BN * 4 /*column-sum accumulator*/;
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
@@ -207,6 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto mask_bar = [&](int w) { return bars + 8u * (2 * C::STAGES + 4 + w); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 8);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* colacc = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw));     // [BN] per-CTA column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -328,6 +331,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int SLAB_COLS = 128 / (int)sizeof(TOUT);      // 64 bf16 or 32 fp32 columns = 128 B per row
     int as = 0;
     uint32_t aph = 0, mph = 0;
+    const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr;
+    const bool want_colsum = (EPI == EPI_DGRAD) && sizeof(TOUT) == 2 && p.col_sum != nullptr;
+    int acc_nb = -1;
+    const int etid = threadIdx.x - 64;                      // 0..127 among the epilogue threads
+    auto flush_colacc = [&](int nb_flush) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // all four epilogue warps have added their slabs
+      for (int i = etid; i < BN; i += 128) {
+        const int col = nb_flush * BN + i;
+        const float sum = colacc[i];
+        if (col < p.N && sum != 0.f) atomicAdd(p.col_sum + col, sum);
+        colacc[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    if (want_colsum) {
+      for (int i = etid; i < BN; i += 128) colacc[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (has_mask && lane == 0) {                            // mask slab of the first work item of this warp
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mb, nb, sp;
+        tile_coords(t, mb, nb, sp);
+        if ((int64_t)mb * BLOCK_M + quarter * 32 < p.M) {
+          mbar_expect_tx(mask_bar(quarter), SLAB_BYTES);
+          tma_load_2d(mask_slab, &map_mask, mask_bar(quarter), nb * BN, mb * BLOCK_M + quarter * 32);
+          break;
+        }
+      }
+    }
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int mb, nb, sp;
       tile_coords(t, mb, nb, sp);
@@ -360,15 +392,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           rs = p.row_scale[row];
           rv = p.row_vec + (int64_t)p.row_seg[row] * p.N;
         }
-        const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr;
+        if (want_colsum && nb != acc_nb) {                 // new column tile: flush the CTA's partial sums
+          if (acc_nb >= 0) flush_colacc(acc_nb);
+          acc_nb = nb;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += SLAB_COLS) {
           const int col0 = n0 + c0;
           if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this slab is in range
-          if (has_mask && lane == 0) {                     // fetch the matching slab of the ReLU source
-            mbar_expect_tx(mask_bar(quarter), SLAB_BYTES);
-            tma_load_2d(mask_slab, &map_mask, mask_bar(quarter), col0, (int)row0);
-          }
           float v[SLAB_COLS];
 #pragma unroll
           for (int j = 0; j < SLAB_COLS / 32; ++j) {
@@ -400,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (has_mask) {
-              mbar_wait(mask_bar(quarter), mph);
+              mbar_wait(mask_bar(quarter), mph);            // slab fetched ahead (issued one slab earlier)
               mph ^= 1u;
 #pragma unroll
               for (int c = 0; c < 8; ++c) {                 // bf16 mask slab: 8 chunks of 8 columns per row
@@ -411,6 +442,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   const float2 f = __bfloat1622float2(h[j]);
                   if (!(f.x > 0.f)) v[8 * c + 2 * j] = 0.f;
                   if (!(f.y > 0.f)) v[8 * c + 2 * j + 1] = 0.f;
+                }
+              }
+              __syncwarp();                                 // every lane is done with the mask slab
+              if (lane == 0) {                              // prefetch the next slab this warp will process
+                int64_t nt = t;
+                int nc0 = c0 + SLAB_COLS;
+                bool found = (nc0 < BN) && (n0 + nc0 < p.N);
+                while (!found) {
+                  nt += gridDim.x;
+                  if (nt >= total_tiles) break;
+                  nc0 = 0;
+                  int mb2, nb2, sp2;
+                  tile_coords(nt, mb2, nb2, sp2);
+                  found = (int64_t)mb2 * BLOCK_M + quarter * 32 < p.M;
+                }
+                if (found) {
+                  int mb2, nb2, sp2;
+                  tile_coords(nt, mb2, nb2, sp2);
+                  mbar_expect_tx(mask_bar(quarter), SLAB_BYTES);
+                  tma_load_2d(mask_slab, &map_mask, mask_bar(quarter), nb2 * BN + nc0, mb2 * BLOCK_M + quarter * 32);
                 }
               }
             }
@@ -437,6 +488,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_2d(&map_c, out_slab, col0, (int)row0);   // rows >= M and cols >= N are clipped by the tensor map
             bulk_commit();
           }
+          if (want_colsum) {
+            // column sums of the slab as stored (bf16-rounded): lane owns the 4-byte word `lane` of every row
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              uint32_t wv;
+              const uint32_t addr = out_slab + (uint32_t)r * 128u + (((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) | (((uint32_t)lane & 3u) << 2));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(addr) : "memory");
+              const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&wv));
+              s0 += f.x;
+              s1 += f.y;
+            }
+            atomicAdd(&colacc[c0 + 2 * lane], s0);
+            atomicAdd(&colacc[c0 + 2 * lane + 1], s1);
+          }
         }
       }
       tcgen05_fence_before();
@@ -444,6 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar(as));          // this warp has drained its quarter of the accumulator
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
+    if (want_colsum && acc_nb >= 0) flush_colacc(acc_nb);
     if (EPI != EPI_SPLIT && lane == 0) bulk_wait_all();     // all bulk stores of this warp have completed
   }
 
@@ -576,7 +643,8 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
 }
 
 int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
-                        const float* row_scale, const float* row_vec, const int32_t* row_seg, cudaStream_t st) {
+                        const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum,
+                        cudaStream_t st) {
   if (!aligned16(dy) || !aligned16(w) || !aligned16(dx) || (relu_src && !aligned16(relu_src))) {
     set_error("linear_bwd_input(tcgen05): operands must be 16-byte aligned");
     return MURCL_EINVAL;
@@ -591,7 +659,7 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   Params p{};
   p.M = M; p.N = K; p.K = N; p.ldc = K; p.C = dx;
   p.relu_src = static_cast<const __nv_bfloat16*>(relu_src);
-  p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg;
+  p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.col_sum = col_sum;
   p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
   CUtensorMap mc, mm;

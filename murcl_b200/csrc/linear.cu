@@ -14,7 +14,7 @@ bool tc_bwd_input_supported(int64_t M, int N, int K, int dtype);
 bool tc_bwd_weight_supported(int64_t M, int N, int K, int dtype);
 int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, cudaStream_t);
 int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                        const int32_t*, cudaStream_t);
+                        const int32_t*, float*, cudaStream_t);
 int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
 int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t);
 
@@ -45,8 +45,8 @@ int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, i
 }
 
 int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
-                           const float* row_scale, const float* row_vec, const int32_t* row_seg, int dtype, int backend,
-                           void* stream) {
+                           const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum, int dtype,
+                           int backend, void* stream) {
   MURCL_REQUIRE(dy && w && dx, "linear_bwd_input: null pointer");
   MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_input: bad shape");
   MURCL_REQUIRE(valid_dtype(dtype), "linear_bwd_input: bad dtype");
@@ -59,8 +59,10 @@ int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, i
     return MURCL_EUNSUPPORTED;
   }
   if (backend != MURCL_GEMM_SIMT && tc_ok)
-    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, as_stream(stream));
-  return simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, dtype, as_stream(stream));
+    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, col_sum, as_stream(stream));
+  int rc = simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, dtype, as_stream(stream));
+  if (rc != MURCL_OK || col_sum == nullptr) return rc;
+  return colsum_impl(dx, M, K, dtype, col_sum, as_stream(stream));       // same sums, separate pass
 }
 
 int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K) {

@@ -133,6 +133,70 @@ __global__ void __launch_bounds__(256) seg_wsum_partial_kernel(const float* __re
   }
 }
 
+// Fast path: 16-byte loads (8 bf16 / 4 fp32 columns per thread), L/VEC column threads x 256/(L/VEC) row groups,
+// four rows in flight per thread.  Requires L % VEC == 0 and L/VEC <= 256.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) seg_wsum_partial_vec_kernel(const float* __restrict__ p, const T* __restrict__ h,
+                                                                   const int64_t* __restrict__ offsets, int L,
+                                                                   float* __restrict__ ws) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  extern __shared__ float sm[];            // [rows_par][C][L]
+  const int b = blockIdx.x, j = blockIdx.y, S = gridDim.y;
+  const int64_t lo = offsets[b], hi = offsets[b + 1];
+  const int64_t len = hi - lo;
+  const int64_t r0 = lo + len * j / S, r1 = lo + len * (j + 1) / S;
+  const int col_threads = L / VEC;
+  const int rows_par = blockDim.x / col_threads;
+  const int ct = threadIdx.x % col_threads, rg = threadIdx.x / col_threads;
+  const int col = ct * VEC;
+  float acc[C][VEC];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
+  auto load_row = [&](int64_t n, float (&x)[VEC]) {
+    const float4 a = load4(h + n * L + col);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    if (VEC == 8) {
+      const float4 b4 = load4(h + n * L + col + 4);
+      x[4 % VEC] = b4.x; x[5 % VEC] = b4.y; x[6 % VEC] = b4.z; x[7 % VEC] = b4.w;
+    }
+  };
+  auto fma_row = [&](int64_t n, const float (&x)[VEC]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float w = p[n * C + c];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(w, x[v], acc[c][v]);
+    }
+  };
+  if (rg < rows_par) {
+    int64_t n = r0 + rg;
+    const int64_t step = rows_par;
+    for (; n + 3 * step < r1; n += 4 * step) {
+      float x0[VEC], x1[VEC], x2[VEC], x3[VEC];
+      load_row(n, x0); load_row(n + step, x1); load_row(n + 2 * step, x2); load_row(n + 3 * step, x3);
+      fma_row(n, x0); fma_row(n + step, x1); fma_row(n + 2 * step, x2); fma_row(n + 3 * step, x3);
+    }
+    for (; n < r1; n += step) {
+      float x0[VEC];
+      load_row(n, x0);
+      fma_row(n, x0);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) sm[((int64_t)rg * C + c) * L + col + v] = acc[c][v];
+  }
+  __syncthreads();
+  float* out = ws + ((int64_t)b * S + j) * C * L;
+  for (int i = threadIdx.x; i < C * L; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < rows_par; ++r) t += sm[(int64_t)r * C * L + i];
+    out[i] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) seg_wsum_final_kernel(const float* __restrict__ ws, int S, int64_t per_bag,
                                                              float* __restrict__ out, int64_t total) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,6 +276,52 @@ __global__ void __launch_bounds__(256) pool_bwd_scores_kernel(const float* __res
   }
 }
 
+// Fast path for one score column (ABMIL / CLAM): 16-byte loads, two rows of a warp in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) pool_bwd_scores_c1_kernel(const float* __restrict__ p, const T* __restrict__ h,
+                                                                 const float* __restrict__ dM, const float* __restrict__ kbuf,
+                                                                 const int32_t* __restrict__ row_seg, int64_t n_rows, int L,
+                                                                 float* __restrict__ ds) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  if (row0 >= n_rows) return;
+  const bool two = row0 + 1 < n_rows;
+  const int b0 = row_seg[row0], b1 = two ? row_seg[row0 + 1] : b0;
+  float a0 = 0.f, a1 = 0.f;
+  for (int d = lane * VEC; d < L; d += 32 * VEC) {
+    float x0[8], x1[8], g0[8], g1[8];
+    {
+      const float4 u = load4(h + row0 * L + d);
+      x0[0] = u.x; x0[1] = u.y; x0[2] = u.z; x0[3] = u.w;
+      if (VEC == 8) { const float4 v = load4(h + row0 * L + d + 4); x0[4] = v.x; x0[5] = v.y; x0[6] = v.z; x0[7] = v.w; }
+    }
+    if (two) {
+      const float4 u = load4(h + (row0 + 1) * L + d);
+      x1[0] = u.x; x1[1] = u.y; x1[2] = u.z; x1[3] = u.w;
+      if (VEC == 8) { const float4 v = load4(h + (row0 + 1) * L + d + 4); x1[4] = v.x; x1[5] = v.y; x1[6] = v.z; x1[7] = v.w; }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      const float4 q0 = *reinterpret_cast<const float4*>(dM + (int64_t)b0 * L + d + i);
+      g0[i] = q0.x; g0[i + 1] = q0.y; g0[i + 2] = q0.z; g0[i + 3] = q0.w;
+      const float4 q1 = *reinterpret_cast<const float4*>(dM + (int64_t)b1 * L + d + i);
+      g1[i] = q1.x; g1[i + 1] = q1.y; g1[i + 2] = q1.z; g1[i + 3] = q1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      a0 = fmaf(g0[i], x0[i], a0);
+      if (two) a1 = fmaf(g1[i], x1[i], a1);
+    }
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if (lane == 0) {
+    ds[row0] = p[row0] * (a0 - kbuf[b0]);
+    if (two) ds[row0 + 1] = p[row0 + 1] * (a1 - kbuf[b1]);
+  }
+}
+
 // dh[n,:] (+)= sum_c p[n,c] * dM[b,c,:]   (direct term of the pooling backward)
 template <typename T>
 __global__ void __launch_bounds__(256) pool_bwd_direct_kernel(const float* __restrict__ p, const float* __restrict__ dM,
@@ -229,54 +339,110 @@ __global__ void __launch_bounds__(256) pool_bwd_direct_kernel(const float* __res
 }
 
 // ---- backward through the score projection tail -------------------------------------------------
+// Lane owns columns 4*lane + 128*i (8/16-byte accesses).  Besides d(pre-activation) (written over uv) the kernel
+// accumulates dwc[D] and, when dpre_colsum != NULL, the column sums of what it writes (= the bias gradient of the
+// attention projection), so no separate pass over the [N, D|2D] tensor is needed.
 template <typename T, bool GATED>
 __global__ void __launch_bounds__(256) attn_score_bwd_kernel(T* __restrict__ uv, const float* __restrict__ wc,
                                                              const float* __restrict__ ds, float* __restrict__ dwc,
-                                                             float* __restrict__ dbc, int64_t N, int D,
-                                                             int rows_per_cta) {
-  extern __shared__ float sm[];   // [D] CTA partial of dwc
+                                                             float* __restrict__ dbc, float* __restrict__ dpre_colsum,
+                                                             int64_t N, int D, int rows_per_cta) {
+  extern __shared__ float sm[];   // [D] dwc partial, [2D] column sums partial
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) sm[d] = 0.f;
-  __syncthreads();
   const int ld = GATED ? 2 * D : D;
+  for (int d = threadIdx.x; d < D + ld; d += blockDim.x) sm[d] = 0.f;
+  __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(N, r0 + rows_per_cta);
   float dsum = 0.f;
-  // Each lane owns columns d = lane + 32*i, so its dwc partials stay in registers across rows.
-  constexpr int MAXI = 16;   // D <= 512
-  float part[MAXI];
+  constexpr int MAXI = 4;         // D <= 512
+  float part[MAXI][4], csa[MAXI][4], csb[MAXI][4];
 #pragma unroll
-  for (int i = 0; i < MAXI; ++i) part[i] = 0.f;
+  for (int i = 0; i < MAXI; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[i][j] = csa[i][j] = csb[i][j] = 0.f;
   for (int64_t row = r0 + w; row < r1; row += nw) {
     const float g = ds[row];
     if (lane == 0) dsum += g;
     T* r = uv + row * ld;
 #pragma unroll
     for (int i = 0; i < MAXI; ++i) {
-      const int d = lane + 32 * i;
+      const int d = 4 * lane + 128 * i;
       if (d < D) {
-        const float u = Store<T>::load(r + d);
-        const float gw = g * wc[d];
+        const float4 u4 = load4(r + d);
+        const float4 w4 = *reinterpret_cast<const float4*>(wc + d);
+        const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        float oa[4], ob[4];
         if (GATED) {
-          const float v = Store<T>::load(r + D + d);
-          part[i] = fmaf(g, u * v, part[i]);
-          Store<T>::store(r + d, gw * v * (1.f - u * u));
-          Store<T>::store(r + D + d, gw * u * v * (1.f - v));
+          const float4 v4 = load4(r + D + d);
+          const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float gw = g * ww[j];
+            part[i][j] = fmaf(g, u[j] * v[j], part[i][j]);
+            oa[j] = gw * v[j] * (1.f - u[j] * u[j]);
+            ob[j] = gw * u[j] * v[j] * (1.f - v[j]);
+            csb[i][j] += ob[j];
+          }
+          store4(r + D + d, make_float4(ob[0], ob[1], ob[2], ob[3]));
         } else {
-          part[i] = fmaf(g, u, part[i]);
-          Store<T>::store(r + d, gw * (1.f - u * u));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            part[i][j] = fmaf(g, u[j], part[i][j]);
+            oa[j] = g * ww[j] * (1.f - u[j] * u[j]);
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) csa[i][j] += oa[j];
+        store4(r + d, make_float4(oa[0], oa[1], oa[2], oa[3]));
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < MAXI; ++i) {
-    const int d = lane + 32 * i;
-    if (d < D) atomicAdd(&sm[d], part[i]);
+    const int d = 4 * lane + 128 * i;
+    if (d < D) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sm[d + j], part[i][j]);
+        atomicAdd(&sm[D + d + j], csa[i][j]);
+        if (GATED) atomicAdd(&sm[2 * D + d + j], csb[i][j]);
+      }
+    }
   }
   __syncthreads();
   for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(&dwc[d], sm[d]);
+  if (dpre_colsum)
+    for (int d = threadIdx.x; d < ld; d += blockDim.x) atomicAdd(&dpre_colsum[d], sm[D + d]);
   if (dbc && lane == 0 && dsum != 0.f) atomicAdd(dbc, dsum);
+}
+
+// Any-D fallback (D not a multiple of 4 or > 512): one column per lane step, no fused column sums.
+template <typename T, bool GATED>
+__global__ void __launch_bounds__(256) attn_score_bwd_generic_kernel(T* __restrict__ uv, const float* __restrict__ wc,
+                                                                     const float* __restrict__ ds, float* __restrict__ dwc,
+                                                                     float* __restrict__ dbc, int64_t N, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int ld = GATED ? 2 * D : D;
+  const float g = ds[row];
+  T* r = uv + row * ld;
+  for (int d = lane; d < D; d += 32) {
+    const float u = Store<T>::load(r + d);
+    const float gw = g * wc[d];
+    if (GATED) {
+      const float v = Store<T>::load(r + D + d);
+      atomicAdd(&dwc[d], g * u * v);
+      Store<T>::store(r + d, gw * v * (1.f - u * u));
+      Store<T>::store(r + D + d, gw * u * v * (1.f - v));
+    } else {
+      atomicAdd(&dwc[d], g * u);
+      Store<T>::store(r + d, gw * (1.f - u * u));
+    }
+  }
+  if (dbc && lane == 0) atomicAdd(dbc, g);
 }
 
 }  // namespace murcl
@@ -326,12 +492,26 @@ int murcl_seg_wsum(const float* p, const void* h, const int64_t* offsets, int64_
   const int S = wsum_splits(n_rows, B);
   MURCL_REQUIRE(S <= 65535, "seg_wsum: too many splits");
   cudaStream_t st = as_stream(stream);
-  const size_t smem = sizeof(float) * 256 * 4;
   dim3 grid(B, S);
-  if (dtype == MURCL_F32) seg_wsum_partial_kernel<float><<<grid, 256, smem, st>>>(p, (const float*)h, offsets, C, L, workspace);
-  else if (dtype == MURCL_BF16)
-    seg_wsum_partial_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(p, (const __nv_bfloat16*)h, offsets, C, L, workspace);
-  else MURCL_REQUIRE(false, "seg_wsum: bad dtype %d", dtype);
+  MURCL_REQUIRE(dtype == MURCL_F32 || dtype == MURCL_BF16, "seg_wsum: bad dtype %d", dtype);
+  const int vec = dtype == MURCL_BF16 ? 8 : 4;
+  const bool fast = (L % vec == 0) && (L / vec <= 256) && (C == 1 || C == 2) &&
+                    ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
+  if (fast) {
+    const int rows_par = 256 / (L / vec);
+    const size_t smem = sizeof(float) * (size_t)rows_par * C * L;          // <= 256/ (L/vec) * C * L floats <= 16 KB * C
+    if (dtype == MURCL_BF16) {
+      if (C == 1) seg_wsum_partial_vec_kernel<__nv_bfloat16, 1><<<grid, 256, smem, st>>>(p, (const __nv_bfloat16*)h, offsets, L, workspace);
+      else seg_wsum_partial_vec_kernel<__nv_bfloat16, 2><<<grid, 256, smem, st>>>(p, (const __nv_bfloat16*)h, offsets, L, workspace);
+    } else {
+      if (C == 1) seg_wsum_partial_vec_kernel<float, 1><<<grid, 256, smem, st>>>(p, (const float*)h, offsets, L, workspace);
+      else seg_wsum_partial_vec_kernel<float, 2><<<grid, 256, smem, st>>>(p, (const float*)h, offsets, L, workspace);
+    }
+  } else {
+    const size_t smem = sizeof(float) * 256 * 4;
+    if (dtype == MURCL_F32) seg_wsum_partial_kernel<float><<<grid, 256, smem, st>>>(p, (const float*)h, offsets, C, L, workspace);
+    else seg_wsum_partial_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(p, (const __nv_bfloat16*)h, offsets, C, L, workspace);
+  }
   int rc = check_launch("seg_wsum_partial_kernel");
   if (rc != MURCL_OK) return rc;
   const int64_t total = (int64_t)B * C * L;
@@ -349,12 +529,21 @@ int murcl_pool_bwd_scores(const float* p, const void* h, const float* dM, const 
   pool_k_kernel<<<dim3(B, C), 128, 0, st>>>(dM, M, offsets, C, L, inv_sqrt_n, kbuf);
   int rc = check_launch("pool_k_kernel");
   if (rc != MURCL_OK) return rc;
+  MURCL_REQUIRE(dtype == MURCL_F32 || dtype == MURCL_BF16, "pool_bwd_scores: bad dtype %d", dtype);
+  const int vec = dtype == MURCL_BF16 ? 8 : 4;
+  if (C == 1 && L % vec == 0 && ((reinterpret_cast<uintptr_t>(h) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dM) & 15) == 0)) {
+    const int grid = ceil_div(n_rows, 16);
+    if (dtype == MURCL_F32)
+      pool_bwd_scores_c1_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)h, dM, kbuf, row_seg, n_rows, L, ds);
+    else
+      pool_bwd_scores_c1_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)h, dM, kbuf, row_seg, n_rows, L, ds);
+    return check_launch("pool_bwd_scores_c1_kernel");
+  }
   const int grid = ceil_div(n_rows, 8);
   if (dtype == MURCL_F32)
     pool_bwd_scores_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)h, dM, kbuf, row_seg, n_rows, C, L, ds);
-  else if (dtype == MURCL_BF16)
+  else
     pool_bwd_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)h, dM, kbuf, row_seg, n_rows, C, L, ds);
-  else MURCL_REQUIRE(false, "pool_bwd_scores: bad dtype %d", dtype);
   return check_launch("pool_bwd_scores_kernel");
 }
 
@@ -372,23 +561,39 @@ int murcl_pool_bwd_direct(const float* p, const float* dM, const int32_t* row_se
   return check_launch("pool_bwd_direct_kernel");
 }
 
-int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, int64_t N, int D, int gated,
-                         int dtype, void* stream) {
+int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, float* dpre_colsum, int64_t N,
+                         int D, int gated, int dtype, void* stream) {
   MURCL_REQUIRE(uv && wc && ds && dwc, "attn_score_bwd: null pointer");
-  MURCL_REQUIRE(N >= 0 && D > 0 && D <= 512, "attn_score_bwd: D=%d out of range (<= 512)", D);
+  MURCL_REQUIRE(N >= 0 && D > 0, "attn_score_bwd: bad shape");
+  MURCL_REQUIRE(dtype == MURCL_F32 || dtype == MURCL_BF16, "attn_score_bwd: bad dtype %d", dtype);
   if (N == 0) return MURCL_OK;
-  const int rows_per_cta = 256;
-  const int grid = ceil_div(N, rows_per_cta);
-  const size_t smem = sizeof(float) * D;
   cudaStream_t st = as_stream(stream);
+  const int ld = gated ? 2 * D : D;
+  const bool fast = (D % 4 == 0) && D <= 512 && ((reinterpret_cast<uintptr_t>(uv) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(wc) & 15) == 0);
+  if (!fast) {
+    const int grid = ceil_div(N, 8);
+    if (dtype == MURCL_F32) {
+      if (gated) attn_score_bwd_generic_kernel<float, true><<<grid, 256, 0, st>>>((float*)uv, wc, ds, dwc, dbc, N, D);
+      else attn_score_bwd_generic_kernel<float, false><<<grid, 256, 0, st>>>((float*)uv, wc, ds, dwc, dbc, N, D);
+    } else {
+      if (gated) attn_score_bwd_generic_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D);
+      else attn_score_bwd_generic_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D);
+    }
+    int rc = check_launch("attn_score_bwd_generic_kernel");
+    if (rc != MURCL_OK || dpre_colsum == nullptr) return rc;
+    return murcl_colsum(uv, N, ld, dtype, dpre_colsum, stream);
+  }
+  int rows_per_cta = (int)((N + 4 * sm_count() - 1) / (4 * sm_count()));
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  const int grid = ceil_div(N, rows_per_cta);
+  const size_t smem = sizeof(float) * (size_t)(D + ld);
   if (dtype == MURCL_F32) {
-    if (gated) attn_score_bwd_kernel<float, true><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, N, D, rows_per_cta);
-    else attn_score_bwd_kernel<float, false><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, N, D, rows_per_cta);
-  } else if (dtype == MURCL_BF16) {
-    if (gated) attn_score_bwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D, rows_per_cta);
-    else attn_score_bwd_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D, rows_per_cta);
+    if (gated) attn_score_bwd_kernel<float, true><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
+    else attn_score_bwd_kernel<float, false><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
   } else {
-    MURCL_REQUIRE(false, "attn_score_bwd: bad dtype %d", dtype);
+    if (gated) attn_score_bwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
+    else attn_score_bwd_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
   }
   return check_launch("attn_score_bwd_kernel");
 }

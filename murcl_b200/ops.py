@@ -135,7 +135,7 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
     return y
 
 
-def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None):
+def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None, col_sum=None):
     _chk(dy, "linear_bwd_input.dy"); _chk(w, "linear_bwd_input.w")
     if dy.dtype != w.dtype:
         raise MurclError(f"linear_bwd_input: dy is {dy.dtype} but w is {w.dtype}")
@@ -148,7 +148,8 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
     with _Timed("linear_bwd_input", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
-                                                 _p(row_seg), _dt(dy), _backend(), _s()), "murcl_linear_bwd_input")
+                                                 _p(row_seg), _p(col_sum), _dt(dy), _backend(), _s()),
+              "murcl_linear_bwd_input")
     return dx
 
 
@@ -226,12 +227,15 @@ def pool_bwd_direct(p, dM, row_seg, C, L, out, accumulate):
 
 
 def attn_score_bwd_(uv, wc, ds, D, gated):
-    """In place: uv becomes the gradient w.r.t. the pre-activations.  Returns (dwc [D], dbc [1])."""
-    dwc = torch.zeros((D,), device=uv.device, dtype=torch.float32)
-    dbc = torch.zeros((1,), device=uv.device, dtype=torch.float32)
-    check(_lib.load().murcl_attn_score_bwd(_p(uv), _p(wc), _p(ds), _p(dwc), _p(dbc), uv.shape[0], D, int(gated), _dt(uv),
-                                           _s()), "murcl_attn_score_bwd")
-    return dwc, dbc
+    """In place: uv becomes the gradient w.r.t. the pre-activations.  Returns (dwc [D], dbc [1], column sums of the
+    new uv [D | 2D] = bias gradient of the attention projection)."""
+    buf = torch.zeros((D + 1 + uv.shape[1],), device=uv.device, dtype=torch.float32)      # one memset for all three
+    dwc, dbc, dpre = buf[:D], buf[D:D + 1], buf[D + 1:]
+    if dpre.data_ptr() % 16:
+        dpre = torch.zeros((uv.shape[1],), device=uv.device, dtype=torch.float32)
+    check(_lib.load().murcl_attn_score_bwd(_p(uv), _p(wc), _p(ds), _p(dwc), _p(dbc), _p(dpre), uv.shape[0], D, int(gated),
+                                           _dt(uv), _s()), "murcl_attn_score_bwd")
+    return dwc, dbc, dpre
 
 
 def seg_topk_ends(p, offsets, B, k):
@@ -465,12 +469,17 @@ class _MILAggregate(torch.autograd.Function):
         L = H.shape[1]
         dM = dM.contiguous().float()
         ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, meta["inv_sqrt_n"])
-        dwc, dbc = attn_score_bwd_(uv, wc_f, ds, D, gated)          # uv now holds d(pre-activation)
-        dwab, dbab = linear_bwd_weight(uv, H)
+        dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated)    # uv now holds d(pre-activation)
+        dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
         relu_src = H if n_enc > 0 else None
-        dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg)     # + p_n dM[b] direct term, ReLU mask
-        d_inst_w = d_inst_b = None
         inst = meta.get("inst")
+        # bias gradients ride along as fused column sums of each dZ (the instance-loss scatter below changes dZ
+        # after the fact, so that case takes the separate column-sum pass)
+        fuse_db = n_enc > 0 and inst is None
+        db_next = torch.zeros((n_enc, L), device=uv.device, dtype=torch.float32) if fuse_db else None
+        dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg,
+                              col_sum=db_next[n_enc - 1] if fuse_db else None)     # + p_n dM[b] direct term, ReLU mask
+        d_inst_w = d_inst_b = None
         if inst is not None:
             idx, rows, dlogits, iw = rest
             G = len(inst["groups"])
@@ -486,10 +495,12 @@ class _MILAggregate(torch.autograd.Function):
             scatter_add_rows_(dz, idx, drows.contiguous())
         grads_enc = []
         for l in range(n_enc, 0, -1):
-            dw, db = linear_bwd_weight(dz, hs[l - 1])
+            dw, db = linear_bwd_weight(dz, hs[l - 1], want_bias=not fuse_db)
+            if fuse_db:
+                db = db_next[l - 1]
             grads_enc = [dw, db] + grads_enc
             if l > 1:
-                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1])
+                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1], col_sum=db_next[l - 2] if fuse_db else None)
             elif ctx.needs_input_grad[0]:
                 dz = linear_bwd_input(dz, enc_w[0])
         dx = None

@@ -151,9 +151,11 @@ def test_linear_simt(M, N, K):
     try:
         y = ops.linear_fwd(xd, wd, bd, ops.ACT_RELU)
         assert_close(y, y_ref.float(), 2e-6, "fwd")
-        dx = ops.linear_bwd_input(dyd, wd, mask_src.to(DEV))
+        cs = torch.zeros(K, device=DEV)
+        dx = ops.linear_bwd_input(dyd, wd, mask_src.to(DEV), col_sum=cs)
         dx_ref = (dy.double() @ w.double()) * (mask_src > 0)
         assert_close(dx, dx_ref.float(), 2e-6, "bwd_input")
+        assert_close(cs, dx_ref.sum(0).float(), 1e-5, "column sums")
         dw, db = ops.linear_bwd_weight(dyd, xd)
         assert_close(dw, (dy.double().t() @ x.double()).float(), 5e-6, "bwd_weight")
         assert_close(db, dy.double().sum(0).float(), 5e-6, "bias grad")

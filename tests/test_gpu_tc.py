@@ -70,6 +70,11 @@ def test_tc_input_grad(M, N, K):
     dx2 = ops.linear_bwd_input(dy.to(DEV), w.to(DEV), relu_src.to(DEV), rs.to(DEV), rv.to(DEV), seg.to(DEV))
     assert_close(dx2.float(), ref2.float(), 4e-3, "row term + mask")
     assert bool(((dx2 == 0) | (relu_src.to(DEV) > 0)).all())
+    # fused column sums of the stored (bf16-rounded) result = bias gradient of the next layer
+    cs = torch.zeros(K, device=DEV)
+    dx3 = ops.linear_bwd_input(dy.to(DEV), w.to(DEV), relu_src.to(DEV), rs.to(DEV), rv.to(DEV), seg.to(DEV), col_sum=cs)
+    assert torch.equal(dx3, dx2)
+    assert_close(cs, dx3.double().sum(0).float(), 2e-5, "fused column sums")
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES + [(131072, 512, 512), (20000, 128, 512)])
