@@ -32,7 +32,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;           // two per TMEM lane quarter, splitting the columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int SMEM_BUDGET = 224 * 1024;
 
@@ -180,12 +181,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a
 }
 
 constexpr int SLAB_BYTES = 32 * 128;        // one epilogue warp's staging slab: 32 rows x 128 B
-constexpr int STAGING_BYTES = 4 * SLAB_BYTES * 2;   // per warp: output slab + mask slab
 
-template <int BN>
+template <int BN, int EPI>
 struct Cfg {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SLABS_PER_WARP = (EPI == 1) ? 2 : 1;          // output slab (+ ReLU-mask slab for the input grad)
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: powers of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
@@ -196,18 +198,18 @@ template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_mask, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t staging = tiles + C::STAGES * C::STAGE_BYTES;        // 1024 B aligned (stage sizes are multiples of 1024)
-  const uint32_t bars = staging + STAGING_BYTES;
+  const uint32_t bars = staging + C::STAGING_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
   auto mask_bar = [&](int w) { return bars + 8u * (2 * C::STAGES + 4 + w); };
-  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 8);
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4 + NUM_EPI_WARPS);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   float* colacc = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw));     // [BN] per-CTA column sums
 
@@ -220,9 +222,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);          // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), NUM_EPI_WARPS);          // one arrival per epilogue warp
     }
-    for (int w = 0; w < 4; ++w) mbar_init(mask_bar(w), 1);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(mask_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
@@ -322,10 +324,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue warps (2..5) =================
+    // ================= epilogue warps (2..9) =================
     const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) belong to this warp
-    const uint32_t out_slab = staging + (uint32_t)quarter * (2 * SLAB_BYTES);
-    const uint32_t mask_slab = out_slab + SLAB_BYTES;
+    const int ew = warp - 2;                               // 0..7
+    const int half = ew >> 2;                              // the two warps of a quarter take alternate column slabs
+    const uint32_t out_slab = staging + (uint32_t)ew * (C::SLABS_PER_WARP * SLAB_BYTES);
+    const uint32_t mask_slab = out_slab + SLAB_BYTES;      // only carved for EPI_DGRAD
     const uint32_t my_row_off = (uint32_t)lane * 128u;
     const uint32_t swz = (uint32_t)(lane & 7);             // 128B swizzle: 16-byte chunk index ^= row & 7
     constexpr int SLAB_COLS = 128 / (int)sizeof(TOUT);      // 64 bf16 or 32 fp32 columns = 128 B per row
@@ -334,28 +338,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr;
     const bool want_colsum = (EPI == EPI_DGRAD) && sizeof(TOUT) == 2 && p.col_sum != nullptr;
     int acc_nb = -1;
-    const int etid = threadIdx.x - 64;                      // 0..127 among the epilogue threads
+    const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
     auto flush_colacc = [&](int nb_flush) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");        // all four epilogue warps have added their slabs
-      for (int i = etid; i < BN; i += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // all epilogue warps have added their slabs
+      for (int i = etid; i < BN; i += 32 * NUM_EPI_WARPS) {
         const int col = nb_flush * BN + i;
         const float sum = colacc[i];
         if (col < p.N && sum != 0.f) atomicAdd(p.col_sum + col, sum);
         colacc[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     if (want_colsum) {
-      for (int i = etid; i < BN; i += 128) colacc[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = etid; i < BN; i += 32 * NUM_EPI_WARPS) colacc[i] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (has_mask && lane == 0) {                            // mask slab of the first work item of this warp
       for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mb, nb, sp;
         tile_coords(t, mb, nb, sp);
-        if ((int64_t)mb * BLOCK_M + quarter * 32 < p.M) {
-          mbar_expect_tx(mask_bar(quarter), SLAB_BYTES);
-          tma_load_2d(mask_slab, &map_mask, mask_bar(quarter), nb * BN, mb * BLOCK_M + quarter * 32);
+        if ((int64_t)mb * BLOCK_M + quarter * 32 < p.M && nb * BN + half * SLAB_COLS < p.N) {
+          mbar_expect_tx(mask_bar(ew), SLAB_BYTES);
+          tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb * BN + half * SLAB_COLS, mb * BLOCK_M + quarter * 32);
           break;
         }
       }
@@ -372,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (EPI == EPI_SPLIT) {
         // fp32 partial sums straight to the split workspace (few tiles per launch: not worth staging)
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(t_row + (uint32_t)c0, r);
           const int col0 = n0 + c0;
@@ -397,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           acc_nb = nb;
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += SLAB_COLS) {
+        for (int c0 = half * SLAB_COLS; c0 < BN; c0 += 2 * SLAB_COLS) {
           const int col0 = n0 + c0;
           if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this slab is in range
           float v[SLAB_COLS];
@@ -431,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (has_mask) {
-              mbar_wait(mask_bar(quarter), mph);            // slab fetched ahead (issued one slab earlier)
+              mbar_wait(mask_bar(ew), mph);                 // slab fetched ahead (issued one slab earlier)
               mph ^= 1u;
 #pragma unroll
               for (int c = 0; c < 8; ++c) {                 // bf16 mask slab: 8 chunks of 8 columns per row
@@ -447,21 +451,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __syncwarp();                                 // every lane is done with the mask slab
               if (lane == 0) {                              // prefetch the next slab this warp will process
                 int64_t nt = t;
-                int nc0 = c0 + SLAB_COLS;
+                int nc0 = c0 + 2 * SLAB_COLS;
                 bool found = (nc0 < BN) && (n0 + nc0 < p.N);
                 while (!found) {
                   nt += gridDim.x;
                   if (nt >= total_tiles) break;
-                  nc0 = 0;
+                  nc0 = half * SLAB_COLS;
                   int mb2, nb2, sp2;
                   tile_coords(nt, mb2, nb2, sp2);
-                  found = (int64_t)mb2 * BLOCK_M + quarter * 32 < p.M;
+                  found = ((int64_t)mb2 * BLOCK_M + quarter * 32 < p.M) && (nb2 * BN + nc0 < p.N);
                 }
                 if (found) {
                   int mb2, nb2, sp2;
                   tile_coords(nt, mb2, nb2, sp2);
-                  mbar_expect_tx(mask_bar(quarter), SLAB_BYTES);
-                  tma_load_2d(mask_slab, &map_mask, mask_bar(quarter), nb2 * BN + nc0, mb2 * BLOCK_M + quarter * 32);
+                  mbar_expect_tx(mask_bar(ew), SLAB_BYTES);
+                  tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb2 * BN + nc0, mb2 * BLOCK_M + quarter * 32);
                 }
               }
             }
@@ -566,7 +570,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mm, const Params& p,
                   cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT>;
   static bool configured = false;
   if (!configured) {
