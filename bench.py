@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-bags", type=int, default=8, help="slides in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp32-store", action="store_true", help="keep the slide store in fp32 even in bf16 mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -61,7 +62,8 @@ def workload_config(a, world):
             "bags_per_gpu": a.bags, "global_bags": a.bags * world, "T": a.T, "views": 2, "feat_size": a.feat_size,
             "feat_dim": a.dim, "clusters": a.clusters, "patches_per_bag": f"U[{a.min_patches},{a.max_patches}]",
             "arch": "ABMIL(512,512,128)+Full_layer(512,1024,128)", "parallelism": f"dp{world} (bags sharded per rank)",
-            "l2_policy": "inputs larger than L2 (CSR store ~2 GB/GPU, activations 134 MB each)",
+            "l2_policy": "inputs larger than L2 (CSR store >= 1 GB/GPU, activations 268 MB each)",
+            "slide_store_dtype": "bf16" if (a.precision == "bf16" and not a.fp32_store) else "f32",
             "bag_passes_per_step": a.bags * world * a.T * 2}
 
 
@@ -73,7 +75,9 @@ def make_host_batch(a, seed, pin=True):
     from murcl_b200.csr import HostBags
     sizes = synth.camelyon_sizes(a.bags, a.min_patches, a.max_patches, seed=seed)
     feats, _clusters, labels = synth.make_bags(sizes, a.dim, a.clusters, seed=seed)
-    return HostBags(feats, labels, a.clusters, pin=pin)
+    # bf16 mode keeps the slide features as bf16 on the host too (what the first GEMM consumes): half the H2D bytes
+    store_dtype = torch.bfloat16 if (a.precision == "bf16" and not a.fp32_store) else torch.float32
+    return HostBags(feats, labels, a.clusters, pin=pin, dtype=store_dtype)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -373,7 +377,7 @@ def main():
         e2e = {"value": round(a.bags * world * a.e2e_steps / (ms_e2e * 1e-3), 2), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": a.e2e_steps,
                "ms_per_step": round(ms_e2e / a.e2e_steps, 3),
-               "note": "per step: H2D of the step's slides (fp32 CSR + cluster ids) from pinned memory on a copy stream, "
+               "note": "per step: H2D of the step's slides (CSR features + cluster ids) from pinned memory on a copy stream, "
                        "double-buffered against compute; loss.item() each step"}
 
     roof = roofline_probe(job, stores[0], peaks) if rank == 0 else None

@@ -74,10 +74,11 @@ int murcl_pack_select(const int32_t* patch_cluster, const int32_t* patch_rank, c
                       int S, int K, int FS, int32_t* sel_idx, int32_t* sel_cnt, void* stream);
 
 /* Gather + zero pad (+ mixup when lam != NULL): out[s,r,:] = lam[s]*x(s,r) + (1-lam[s])*x(perm[s],r)
- * with x(s,r) = feats[sel_idx[s,r]] or 0; products and sum rounded separately like the
- * reference (datasets.py:268-270).  feats fp32 [n_rows,D]; out [S,FS,D] in out_dtype
- * (MURCL_BF16 rounds the fp32 result to nearest-even). */
-int murcl_pack_gather(const float* feats, int D, const int32_t* sel_idx, int S, int FS,
+ * with x(s,r) = feats[sel_idx[s,r]] or 0; products and sum rounded separately in fp32 like the
+ * reference (datasets.py:268-270).  feats [n_rows,D] in feat_dtype (fp32 as the reference stores it; bf16 halves
+ * the store and the per-step H2D volume in bf16 mode); out [S,FS,D] in out_dtype (MURCL_BF16 rounds the fp32
+ * result to nearest-even). */
+int murcl_pack_gather(const void* feats, int feat_dtype, int D, const int32_t* sel_idx, int S, int FS,
                       const float* lam, const int32_t* perm, void* out, int out_dtype, void* stream);
 
 /* ---- dense layers: every nn.Linear on the path (abmil.py:12-32, clam.py:18-77,

@@ -29,7 +29,7 @@ SIGNATURES = {
     "murcl_launch_count": (_l, []),
     "murcl_csr_rank_patches": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "murcl_pack_select": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
-    "murcl_pack_gather": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _p]),
+    "murcl_pack_gather": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _p]),
     "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
     "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),

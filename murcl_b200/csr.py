@@ -35,11 +35,11 @@ class BagStore:
 
     # -- construction ---------------------------------------------------------------------------
     @staticmethod
-    def _stack_feats(feat_list, device) -> tuple:
+    def _stack_feats(feat_list, device, dtype=torch.float32) -> tuple:
         sizes = [int(f.shape[-2]) for f in feat_list]
         d = int(feat_list[0].shape[-1])
         offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        feats = torch.empty((int(offsets[-1]), d), dtype=torch.float32, device=device)
+        feats = torch.empty((int(offsets[-1]), d), dtype=dtype, device=device)
         for f, lo, hi in zip(feat_list, offsets[:-1], offsets[1:]):
             # host (ideally pinned) or device source: one copy straight into the CSR slot
             feats[lo:hi].copy_(f.reshape(-1, d), non_blocking=True)
@@ -95,7 +95,7 @@ class BagStore:
         """Device buffers sized for ``host`` (contents undefined until ``copy_from_host``)."""
         device = torch.device(device) if device is not None else torch.device("cuda")
         n_rows, d = host.feats.shape
-        return cls(torch.empty((n_rows, d), dtype=torch.float32, device=device), host.offsets,
+        return cls(torch.empty((n_rows, d), dtype=host.feats.dtype, device=device), host.offsets,
                    torch.empty((n_rows,), dtype=torch.int32, device=device),
                    torch.empty((n_rows,), dtype=torch.int32, device=device),
                    torch.empty(tuple(host.cluster_sizes.shape), dtype=torch.int32, device=device), host.K)
@@ -153,8 +153,8 @@ class BagStore:
 
 
 def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, perm=None, out_dtype=torch.float32):
-    if not feats.is_cuda or feats.dtype != torch.float32 or not feats.is_contiguous():
-        raise MurclError("gather: feats must be a contiguous fp32 CUDA tensor")
+    if not feats.is_cuda or feats.dtype not in (torch.float32, torch.bfloat16) or not feats.is_contiguous():
+        raise MurclError("gather: feats must be a contiguous fp32 or bf16 CUDA tensor")
     S, FS = sel_idx.shape
     D = feats.shape[1]
     out = torch.empty((S, FS, D), dtype=out_dtype, device=feats.device)
@@ -163,8 +163,9 @@ def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, per
         perm = perm.detach().reshape(-1).to(torch.int32).contiguous()
         if lam.numel() != S or perm.numel() != S:
             raise MurclError("gather: lam / perm must have one entry per output slot")
-    code = {torch.float32: F32, torch.bfloat16: BF16}[out_dtype]
-    check(_lib.load().murcl_pack_gather(feats.data_ptr(), D, sel_idx.data_ptr(), S, FS,
+    code_of = {torch.float32: F32, torch.bfloat16: BF16}
+    code = code_of[out_dtype]
+    check(_lib.load().murcl_pack_gather(feats.data_ptr(), code_of[feats.dtype], D, sel_idx.data_ptr(), S, FS,
                                         None if lam is None else lam.data_ptr(), None if perm is None else perm.data_ptr(),
                                         out.data_ptr(), code, _s()), "murcl_pack_gather")
     return out
@@ -173,13 +174,13 @@ def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, per
 class HostBags:
     """A batch of slides staged in PINNED host memory in the CSR layout (what a data loader hands over)."""
 
-    def __init__(self, feat_list, labels_list, num_clusters: int, pin: bool = True):
+    def __init__(self, feat_list, labels_list, num_clusters: int, pin: bool = True, dtype: torch.dtype = torch.float32):
         sizes = [int(f.shape[-2]) for f in feat_list]
         d = int(feat_list[0].shape[-1])
         self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64).tolist()
         n_rows = self.offsets[-1]
         self.K = int(num_clusters)
-        self.feats = torch.empty((n_rows, d), dtype=torch.float32)
+        self.feats = torch.empty((n_rows, d), dtype=dtype)         # bf16 in bf16 mode: half the H2D bytes per step
         self.patch_cluster = torch.empty((n_rows,), dtype=torch.int32)
         self.patch_rank = torch.empty((n_rows,), dtype=torch.int32)
         self.cluster_sizes = torch.zeros((len(sizes), self.K), dtype=torch.int32)

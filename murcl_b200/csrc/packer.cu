@@ -125,8 +125,11 @@ __global__ void __launch_bounds__(512) pack_select_kernel(const int32_t* __restr
 }
 
 // ---- gather + pad + mixup ----------------------------------------------------------------------
-template <typename TO, bool MIX>
-__global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restrict__ feats, int D,
+// TI = storage of the CSR feature buffer (fp32 as the reference holds it, or bf16 for the bf16 mode's halved
+// footprint / H2D volume), TO = storage of the packed batch.  The mix is always two rounded fp32 products and
+// one rounded fp32 add (datasets.py:268-270), then one rounding to TO.
+template <typename TI, typename TO, bool MIX>
+__global__ void __launch_bounds__(256) pack_gather_kernel(const TI* __restrict__ feats, int D,
                                                           const int32_t* __restrict__ sel_idx, int64_t n_out_rows,
                                                           int FS, const float* __restrict__ lam,
                                                           const int32_t* __restrict__ perm, TO* __restrict__ out) {
@@ -135,8 +138,8 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restric
   if (row >= n_out_rows) return;
   const int slot = (int)(row / FS), r = (int)(row % FS);
   const int32_t ia = sel_idx[row];
-  const float* pa = (ia >= 0) ? feats + (int64_t)ia * D : nullptr;
-  const float* pb = nullptr;
+  const TI* pa = (ia >= 0) ? feats + (int64_t)ia * D : nullptr;
+  const TI* pb = nullptr;
   float l0 = 1.f, l1 = 0.f;
   if (MIX) {
     const int32_t ib = sel_idx[(int64_t)perm[slot] * FS + r];
@@ -145,11 +148,12 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restric
     l1 = __fsub_rn(1.f, l0);
   }
   TO* po = out + row * D;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if ((D & 3) == 0) {
     for (int c = lane * 4; c < D; c += 128) {
-      float4 a = pa ? __ldg(reinterpret_cast<const float4*>(pa + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a = pa ? load4(pa + c) : zero4;
       if (MIX) {
-        float4 b = pb ? __ldg(reinterpret_cast<const float4*>(pb + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = pb ? load4(pb + c) : zero4;
         a.x = __fadd_rn(__fmul_rn(l0, a.x), __fmul_rn(l1, b.x));
         a.y = __fadd_rn(__fmul_rn(l0, a.y), __fmul_rn(l1, b.y));
         a.z = __fadd_rn(__fmul_rn(l0, a.z), __fmul_rn(l1, b.z));
@@ -159,11 +163,21 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restric
     }
   } else {
     for (int c = lane; c < D; c += 32) {
-      float a = pa ? pa[c] : 0.f;
-      if (MIX) a = __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, pb ? pb[c] : 0.f));
+      float a = pa ? Store<TI>::load(pa + c) : 0.f;
+      if (MIX) a = __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, pb ? Store<TI>::load(pb + c) : 0.f));
       Store<TO>::store(po + c, a);
     }
   }
+}
+
+template <typename TI, typename TO>
+static void launch_gather(const void* feats, int D, const int32_t* sel_idx, int64_t rows, int FS, const float* lam,
+                          const int32_t* perm, void* out, cudaStream_t st) {
+  const int grid = ceil_div(rows, 8);
+  if (lam != nullptr)
+    pack_gather_kernel<TI, TO, true><<<grid, 256, 0, st>>>((const TI*)feats, D, sel_idx, rows, FS, lam, perm, (TO*)out);
+  else
+    pack_gather_kernel<TI, TO, false><<<grid, 256, 0, st>>>((const TI*)feats, D, sel_idx, rows, FS, lam, perm, (TO*)out);
 }
 
 }  // namespace murcl
@@ -194,23 +208,22 @@ int murcl_pack_select(const int32_t* patch_cluster, const int32_t* patch_rank, c
   return check_launch("pack_select_kernel");
 }
 
-int murcl_pack_gather(const float* feats, int D, const int32_t* sel_idx, int S, int FS, const float* lam,
+int murcl_pack_gather(const void* feats, int feat_dtype, int D, const int32_t* sel_idx, int S, int FS, const float* lam,
                       const int32_t* perm, void* out, int out_dtype, void* stream) {
   MURCL_REQUIRE(feats && sel_idx && out, "pack_gather: null pointer");
   MURCL_REQUIRE(S >= 0 && FS > 0 && D > 0, "pack_gather: S=%d FS=%d D=%d out of range", S, FS, D);
   MURCL_REQUIRE((lam == nullptr) == (perm == nullptr), "pack_gather: lam and perm must be given together");
   MURCL_REQUIRE(out_dtype == MURCL_F32 || out_dtype == MURCL_BF16, "pack_gather: bad out_dtype %d", out_dtype);
+  MURCL_REQUIRE(feat_dtype == MURCL_F32 || feat_dtype == MURCL_BF16, "pack_gather: bad feat_dtype %d", feat_dtype);
   if (S == 0) return MURCL_OK;
   const int64_t rows = (int64_t)S * FS;
-  const int grid = ceil_div(rows, 8);
   cudaStream_t st = as_stream(stream);
-  const bool mix = lam != nullptr;
-  if (out_dtype == MURCL_F32) {
-    if (mix) pack_gather_kernel<float, true><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (float*)out);
-    else pack_gather_kernel<float, false><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (float*)out);
+  if (feat_dtype == MURCL_F32) {
+    if (out_dtype == MURCL_F32) launch_gather<float, float>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
+    else launch_gather<float, __nv_bfloat16>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
   } else {
-    if (mix) pack_gather_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (__nv_bfloat16*)out);
-    else pack_gather_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(feats, D, sel_idx, rows, FS, lam, perm, (__nv_bfloat16*)out);
+    if (out_dtype == MURCL_F32) launch_gather<__nv_bfloat16, float>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
+    else launch_gather<__nv_bfloat16, __nv_bfloat16>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
   }
   return check_launch("pack_gather_kernel");
 }

@@ -133,6 +133,24 @@ def test_mixup_bit_exact(golden):
     assert torch.equal(fused.cpu(), O.mixup_apply(dense, lam, perm))
 
 
+def test_bf16_slide_store():
+    """bf16 mode may keep the slide features in bf16 (half the store and the per-step H2D): selection is unchanged,
+    the mix is still fp32 arithmetic on the stored values."""
+    from murcl_b200.csr import BagStore, HostBags
+    feats, clusters, labels = synth.make_bags([300, 90, 64, 200], 32, 4, seed=8)
+    host = HostBags(feats, labels, 4, pin=True, dtype=torch.bfloat16)
+    store = BagStore.empty_like_host(host, DEV)
+    store.copy_from_host(host)
+    ref_store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    assert torch.equal(store.patch_rank, ref_store.patch_rank) and torch.equal(store.cluster_sizes, ref_store.cluster_sizes)
+    actions = torch.rand(4, 4, generator=synth.gen(9))
+    lam = 0.9 + 0.1 * torch.rand(4, 1, generator=synth.gen(10))
+    perm = torch.randperm(4, generator=synth.gen(12))
+    got = store.pack(actions.to(DEV), 64, lam.to(DEV), perm.to(DEV), torch.bfloat16)
+    dense, _ = O.get_feats([f.bfloat16().float() for f in feats], clusters, actions, 64)
+    assert torch.equal(got.cpu(), O.mixup_apply(dense, lam, perm).to(torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------------------------
 # dense layers
 # ------------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ def test_library_exports_header_symbols():
 def test_argument_validation_without_gpu():
     """Bad arguments are rejected before any CUDA call, with a message."""
     lib = _lib.load()
-    rc = lib.murcl_pack_gather(None, 8, None, 1, 4, None, None, None, 0, None)
+    rc = lib.murcl_pack_gather(None, 0, 8, None, 1, 4, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.murcl_last_error()
     rc = lib.murcl_linear_fwd(1, 1, None, 1, 4, 0, 4, 0, 0, 0, 0, None)
     assert rc == -1
