@@ -154,21 +154,32 @@ class Job:
         self.launches_per_step = None
 
     def capture(self, stores):
-        """One CUDA graph per (double-buffered) store, sharing a memory pool.  Returns False if capture fails."""
-        from murcl_b200 import _lib, pretrain
+        """One CUDA graph per (double-buffered) store, sharing a memory pool.  Returns False (on every rank) if the
+        capture fails on any rank."""
+        import torch.distributed as dist
+        from murcl_b200 import pretrain
+        ok = True
         try:
             pool = None
+            # NCCL's watchdog thread polls events while we capture: keep the capture thread-local under torchrun
+            mode = "thread_local" if self.world > 1 else "global"
             for i, st in enumerate(stores):
-                g = pretrain.GraphedStep(lambda st=st: self.step(st), warmup=2 if i == 0 else 0, pool=pool)
+                g = pretrain.GraphedStep(lambda st=st: self.step(st), warmup=2 if i == 0 else 0, pool=pool,
+                                         capture_error_mode=mode)
                 pool = g.pool()
                 self.graphs[id(st)] = g
                 self.launches_per_step = g.launches
-            return True
         except Exception as e:                                  # noqa: BLE001 - report and fall back to eager launches
-            sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
+            sys.stderr.write(f"[bench] rank {self.rank}: CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
+            ok = False
+        torch.cuda.synchronize()
+        if self.world > 1:
+            flag = torch.tensor([1 if ok else 0], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        if not ok:
             self.graphs = {}
-            torch.cuda.synchronize()
-            return False
+        return ok
 
     def run(self, store):
         g = self.graphs.get(id(store))

@@ -105,7 +105,7 @@ class GraphedStep:
     collectives - are stream-ordered, so the whole step replays as a single graph launch.  The bag store and
     every tensor the step touches keep fixed addresses (torch's graph-private pool)."""
 
-    def __init__(self, step_fn, warmup: int = 2, pool=None):
+    def __init__(self, step_fn, warmup: int = 2, pool=None, capture_error_mode: str = "global"):
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -116,7 +116,7 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph, pool=pool):
+        with torch.cuda.graph(self.graph, pool=pool, capture_error_mode=capture_error_mode):
             self.loss = step_fn()
         self.launches = _lib.launch_count() - n0          # libmurcl_b200 kernels per replay
 
