@@ -313,6 +313,15 @@ def run_reference(a):
                       "gpu_launches": 0}))
 
 
+_T0 = time.time()
+
+
+def vlog(msg):
+    if os.environ.get("MURCL_BENCH_VERBOSE"):
+        sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -327,8 +336,10 @@ def main():
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     os.environ["MURCL_PRECISION"] = a.precision          # heads (Full_layer, actor, decoder) follow the same mode
+    vlog("init_process_group")
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    vlog("process group up")
     from murcl_b200 import _lib
     from murcl_b200.csr import BagStore
     _lib.load()
@@ -342,12 +353,17 @@ def main():
     for s, h in zip(stores, host):
         s.copy_from_host(h)
     torch.cuda.synchronize()
+    vlog("host batches staged, stores on device")
     job = Job(a, rank, world, device)
+    vlog("job built")
 
     # ---- device-resident throughput --------------------------------------------------------------
     graphed = (not a.no_graph) and job.capture(stores)
+    vlog(f"graph capture: {graphed}")
     for i in range(a.warmup):
         job.run(stores[i % 2])
+    torch.cuda.synchronize()
+    vlog("warm-up done")
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
@@ -356,6 +372,7 @@ def main():
     launches = job.launches_per_step * a.steps if graphed else _lib.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     value = a.bags * world * a.steps / (ms * 1e-3)
+    vlog(f"timed region done: {ms / a.steps:.2f} ms/step")
 
     # ---- end to end from pinned host buffers -------------------------------------------------------
     e2e = None
@@ -391,7 +408,8 @@ def main():
                "note": "per step: H2D of the step's slides (CSR features + cluster ids) from pinned memory on a copy stream, "
                        "double-buffered against compute; loss.item() each step"}
 
-    roof = roofline_probe(job, stores[0], peaks) if rank == 0 else None
+    roof = roofline_probe(job, stores[0], peaks)      # every rank runs it: the step contains collectives
+    vlog("roofline probe done")
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu, _ = cpu_baseline(a)
