@@ -414,9 +414,6 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu, _ = cpu_baseline(a)
 
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -424,7 +421,14 @@ def main():
                "config": dict(workload_config(a, world), cuda_graph=bool(graphed)), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roof, "cpu_baseline": cpu,
                "bag_passes_per_s": round(value * a.T * 2, 1)}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        # Tear down without ncclCommDestroy: destroying a communicator whose kernels live inside captured CUDA graphs
+        # can block; every rank has finished its work and rank 0 has printed, so synchronise the device and exit.
+        torch.cuda.synchronize()          # all collectives this rank took part in have completed
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
