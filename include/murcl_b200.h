@@ -183,7 +183,8 @@ int murcl_clam_inst_ce_bwd(const float* rows, const float* dlogits, const float*
 
 /* z fp32 [2B,d]: rows [0,B) view i, [B,2B) view j.  loss[1] = mean_a(LSE_{b!=a} s_ab - s_a,pos(a)),
  * s = cos/tau; dz[2B,d] = d loss / d z (NULL to skip); cos_pair[B] = cos(z_i[b], z_j[b]) (NULL to
- * skip).  workspace: 2B*d + 4*2B floats. */
+ * skip).  workspace: murcl_ntxent_workspace(B, d) floats (normalised rows, the [2B,2B] Gram matrix, scratch). */
+int64_t murcl_ntxent_workspace(int B, int d);
 int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
                          float* workspace, void* stream);
 

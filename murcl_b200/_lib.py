@@ -49,6 +49,7 @@ SIGNATURES = {
     "murcl_scatter_add_rows": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "murcl_clam_inst_ce_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
     "murcl_clam_inst_ce_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
+    "murcl_ntxent_workspace": (_l, [_i, _i]),
     "murcl_ntxent_fwd_bwd": (_i, [_p, _i, _i, _f, _p, _p, _p, _p, _p]),
     "murcl_gru_cell_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_gru_cell_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),

@@ -200,7 +200,7 @@ static int launch(const GemmParams& p, int splits, cudaStream_t st) {
 // Forward / input-gradient launch.  When the output has too few 128x128 tiles to fill the GPU (the heads:
 // M = batch size) the reduction is split across gridDim.z into a stream-ordered scratch buffer.
 template <typename TA, typename TB, typename TC, bool A_KC, bool B_KC>
-static int launch_auto(GemmParams p, cudaStream_t st) {
+static int launch_auto(GemmParams p, cudaStream_t st, float* ext_ws = nullptr, int64_t ext_ws_floats = 0) {
   const int ctas = ceil_div(p.M, BM) * ceil_div(p.N, BN);
   int splits = 1;
   if (ctas * 2 <= sm_count() && p.K >= 256) {
@@ -215,10 +215,15 @@ static int launch_auto(GemmParams p, cudaStream_t st) {
   splits = (int)((p.K + chunk - 1) / chunk);
   float* ws = nullptr;
   const size_t bytes = sizeof(float) * (size_t)splits * p.M * p.N;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st);
-  if (e != cudaSuccess) {
-    set_error("gemm_simt: cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    return MURCL_ECUDA;
+  const bool own = !(ext_ws != nullptr && (int64_t)splits * p.M * p.N <= ext_ws_floats);
+  if (!own) {
+    ws = ext_ws;                       // caller-provided scratch (keeps the call free of allocations)
+  } else {
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st);
+    if (e != cudaSuccess) {
+      set_error("gemm_simt: cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return MURCL_ECUDA;
+    }
   }
   GemmParams q = p;
   q.C = ws;
@@ -232,7 +237,7 @@ static int launch_auto(GemmParams p, cudaStream_t st) {
     splitk_epilogue_kernel<TC><<<ceil_div(p.M * p.N, 256), 256, 0, st>>>(ws, splits, r);
     rc = check_launch("splitk_epilogue_kernel");
   }
-  cudaFreeAsync(ws, st);
+  if (own) cudaFreeAsync(ws, st);
   return rc;
 }
 
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const T* __restrict__
 }
 
 int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act,
-                    int dtype, int out_dtype, cudaStream_t st) {
+                    int dtype, int out_dtype, cudaStream_t st, float* ws, int64_t ws_floats) {
   GemmParams p{};
   p.A = x; p.B = w; p.C = y; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldb = K; p.ldc = N;
   p.bias = bias; p.act = act; p.k_chunk = K;
@@ -328,7 +333,7 @@ int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, in
     }
     return check_launch("skinny_fwd_kernel");
   }
-  if (dtype == MURCL_F32 && out_dtype == MURCL_F32) return launch_auto<float, float, float, true, true>(p, st);
+  if (dtype == MURCL_F32 && out_dtype == MURCL_F32) return launch_auto<float, float, float, true, true>(p, st, ws, ws_floats);
   if (dtype == MURCL_BF16 && out_dtype == MURCL_BF16)
     return launch_auto<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, true>(p, st);
   if (dtype == MURCL_BF16 && out_dtype == MURCL_F32)
@@ -339,7 +344,7 @@ int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, in
 
 int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
                           const float* row_scale, const float* row_vec, const int32_t* row_seg, int dtype,
-                          cudaStream_t st) {
+                          cudaStream_t st, float* ws, int64_t ws_floats) {
   GemmParams p{};
   // C = dx [M, K]; reduction over N; A = dy [M,N] k-contiguous; B(n'=k_in, k'=n) = w[n, k_in] n'-contiguous.
   p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
@@ -355,7 +360,7 @@ int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, in
                                                                row_scale, row_vec, row_seg);
     return check_launch("skinny_dgrad_kernel");
   }
-  if (dtype == MURCL_F32) return launch_auto<float, float, float, true, false>(p, st);
+  if (dtype == MURCL_F32) return launch_auto<float, float, float, true, false>(p, st, ws, ws_floats);
   return launch_auto<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, true, false>(p, st);
 }
 

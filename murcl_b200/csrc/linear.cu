@@ -3,9 +3,10 @@
 #include "common.cuh"
 
 namespace murcl {
-int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t);
+int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t,
+                    float* ws = nullptr, int64_t ws_floats = 0);
 int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                          const int32_t*, int, cudaStream_t);
+                          const int32_t*, int, cudaStream_t, float* ws = nullptr, int64_t ws_floats = 0);
 int64_t simt_linear_bwd_weight_workspace(int64_t, int, int);
 int simt_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, float*, cudaStream_t);
 

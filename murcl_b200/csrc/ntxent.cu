@@ -1,15 +1,23 @@
 // Fused NT-Xent / InfoNCE loss with gradient.  Replaces utils/losses.py:24-41 (which materialises a
 // [2B,2B,d] broadcast and indexes with a CPU mask) and the per-bag cosine reward of
-// train_MuRCL.py:253,282.  The problem is tiny (2B x d floats): it is launch/latency bound, so the
-// whole thing is four short kernels on one stream with no host round trip.
+// train_MuRCL.py:253,282.  Everything stays on one stream with no host round trip.
 //
 //   zn_a = z_a / max(|z_a|, 1e-8)                      s_ab = zn_a . zn_b / tau
 //   L    = 1/(2B) sum_a [ LSE_{b != a} s_ab - s_{a,pos(a)} ],  pos(a) = a +/- B
 //   dL/dzn_a = 1/(2B tau) sum_{b != a} [ e^{s_ab - lse_a} + e^{s_ab - lse_b} - 2 [b = pos(a)] ] zn_b
 //   dL/dz_a  = (dzn_a - (dzn_a . zn_a) zn_a) / |z_a|      (|z_a| > eps)
+//
+// Under data parallelism 2B is the GLOBAL batch (2048 rows on 8 GPUs), so the two contractions are real GEMMs:
+// the Gram matrix G = Zn Zn^T ([2B,2B], a few MB of scratch) and dZn = C Zn go through the exact-fp32 SIMT GEMM;
+// the row log-sum-exp and the coefficient matrix C are coalesced row kernels over G.
 #include "common.cuh"
 
 namespace murcl {
+
+int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t,
+                    float* ws, int64_t ws_floats);
+int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
+                          const int32_t*, int, cudaStream_t, float* ws, int64_t ws_floats);
 
 constexpr float COS_EPS = 1e-8f;
 
@@ -29,44 +37,27 @@ __global__ void __launch_bounds__(256) ntx_normalize_kernel(const float* __restr
   if (lane == 0) inv_norm[row] = inv;
 }
 
-// One CTA per row a: logits against every b, masked log-sum-exp, positive logit.
-__global__ void __launch_bounds__(256) ntx_rows_kernel(const float* __restrict__ zn, int B, int d, float inv_tau,
+// One CTA per row a of the Gram matrix: masked log-sum-exp over b != a and the positive logit.
+__global__ void __launch_bounds__(256) ntx_rows_kernel(const float* __restrict__ gram, int B, float inv_tau,
                                                        float* __restrict__ lse, float* __restrict__ row_loss,
                                                        float* __restrict__ cos_pair) {
-  extern __shared__ float sm[];        // [d] the row, then [32] reduction scratch
-  float* za = sm;
-  float* red = sm + d;
+  __shared__ float red[32];
   const int a = blockIdx.x, R = 2 * B;
   const int pos = a < B ? a + B : a - B;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) za[j] = zn[(int64_t)a * d + j];
-  __syncthreads();
-  float m = -INFINITY, s_pos = 0.f;
-  // pass 1: max over b != a (logits recomputed in pass 2; d is small)
-  for (int b = threadIdx.x; b < R; b += blockDim.x) {
-    if (b == a) continue;
-    float dot = 0.f;
-    const float* zb = zn + (int64_t)b * d;
-    for (int j = 0; j < d; ++j) dot = fmaf(za[j], zb[j], dot);
-    const float s = dot * inv_tau;
-    m = fmaxf(m, s);
-    if (b == pos) s_pos = s;
-  }
+  const float* g = gram + (int64_t)a * R;
+  float m = -INFINITY;
+  for (int b = threadIdx.x; b < R; b += blockDim.x)
+    if (b != a) m = fmaxf(m, g[b] * inv_tau);
   m = block_max(m, red);
   float l = 0.f;
-  for (int b = threadIdx.x; b < R; b += blockDim.x) {
-    if (b == a) continue;
-    float dot = 0.f;
-    const float* zb = zn + (int64_t)b * d;
-    for (int j = 0; j < d; ++j) dot = fmaf(za[j], zb[j], dot);
-    l += expf(dot * inv_tau - m);
-  }
+  for (int b = threadIdx.x; b < R; b += blockDim.x)
+    if (b != a) l += expf(g[b] * inv_tau - m);
   l = block_sum(l, red);
-  s_pos = block_sum(s_pos, red);      // exactly one thread holds it
   if (threadIdx.x == 0) {
     const float e = m + logf(l);
     lse[a] = e;
-    row_loss[a] = e - s_pos;
-    if (cos_pair && a < B) cos_pair[a] = s_pos / inv_tau;
+    row_loss[a] = e - g[pos] * inv_tau;
+    if (cos_pair && a < B) cos_pair[a] = g[pos];
   }
 }
 
@@ -78,81 +69,88 @@ __global__ void __launch_bounds__(256) ntx_loss_kernel(const float* __restrict__
   if (threadIdx.x == 0) loss[0] = s / (float)R;
 }
 
-__global__ void __launch_bounds__(256) ntx_grad_kernel(const float* __restrict__ zn, const float* __restrict__ inv_norm,
-                                                       const float* __restrict__ lse, int B, int d, float inv_tau,
-                                                       float* __restrict__ dz) {
-  extern __shared__ float sm[];        // [d] row a, [2B] coefficients, [d] dzn, [32] scratch
-  const int a = blockIdx.x, R = 2 * B;
-  float* za = sm;
-  float* coef = sm + d;
-  float* g = coef + R;
-  float* red = g + d;
-  const int pos = a < B ? a + B : a - B;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) za[j] = zn[(int64_t)a * d + j];
-  __syncthreads();
-  const float lse_a = lse[a];
-  for (int b = threadIdx.x; b < R; b += blockDim.x) {
-    float c = 0.f;
-    if (b != a) {
-      float dot = 0.f;
-      const float* zb = zn + (int64_t)b * d;
-      for (int j = 0; j < d; ++j) dot = fmaf(za[j], zb[j], dot);
-      const float s = dot * inv_tau;
-      c = expf(s - lse_a) + expf(s - lse[b]) - (b == pos ? 2.f : 0.f);
-    }
-    coef[b] = c;
+// In place: gram[a,b] -> coefficient c_ab (symmetric), 0 on the diagonal.
+__global__ void __launch_bounds__(256) ntx_coef_kernel(float* __restrict__ gram, const float* __restrict__ lse, int B,
+                                                       float inv_tau) {
+  const int R = 2 * B;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * R) return;
+  const int a = (int)(i / R), b = (int)(i % R);
+  float c = 0.f;
+  if (a != b) {
+    const float s = gram[i] * inv_tau;
+    const int pos = a < B ? a + B : a - B;
+    c = expf(s - lse[a]) + expf(s - lse[b]) - (b == pos ? 2.f : 0.f);
   }
-  __syncthreads();
-  const float scale = inv_tau / (float)R;
+  gram[i] = c;
+}
+
+// dz_a from g_a = (C zn)_a * inv_tau / R through the normalisation; one warp per row.
+__global__ void __launch_bounds__(256) ntx_finish_kernel(const float* __restrict__ cz, const float* __restrict__ zn,
+                                                         const float* __restrict__ inv_norm, int rows, int d, float scale,
+                                                         float* __restrict__ dz) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   float proj = 0.f;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    float acc = 0.f;
-    for (int b = 0; b < R; ++b) acc = fmaf(coef[b], zn[(int64_t)b * d + j], acc);
-    acc *= scale;
-    g[j] = acc;
-    proj = fmaf(acc, za[j], proj);
+  for (int j = lane; j < d; j += 32) proj = fmaf(cz[(int64_t)row * d + j] * scale, zn[(int64_t)row * d + j], proj);
+  proj = warp_sum(proj);
+  const float inv = inv_norm[row];
+  const bool clamped = inv >= 1.f / COS_EPS;       // |z| <= eps: zn = z / eps is linear in z, no projection term
+  for (int j = lane; j < d; j += 32) {
+    const float g = cz[(int64_t)row * d + j] * scale;
+    dz[(int64_t)row * d + j] = clamped ? g * inv : (g - proj * zn[(int64_t)row * d + j]) * inv;
   }
-  proj = block_sum(proj, red);
-  const float inv = inv_norm[a];
-  // |z| <= eps: zn = z/eps is linear in z, no projection term.
-  const bool clamped = inv >= 1.f / COS_EPS;
-  for (int j = threadIdx.x; j < d; j += blockDim.x)
-    dz[(int64_t)a * d + j] = clamped ? g[j] * inv : (g[j] - proj * za[j]) * inv;
 }
 
 }  // namespace murcl
 
 using namespace murcl;
 
-extern "C" int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz,
-                                    float* cos_pair, float* workspace, void* stream) {
+extern "C" {
+
+int64_t murcl_ntxent_workspace(int B, int d) {
+  const int64_t R = 2 * (int64_t)B;
+  return R * d /*zn*/ + 4 * R /*inv_norm, lse, row_loss, pad*/ + R * R /*gram / coefficients*/ + R * d /*C zn*/ +
+         32 * R * d /*split-K scratch of the C zn product*/;
+}
+
+int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
+                         float* workspace, void* stream) {
   MURCL_REQUIRE(z && loss && workspace, "ntxent: null pointer");
   MURCL_REQUIRE(B > 0 && d > 0 && temperature > 0.f, "ntxent: bad B=%d d=%d tau=%g", B, d, (double)temperature);
+  MURCL_REQUIRE(B <= 16384, "ntxent: 2B=%d rows exceed the Gram-matrix scratch design", 2 * B);
   const int R = 2 * B;
-  MURCL_REQUIRE((size_t)(2 * d + R + 32) * sizeof(float) <= 200 * 1024, "ntxent: 2B=%d d=%d exceeds shared memory", R, d);
   cudaStream_t st = as_stream(stream);
   float* zn = workspace;
   float* inv_norm = zn + (int64_t)R * d;
   float* lse = inv_norm + R;
   float* row_loss = lse + R;
+  float* gram = row_loss + 2 * R;
+  float* cz = gram + (int64_t)R * R;
+  float* scratch = cz + (int64_t)R * d;
+  const int64_t scratch_floats = 32 * (int64_t)R * d;
   const float inv_tau = 1.f / temperature;
   ntx_normalize_kernel<<<ceil_div(R, 8), 256, 0, st>>>(z, R, d, zn, inv_norm);
   int rc = check_launch("ntx_normalize_kernel");
   if (rc != MURCL_OK) return rc;
-  ntx_rows_kernel<<<R, 256, sizeof(float) * (d + 32), st>>>(zn, B, d, inv_tau, lse, row_loss, cos_pair);
+  // Gram matrix: [R,d] x [R,d]^T -> [R,R]
+  rc = simt_linear_fwd(zn, zn, nullptr, gram, R, R, d, MURCL_ACT_NONE, MURCL_F32, MURCL_F32, st, scratch, scratch_floats);
+  if (rc != MURCL_OK) return rc;
+  ntx_rows_kernel<<<R, 256, 0, st>>>(gram, B, inv_tau, lse, row_loss, cos_pair);
   rc = check_launch("ntx_rows_kernel");
   if (rc != MURCL_OK) return rc;
   ntx_loss_kernel<<<1, 256, 0, st>>>(row_loss, R, loss);
   rc = check_launch("ntx_loss_kernel");
   if (rc != MURCL_OK || dz == nullptr) return rc;
-  const size_t smem = sizeof(float) * (2 * d + R + 32);
-  if (smem > 48 * 1024) {
-    static bool done = false;
-    if (!done) {
-      MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      done = true;
-    }
-  }
-  ntx_grad_kernel<<<R, 256, smem, st>>>(zn, inv_norm, lse, B, d, inv_tau, dz);
-  return check_launch("ntx_grad_kernel");
+  ntx_coef_kernel<<<ceil_div((int64_t)R * R, 256), 256, 0, st>>>(gram, lse, B, inv_tau);
+  rc = check_launch("ntx_coef_kernel");
+  if (rc != MURCL_OK) return rc;
+  // C zn: [R,R] x [R,d] -> [R,d]   (dx = dy . w with dy = C, w = zn)
+  rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, MURCL_F32, st, scratch, scratch_floats);
+  if (rc != MURCL_OK) return rc;
+  ntx_finish_kernel<<<ceil_div(R, 8), 256, 0, st>>>(cz, zn, inv_norm, R, d, inv_tau / (float)R, dz);
+  return check_launch("ntx_finish_kernel");
 }
+
+}  // extern "C"

@@ -361,7 +361,7 @@ def ntxent_raw(z: torch.Tensor, B: int, temperature: float, want_grad=True):
     loss = torch.empty((1,), device=z.device, dtype=torch.float32)
     dz = torch.empty_like(z) if want_grad else None
     cos = torch.empty((B,), device=z.device, dtype=torch.float32)
-    ws = torch.empty((R * d + 4 * R,), device=z.device, dtype=torch.float32)
+    ws = torch.empty((int(_lib.load().murcl_ntxent_workspace(B, d)),), device=z.device, dtype=torch.float32)
     check(_lib.load().murcl_ntxent_fwd_bwd(_p(z), B, d, float(temperature), _p(loss), _p(dz), _p(cos), _p(ws), _s()),
           "murcl_ntxent_fwd_bwd")
     return loss, dz, cos
