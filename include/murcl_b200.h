@@ -93,10 +93,13 @@ int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, i
  * pre-activation.  When row_scale != NULL: dx += row_scale[m] * row_vec[row_seg[m]][k] before
  * masking (the direct softmax-pool term, see murcl_pool_bwd).  When col_sum != NULL (fp32 [K], zeroed by
  * the caller) the column sums of the stored result are accumulated into it: dx is the next layer's dZ, so this
- * is that layer's bias gradient, produced without another pass over dx. */
+ * is that layer's bias gradient, produced without another pass over dx.  out_scale (0 or 1 = none) multiplies
+ * the masked result: it is 1/(1-p) when relu_src was dropped out after its ReLU (clam.py:70-71), since the zeros
+ * of relu_src then mark "inactive OR dropped". */
 int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K,
                            const void* relu_src, const float* row_scale, const float* row_vec,
-                           const int32_t* row_seg, float* col_sum, int dtype, int backend, void* stream);
+                           const int32_t* row_seg, float* col_sum, float out_scale, int dtype, int backend,
+                           void* stream);
 
 /* dw[N,K] (fp32) = dy[M,N]^T . x[M,K], db[N] (fp32, may be NULL) = column sums of dy.
  * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats. */
@@ -138,9 +141,10 @@ int murcl_pool_bwd_direct(const float* p, const float* dM, const int32_t* row_se
 /* Backward through the score: given ds[N] and the saved activations uv, overwrites uv with the
  * gradient w.r.t. the pre-activations (tanh' / sigmoid' applied) and accumulates dwc[D], dbc[1] and - when
  * dpre_colsum != NULL - the column sums of the written gradient ([D] or [2D]: the bias gradient of the
- * attention projection).  All three are fp32 and must be zeroed by the caller. */
+ * attention projection).  All three are fp32 and must be zeroed by the caller.  drop_scale = 1/(1-p) when uv went
+ * through murcl_dropout after its activations (clam.py:46-48), else 1 (or 0). */
 int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, float* dpre_colsum,
-                         int64_t N, int D, int gated, int dtype, void* stream);
+                         int64_t N, int D, int gated, float drop_scale, int dtype, void* stream);
 
 /* ---- (3) segmented reductions: clam.py:103-132 (top-k instance loss), dsmil.py:71-78 ---- */
 
@@ -208,6 +212,9 @@ int murcl_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t
 int murcl_row_segments(const int64_t* offsets, int B, int32_t* row_seg, void* stream);
 /* out[n] = (fp32) column sums of a[M,N] (storage dtype). */
 int murcl_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* stream);
+/* In-place inverted dropout: x[i] = keep_i ? x[i]/(1-p) : 0 with keep_i from a counter-based hash of (seed, i);
+ * the 64-bit seed is read from device memory (fresh per CUDA-graph replay). */
+int murcl_dropout(void* x, int64_t n, float p, const int64_t* seed_dev, int dtype, void* stream);
 /* dz = dy * (y > 0) elementwise (ReLU backward), same storage dtype. */
 int murcl_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, int dtype, void* stream);
 

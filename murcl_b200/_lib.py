@@ -31,7 +31,7 @@ SIGNATURES = {
     "murcl_pack_select": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "murcl_pack_gather": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _p]),
     "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
-    "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),
     "murcl_linear_bwd_weight": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _p, _p]),
     "murcl_attn_score_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p]),
@@ -40,7 +40,7 @@ SIGNATURES = {
     "murcl_seg_wsum": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _p, _p, _p]),
     "murcl_pool_bwd_scores": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p, _p, _p]),
     "murcl_pool_bwd_direct": (_i, [_p, _p, _p, _l, _i, _i, _i, _p, _i, _p]),
-    "murcl_attn_score_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p]),
+    "murcl_attn_score_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _f, _i, _p]),
     "murcl_seg_topk_ends": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "murcl_seg_argmax": (_i, [_p, _p, _i, _i, _p, _p]),
     "murcl_dsmil_scores_fwd": (_i, [_p, _p, _p, _l, _i, _i, _p, _p]),
@@ -58,6 +58,7 @@ SIGNATURES = {
     "murcl_row_segments": (_i, [_p, _i, _p, _p]),
     "murcl_colsum": (_i, [_p, _l, _i, _i, _p, _p]),
     "murcl_relu_bwd": (_i, [_p, _p, _p, _l, _i, _p]),
+    "murcl_dropout": (_i, [_p, _l, _f, _p, _i, _p]),
 }
 
 _lib = None

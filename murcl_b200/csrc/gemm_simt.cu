@@ -29,6 +29,7 @@ struct GemmParams {
   const float* row_scale;   // [M] or null: C += row_scale[m] * row_vec[row_seg[m]*N + n]
   const float* row_vec;
   const int32_t* row_seg;
+  float out_scale;          // applied last (1/(1-p) of a dropout that followed the masked ReLU); 0 means 1
   int64_t k_chunk;          // K range per blockIdx.z
   int64_t split_stride;     // elements between split outputs (C is fp32 workspace when gridDim.z > 1)
 };
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
       v = apply_act(v, p.act, n, p.N);
       if (rv) v = fmaf(rs, rv[n], v);
       if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) v = 0.f;
+      if (p.out_scale != 0.f) v *= p.out_scale;
       Store<TC>::store(static_cast<TC*>(p.C) + m * p.ldc + n, v);
     }
   }
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __res
   v = apply_act(v, p.act, n, p.N);
   if (p.row_scale) v = fmaf(p.row_scale[m], p.row_vec[(int64_t)p.row_seg[m] * p.N + n], v);
   if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) v = 0.f;
+  if (p.out_scale != 0.f) v *= p.out_scale;
   Store<TC>::store(static_cast<TC*>(p.C) + m * p.ldc + n, v);
 }
 
@@ -292,7 +295,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx,
                                                            int64_t M, int N, int K, const T* __restrict__ relu_src,
                                                            const float* __restrict__ row_scale, const float* __restrict__ row_vec,
-                                                           const int32_t* __restrict__ row_seg) {
+                                                           const int32_t* __restrict__ row_seg, float out_scale) {
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const T* __restrict__
       if (n < N) v = fmaf(g[n], Store<T>::load(w + (int64_t)n * K + k), v);
     if (rv) v = fmaf(rs, rv[k], v);
     if (relu_src && !(Store<T>::load(relu_src + m * K + k) > 0.f)) v = 0.f;
-    Store<T>::store(dx + m * K + k, v);
+    Store<T>::store(dx + m * K + k, v * out_scale);
   }
 }
 
@@ -343,21 +346,22 @@ int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, in
 }
 
 int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
-                          const float* row_scale, const float* row_vec, const int32_t* row_seg, int dtype,
+                          const float* row_scale, const float* row_vec, const int32_t* row_seg, float out_scale, int dtype,
                           cudaStream_t st, float* ws, int64_t ws_floats) {
   GemmParams p{};
   // C = dx [M, K]; reduction over N; A = dy [M,N] k-contiguous; B(n'=k_in, k'=n) = w[n, k_in] n'-contiguous.
   p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
   p.relu_src = relu_src; p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.k_chunk = N;
+  p.out_scale = out_scale;
   if (N <= SKINNY_N) {
     const int grid = ceil_div(M, 8);
     if (dtype == MURCL_F32)
       skinny_dgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)w, (float*)dx, M, N, K,
-                                                       (const float*)relu_src, row_scale, row_vec, row_seg);
+                                                       (const float*)relu_src, row_scale, row_vec, row_seg, out_scale);
     else
       skinny_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w,
                                                                (__nv_bfloat16*)dx, M, N, K, (const __nv_bfloat16*)relu_src,
-                                                               row_scale, row_vec, row_seg);
+                                                               row_scale, row_vec, row_seg, out_scale);
     return check_launch("skinny_dgrad_kernel");
   }
   if (dtype == MURCL_F32) return launch_auto<float, float, float, true, false>(p, st, ws, ws_floats);

@@ -52,6 +52,7 @@ struct Params {
   const float* row_vec;
   const int32_t* row_seg;
   float* col_sum;     // EPI_DGRAD: accumulated column sums of the stored result (may be null)
+  float out_scale;    // EPI_DGRAD: final scale (1/(1-p) of a dropout that followed the masked ReLU)
   int splits;
   int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
   int64_t split_stride;
@@ -448,6 +449,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   if (!(f.y > 0.f)) v[8 * c + 2 * j + 1] = 0.f;
                 }
               }
+              if (p.out_scale != 1.f) {
+#pragma unroll
+                for (int i = 0; i < SLAB_COLS; ++i) v[i] *= p.out_scale;
+              }
               __syncwarp();                                 // every lane is done with the mask slab
               if (lane == 0) {                              // prefetch the next slab this warp will process
                 int64_t nt = t;
@@ -648,7 +653,7 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
 
 int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
                         const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum,
-                        cudaStream_t st) {
+                        float out_scale, cudaStream_t st) {
   if (!aligned16(dy) || !aligned16(w) || !aligned16(dx) || (relu_src && !aligned16(relu_src))) {
     set_error("linear_bwd_input(tcgen05): operands must be 16-byte aligned");
     return MURCL_EINVAL;
@@ -664,6 +669,7 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   p.M = M; p.N = K; p.K = N; p.ldc = K; p.C = dx;
   p.relu_src = static_cast<const __nv_bfloat16*>(relu_src);
   p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.col_sum = col_sum;
+  p.out_scale = out_scale;
   p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
   CUtensorMap mc, mm;

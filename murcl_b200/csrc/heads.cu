@@ -154,6 +154,35 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy,
   }
 }
 
+// In-place inverted dropout (clam.py:46-48,70-71; abmil.py:15,18): x *= keep / (1 - p).  Counter-based RNG: element i
+// keeps iff splitmix64(seed, i) maps to u >= p; the 64-bit seed is read from DEVICE memory so that a CUDA-graph replay
+// sees a fresh seed each step.  Dropped elements become exact zeros (the backward recognises them by that).
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(T* __restrict__ x, int64_t n, float p, float scale,
+                                                      const int64_t* __restrict__ seed_dev) {
+  const uint64_t seed = (uint64_t)seed_dev[0];
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    float4 v = load4(x + i);
+    v.x = hash_uniform(seed, i) >= p ? v.x * scale : 0.f;
+    v.y = hash_uniform(seed, i + 1) >= p ? v.y * scale : 0.f;
+    v.z = hash_uniform(seed, i + 2) >= p ? v.z * scale : 0.f;
+    v.w = hash_uniform(seed, i + 3) >= p ? v.w * scale : 0.f;
+    store4(x + i, v);
+  } else {
+    for (int64_t j = i; j < n; ++j)
+      Store<T>::store(x + j, hash_uniform(seed, j) >= p ? Store<T>::load(x + j) * scale : 0.f);
+  }
+}
+
 int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st);
   if (e != cudaSuccess) {
@@ -239,6 +268,19 @@ int murcl_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* s
     return MURCL_OK;
   }
   return colsum_impl(a, M, N, dtype, out, as_stream(stream));
+}
+
+int murcl_dropout(void* x, int64_t n, float p, const int64_t* seed_dev, int dtype, void* stream) {
+  MURCL_REQUIRE(x && seed_dev, "dropout: null pointer");
+  MURCL_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%g out of [0,1)", (double)p);
+  if (n <= 0 || p == 0.f) return MURCL_OK;
+  cudaStream_t st = as_stream(stream);
+  const int grid = ceil_div((n + 3) / 4, 256);
+  const float scale = 1.f / (1.f - p);
+  if (dtype == MURCL_F32) dropout_kernel<float><<<grid, 256, 0, st>>>((float*)x, n, p, scale, seed_dev);
+  else if (dtype == MURCL_BF16) dropout_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, n, p, scale, seed_dev);
+  else MURCL_REQUIRE(false, "dropout: bad dtype %d", dtype);
+  return check_launch("dropout_kernel");
 }
 
 int murcl_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, int dtype, void* stream) {

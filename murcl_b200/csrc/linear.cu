@@ -6,7 +6,7 @@ namespace murcl {
 int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t,
                     float* ws = nullptr, int64_t ws_floats = 0);
 int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                          const int32_t*, int, cudaStream_t, float* ws = nullptr, int64_t ws_floats = 0);
+                          const int32_t*, float, int, cudaStream_t, float* ws = nullptr, int64_t ws_floats = 0);
 int64_t simt_linear_bwd_weight_workspace(int64_t, int, int);
 int simt_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, float*, cudaStream_t);
 
@@ -15,7 +15,7 @@ bool tc_bwd_input_supported(int64_t M, int N, int K, int dtype);
 bool tc_bwd_weight_supported(int64_t M, int N, int K, int dtype);
 int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, cudaStream_t);
 int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                        const int32_t*, float*, cudaStream_t);
+                        const int32_t*, float*, float, cudaStream_t);
 int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
 int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t);
 
@@ -46,22 +46,24 @@ int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, i
 }
 
 int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
-                           const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum, int dtype,
-                           int backend, void* stream) {
+                           const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum,
+                           float out_scale, int dtype, int backend, void* stream) {
   MURCL_REQUIRE(dy && w && dx, "linear_bwd_input: null pointer");
   MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_input: bad shape");
   MURCL_REQUIRE(valid_dtype(dtype), "linear_bwd_input: bad dtype");
   MURCL_REQUIRE((row_scale == nullptr) == (row_vec == nullptr) && (row_scale == nullptr) == (row_seg == nullptr),
                 "linear_bwd_input: row_scale, row_vec and row_seg must be given together");
   if (M == 0) return MURCL_OK;
+  if (out_scale == 0.f) out_scale = 1.f;
+  MURCL_REQUIRE(out_scale == 1.f || relu_src != nullptr, "linear_bwd_input: out_scale is the dropout factor of a masked ReLU");
   const bool tc_ok = tc_bwd_input_supported(M, N, K, dtype);
   if (backend == MURCL_GEMM_TCGEN05 && !tc_ok) {
     set_error("linear_bwd_input: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d", (long long)M, N, K, dtype);
     return MURCL_EUNSUPPORTED;
   }
   if (backend != MURCL_GEMM_SIMT && tc_ok)
-    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, col_sum, as_stream(stream));
-  int rc = simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, dtype, as_stream(stream));
+    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, col_sum, out_scale, as_stream(stream));
+  int rc = simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, out_scale, dtype, as_stream(stream));
   if (rc != MURCL_OK || col_sum == nullptr) return rc;
   return colsum_impl(dx, M, K, dtype, col_sum, as_stream(stream));       // same sums, separate pass
 }

@@ -17,7 +17,7 @@ namespace murcl {
 int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t,
                     float* ws, int64_t ws_floats);
 int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                          const int32_t*, int, cudaStream_t, float* ws, int64_t ws_floats);
+                          const int32_t*, float, int, cudaStream_t, float* ws, int64_t ws_floats);
 
 constexpr float COS_EPS = 1e-8f;
 
@@ -147,7 +147,7 @@ int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float*
   rc = check_launch("ntx_coef_kernel");
   if (rc != MURCL_OK) return rc;
   // C zn: [R,R] x [R,d] -> [R,d]   (dx = dy . w with dy = C, w = zn)
-  rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, MURCL_F32, st, scratch, scratch_floats);
+  rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, 1.f, MURCL_F32, st, scratch, scratch_floats);
   if (rc != MURCL_OK) return rc;
   ntx_finish_kernel<<<ceil_div(R, 8), 256, 0, st>>>(cz, zn, inv_norm, R, d, inv_tau / (float)R, dz);
   return check_launch("ntx_finish_kernel");

@@ -346,7 +346,7 @@ template <typename T, bool GATED>
 __global__ void __launch_bounds__(256) attn_score_bwd_kernel(T* __restrict__ uv, const float* __restrict__ wc,
                                                              const float* __restrict__ ds, float* __restrict__ dwc,
                                                              float* __restrict__ dbc, float* __restrict__ dpre_colsum,
-                                                             int64_t N, int D, int rows_per_cta) {
+                                                             int64_t N, int D, int rows_per_cta, float q) {
   extern __shared__ float sm[];   // [D] dwc partial, [2D] column sums partial
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int ld = GATED ? 2 * D : D;
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(256) attn_score_bwd_kernel(T* __restrict__ uv,
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(N, r0 + rows_per_cta);
   float dsum = 0.f;
+  const float iq = 1.f / q;       // q = 1/(1-p) when a dropout followed the activations, else 1
   constexpr int MAXI = 4;         // D <= 512
   float part[MAXI][4], csa[MAXI][4], csb[MAXI][4];
 #pragma unroll
@@ -379,18 +380,21 @@ __global__ void __launch_bounds__(256) attn_score_bwd_kernel(T* __restrict__ uv,
           const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            // u, v are the stored (possibly dropped-and-rescaled by q) activations; ua, va the raw tanh / sigmoid
             const float gw = g * ww[j];
+            const float ua = u[j] * iq, va = v[j] * iq;
             part[i][j] = fmaf(g, u[j] * v[j], part[i][j]);
-            oa[j] = gw * v[j] * (1.f - u[j] * u[j]);
-            ob[j] = gw * u[j] * v[j] * (1.f - v[j]);
+            oa[j] = (u[j] != 0.f) ? gw * v[j] * q * (1.f - ua * ua) : 0.f;
+            ob[j] = (v[j] != 0.f) ? gw * u[j] * q * va * (1.f - va) : 0.f;
             csb[i][j] += ob[j];
           }
           store4(r + D + d, make_float4(ob[0], ob[1], ob[2], ob[3]));
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            const float ua = u[j] * iq;
             part[i][j] = fmaf(g, u[j], part[i][j]);
-            oa[j] = g * ww[j] * (1.f - u[j] * u[j]);
+            oa[j] = (q == 1.f || u[j] != 0.f) ? g * ww[j] * q * (1.f - ua * ua) : 0.f;
           }
         }
 #pragma unroll
@@ -422,7 +426,8 @@ __global__ void __launch_bounds__(256) attn_score_bwd_kernel(T* __restrict__ uv,
 template <typename T, bool GATED>
 __global__ void __launch_bounds__(256) attn_score_bwd_generic_kernel(T* __restrict__ uv, const float* __restrict__ wc,
                                                                      const float* __restrict__ ds, float* __restrict__ dwc,
-                                                                     float* __restrict__ dbc, int64_t N, int D) {
+                                                                     float* __restrict__ dbc, int64_t N, int D, float q) {
+  const float iq = 1.f / q;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -434,12 +439,14 @@ __global__ void __launch_bounds__(256) attn_score_bwd_generic_kernel(T* __restri
     const float gw = g * wc[d];
     if (GATED) {
       const float v = Store<T>::load(r + D + d);
+      const float ua = u * iq, va = v * iq;
       atomicAdd(&dwc[d], g * u * v);
-      Store<T>::store(r + d, gw * v * (1.f - u * u));
-      Store<T>::store(r + D + d, gw * u * v * (1.f - v));
+      Store<T>::store(r + d, u != 0.f ? gw * v * q * (1.f - ua * ua) : 0.f);
+      Store<T>::store(r + D + d, v != 0.f ? gw * u * q * va * (1.f - va) : 0.f);
     } else {
+      const float ua = u * iq;
       atomicAdd(&dwc[d], g * u);
-      Store<T>::store(r + d, gw * (1.f - u * u));
+      Store<T>::store(r + d, (q == 1.f || u != 0.f) ? gw * q * (1.f - ua * ua) : 0.f);
     }
   }
   if (dbc && lane == 0) atomicAdd(dbc, g);
@@ -562,11 +569,12 @@ int murcl_pool_bwd_direct(const float* p, const float* dM, const int32_t* row_se
 }
 
 int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, float* dpre_colsum, int64_t N,
-                         int D, int gated, int dtype, void* stream) {
+                         int D, int gated, float drop_scale, int dtype, void* stream) {
   MURCL_REQUIRE(uv && wc && ds && dwc, "attn_score_bwd: null pointer");
   MURCL_REQUIRE(N >= 0 && D > 0, "attn_score_bwd: bad shape");
   MURCL_REQUIRE(dtype == MURCL_F32 || dtype == MURCL_BF16, "attn_score_bwd: bad dtype %d", dtype);
   if (N == 0) return MURCL_OK;
+  const float q = drop_scale > 0.f ? drop_scale : 1.f;
   cudaStream_t st = as_stream(stream);
   const int ld = gated ? 2 * D : D;
   const bool fast = (D % 4 == 0) && D <= 512 && ((reinterpret_cast<uintptr_t>(uv) & 15) == 0) &&
@@ -574,11 +582,11 @@ int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc,
   if (!fast) {
     const int grid = ceil_div(N, 8);
     if (dtype == MURCL_F32) {
-      if (gated) attn_score_bwd_generic_kernel<float, true><<<grid, 256, 0, st>>>((float*)uv, wc, ds, dwc, dbc, N, D);
-      else attn_score_bwd_generic_kernel<float, false><<<grid, 256, 0, st>>>((float*)uv, wc, ds, dwc, dbc, N, D);
+      if (gated) attn_score_bwd_generic_kernel<float, true><<<grid, 256, 0, st>>>((float*)uv, wc, ds, dwc, dbc, N, D, q);
+      else attn_score_bwd_generic_kernel<float, false><<<grid, 256, 0, st>>>((float*)uv, wc, ds, dwc, dbc, N, D, q);
     } else {
-      if (gated) attn_score_bwd_generic_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D);
-      else attn_score_bwd_generic_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D);
+      if (gated) attn_score_bwd_generic_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D, q);
+      else attn_score_bwd_generic_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, N, D, q);
     }
     int rc = check_launch("attn_score_bwd_generic_kernel");
     if (rc != MURCL_OK || dpre_colsum == nullptr) return rc;
@@ -589,11 +597,11 @@ int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc,
   const int grid = ceil_div(N, rows_per_cta);
   const size_t smem = sizeof(float) * (size_t)(D + ld);
   if (dtype == MURCL_F32) {
-    if (gated) attn_score_bwd_kernel<float, true><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
-    else attn_score_bwd_kernel<float, false><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
+    if (gated) attn_score_bwd_kernel<float, true><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta, q);
+    else attn_score_bwd_kernel<float, false><<<grid, 256, smem, st>>>((float*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta, q);
   } else {
-    if (gated) attn_score_bwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
-    else attn_score_bwd_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta);
+    if (gated) attn_score_bwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta, q);
+    else attn_score_bwd_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>((__nv_bfloat16*)uv, wc, ds, dwc, dbc, dpre_colsum, N, D, rows_per_cta, q);
   }
   return check_launch("attn_score_bwd_kernel");
 }

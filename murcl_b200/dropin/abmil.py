@@ -33,12 +33,12 @@ class ABMIL(nn.Module):
     # ------------------------------------------------------------------------------------------
     def _meta(self, rows):
         prec = self.precision or ops.default_precision()
-        return {"B": rows.B, "gated": False, "inv_sqrt_n": True, "dtype": ops.storage_dtype(prec)}
+        meta = {"B": rows.B, "gated": False, "inv_sqrt_n": True, "dtype": ops.storage_dtype(prec)}
+        if self.training and self.dropout_p > 0:
+            meta["drop"] = {"enc": [self.dropout_p, self.dropout_p, 0.0], "attn": 0.0}     # abmil.py:15,18
+        return meta
 
     def _aggregate(self, x):
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError("train-mode dropout inside the fused encoder is not implemented; "
-                                      "use dropout=0 (the reference default) or eval()")
         rows = to_rows(x)
         enc = [p for i in (0, 3, 6) for p in (self.encoder[i].weight, self.encoder[i].bias)]
         M, p, _s, _il, _pr = ops.mil_aggregate(rows.rows, rows.offsets, rows.row_seg, self._meta(rows),

@@ -104,12 +104,14 @@ class CLAM_SB(nn.Module):
     # ------------------------------------------------------------------------------------------
     def _meta(self, rows):
         prec = self.precision or ops.default_precision()
-        return {"B": rows.B, "gated": bool(self.gate), "inv_sqrt_n": False, "dtype": ops.storage_dtype(prec)}
+        meta = {"B": rows.B, "gated": bool(self.gate), "inv_sqrt_n": False, "dtype": ops.storage_dtype(prec)}
+        if self.training and self.has_dropout:
+            # Dropout(0.25) after the fc ReLU (clam.py:70-71) and after each attention branch (:26-27,46-48)
+            meta["drop"] = {"enc": [0.25], "attn": 0.25}
+        return meta
 
     def _check_mode(self):
-        if self.training and self.has_dropout:
-            raise NotImplementedError("train-mode Dropout(0.25) inside the fused CLAM path is not implemented yet; "
-                                      "build with dropout=False or call eval()")
+        pass
 
     def _instance_plan(self, rows, labels):
         """Host-side layout of the (bag, class) groups the instance loss visits (clam.py:146-166)."""

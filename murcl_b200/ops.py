@@ -63,6 +63,7 @@ def _dt(t: torch.Tensor) -> int:
 # optional per-launch timing of the dense layers (bench.py's roofline probe)
 # ------------------------------------------------------------------------------------------------
 _profile = None
+_debug_save = None          # tests set this to a dict to receive the (post-dropout) activations of the last aggregate
 
 
 def set_profile(log):
@@ -135,7 +136,7 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
     return y
 
 
-def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None, col_sum=None):
+def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None, col_sum=None, out_scale=1.0):
     _chk(dy, "linear_bwd_input.dy"); _chk(w, "linear_bwd_input.w")
     if dy.dtype != w.dtype:
         raise MurclError(f"linear_bwd_input: dy is {dy.dtype} but w is {w.dtype}")
@@ -148,7 +149,7 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
     with _Timed("linear_bwd_input", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
-                                                 _p(row_seg), _p(col_sum), _dt(dy), _backend(), _s()),
+                                                 _p(row_seg), _p(col_sum), float(out_scale), _dt(dy), _backend(), _s()),
               "murcl_linear_bwd_input")
     return dx
 
@@ -226,7 +227,14 @@ def pool_bwd_direct(p, dM, row_seg, C, L, out, accumulate):
     return out
 
 
-def attn_score_bwd_(uv, wc, ds, D, gated):
+def dropout_(x: torch.Tensor, p: float, seed: torch.Tensor) -> torch.Tensor:
+    """In-place inverted dropout; ``seed`` is a 1-element int64 CUDA tensor (device-side, so graph replays differ)."""
+    _chk(x, "dropout.x"); _chk(seed, "dropout.seed", torch.int64)
+    check(_lib.load().murcl_dropout(_p(x), x.numel(), float(p), _p(seed), _dt(x), _s()), "murcl_dropout")
+    return x
+
+
+def attn_score_bwd_(uv, wc, ds, D, gated, drop_scale=1.0):
     """In place: uv becomes the gradient w.r.t. the pre-activations.  Returns (dwc [D], dbc [1], column sums of the
     new uv [D | 2D] = bias gradient of the attention projection)."""
     buf = torch.zeros((D + 1 + uv.shape[1],), device=uv.device, dtype=torch.float32)      # one memset for all three
@@ -234,7 +242,7 @@ def attn_score_bwd_(uv, wc, ds, D, gated):
     if dpre.data_ptr() % 16:
         dpre = torch.zeros((uv.shape[1],), device=uv.device, dtype=torch.float32)
     check(_lib.load().murcl_attn_score_bwd(_p(uv), _p(wc), _p(ds), _p(dwc), _p(dbc), _p(dpre), uv.shape[0], D, int(gated),
-                                           _dt(uv), _s()), "murcl_attn_score_bwd")
+                                           float(drop_scale), _dt(uv), _s()), "murcl_attn_score_bwd")
     return dwc, dbc, dpre
 
 
@@ -410,13 +418,24 @@ class _MILAggregate(torch.autograd.Function):
         D = wc.numel()
         hs = [cast(x.detach().contiguous(), dt)]
         enc_w = []
+        drop = meta.get("drop")                 # train-mode dropout: {"enc": [p after layer 1..n], "attn": p}
+        seeds = None
+        if drop is not None:
+            seeds = torch.randint(0, 2 ** 62, (len(enc) // 2 + 1,), device=x.device, dtype=torch.int64)
         for i in range(0, len(enc), 2):
             w = weight_as(enc[i], dt)
             enc_w.append(w)
-            hs.append(linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU))
+            h = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU)
+            if drop is not None and drop["enc"][i // 2] > 0:
+                dropout_(h, drop["enc"][i // 2], seeds[i // 2:i // 2 + 1])
+            hs.append(h)
         H = hs[-1]
         wab_s = weight_as(wab, dt)
         uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
+        if drop is not None and drop["attn"] > 0:
+            dropout_(uv, drop["attn"], seeds[-1:])
+        if _debug_save is not None:
+            _debug_save.update(hs=[h.clone() for h in hs], uv=uv.clone())
         wc_f = wc.detach().reshape(-1).contiguous().float()
         bc_f = bc.detach().reshape(-1).contiguous().float()
         s = attn_score_fwd(uv, wc_f, bc_f, D, gated)
@@ -469,7 +488,10 @@ class _MILAggregate(torch.autograd.Function):
         L = H.shape[1]
         dM = dM.contiguous().float()
         ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, meta["inv_sqrt_n"])
-        dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated)    # uv now holds d(pre-activation)
+        drop = meta.get("drop")
+        q_attn = 1.0 / (1.0 - drop["attn"]) if drop is not None and drop["attn"] > 0 else 1.0
+        q_enc = [1.0 / (1.0 - pe) if drop is not None and pe > 0 else 1.0 for pe in (drop["enc"] if drop else [0.0] * n_enc)]
+        dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated, q_attn)    # uv now holds d(pre-activation)
         dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
         relu_src = H if n_enc > 0 else None
         inst = meta.get("inst")
@@ -477,8 +499,8 @@ class _MILAggregate(torch.autograd.Function):
         # after the fact, so that case takes the separate column-sum pass)
         fuse_db = n_enc > 0 and inst is None
         db_next = torch.zeros((n_enc, L), device=uv.device, dtype=torch.float32) if fuse_db else None
-        dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg,
-                              col_sum=db_next[n_enc - 1] if fuse_db else None)     # + p_n dM[b] direct term, ReLU mask
+        dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg, col_sum=db_next[n_enc - 1] if fuse_db else None,
+                              out_scale=q_enc[n_enc - 1] if n_enc > 0 else 1.0)      # + p_n dM[b] direct term, ReLU mask
         d_inst_w = d_inst_b = None
         if inst is not None:
             idx, rows, dlogits, iw = rest
@@ -491,7 +513,7 @@ class _MILAggregate(torch.autograd.Function):
                                                      G, _p(iw), L, _p(drows), _p(d_inst_w), _p(d_inst_b), _s()),
                   "murcl_clam_inst_ce_bwd")
             if n_enc > 0:
-                drows = drows * (rows > 0)                              # same ReLU mask as the fused epilogue
+                drows = drows * (rows > 0) * q_enc[n_enc - 1]           # same ReLU (+dropout) mask as the fused epilogue
             scatter_add_rows_(dz, idx, drows.contiguous())
         grads_enc = []
         for l in range(n_enc, 0, -1):
@@ -500,7 +522,8 @@ class _MILAggregate(torch.autograd.Function):
                 db = db_next[l - 1]
             grads_enc = [dw, db] + grads_enc
             if l > 1:
-                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1], col_sum=db_next[l - 2] if fuse_db else None)
+                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1], col_sum=db_next[l - 2] if fuse_db else None,
+                                      out_scale=q_enc[l - 2])
             elif ctx.needs_input_grad[0]:
                 dz = linear_bwd_input(dz, enc_w[0])
         dx = None

@@ -112,13 +112,15 @@ def softmax_pool(scores: Tensor, h: Tensor, post_scale: float = 1.0) -> Tuple[Te
     return p @ h, p
 
 
-def abmil_bag(x: Tensor, sd: StateDict) -> Tensor:
+def abmil_bag(x: Tensor, sd: StateDict, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """One bag through ABMIL (models/abmil.py:35-45): 3x(Linear+ReLU) encoder (:12-21),
     tanh attention (:23-27), softmax over N then / sqrt(N) (:40-41), A.H (:42), Linear+ReLU
     decoder (:29-32,44).  ``fc`` (:33) is never applied.  x [N, D_in] -> [1, L]."""
     h = x
-    for i in (0, 3, 6):
+    for j, i in enumerate((0, 3, 6)):
         h = F.relu(F.linear(h, sd[f"encoder.{i}.weight"], sd[f"encoder.{i}.bias"]))
+        if masks is not None and f"enc{j}" in masks:      # train-mode nn.Dropout (:15,18): multiplicative keep/(1-p)
+            h = h * masks[f"enc{j}"]
     u = torch.tanh(F.linear(h, sd["attention.0.weight"], sd["attention.0.bias"]))
     s = F.linear(u, sd["attention.2.weight"], sd["attention.2.bias"]).squeeze(-1)
     m, _ = softmax_pool(s, h, 1.0 / math.sqrt(h.shape[0]))
@@ -130,15 +132,20 @@ def abmil_forward(bags: Sequence[Tensor], sd: StateDict) -> Tensor:
     return torch.cat([abmil_bag(b.reshape(-1, b.shape[-1]), sd) for b in bags], 0)
 
 
-def clam_attention_scores(h: Tensor, sd: StateDict, prefix: str, gate: bool) -> Tensor:
+def clam_attention_scores(h: Tensor, sd: StateDict, prefix: str, gate: bool,
+                          masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """models/clam.py:18-60: gated ``W_c(tanh(W_a h) * sigmoid(W_b h))`` or plain
     ``W_2 tanh(W_1 h)`` raw scores [N] (dropout off)."""
     if gate:
         a = torch.tanh(F.linear(h, sd[f"{prefix}.attention_a.0.weight"], sd[f"{prefix}.attention_a.0.bias"]))
         b = torch.sigmoid(F.linear(h, sd[f"{prefix}.attention_b.0.weight"], sd[f"{prefix}.attention_b.0.bias"]))
+        if masks is not None:                               # Dropout(0.25) after each branch (clam.py:46-48)
+            a, b = a * masks["attn_a"], b * masks["attn_b"]
         return F.linear(a * b, sd[f"{prefix}.attention_c.weight"], sd[f"{prefix}.attention_c.bias"]).squeeze(-1)
     keys = sorted(k for k in sd if k.startswith(f"{prefix}.module.") and k.endswith(".weight"))
     u = torch.tanh(F.linear(h, sd[keys[0]], sd[keys[0].replace("weight", "bias")]))
+    if masks is not None:
+        u = u * masks["attn_a"]
     return F.linear(u, sd[keys[1]], sd[keys[1].replace("weight", "bias")]).squeeze(-1)
 
 
@@ -172,14 +179,17 @@ def clam_instance_loss(p: Tensor, h: Tensor, sd: StateDict, label: int, n_classe
 
 def clam_sb_bag(x: Tensor, sd: StateDict, *, gate: bool = True, dropout_layers: bool = False,
                 label: Optional[int] = None, instance_eval: bool = False, n_classes: int = 2,
-                k_sample: int = 8, subtyping: bool = False, attention_only: bool = False):
+                k_sample: int = 8, subtyping: bool = False, attention_only: bool = False,
+                masks: Optional[Dict[str, Tensor]] = None):
     """One bag through CLAM_SB in eval mode (models/clam.py:134-181).  ``dropout_layers``
     only shifts the index of the attention sub-module in the Sequential (:69-77): it is
     ``attention_net.3`` when the model was built with dropout=True and ``.2`` otherwise.
     Returns (M [1,512], results dict) or raw scores [1,N] when ``attention_only`` (:141-142)."""
     att = "attention_net.3" if dropout_layers else "attention_net.2"
     h = F.relu(F.linear(x, sd["attention_net.0.weight"], sd["attention_net.0.bias"]))
-    s = clam_attention_scores(h, sd, att, gate)
+    if masks is not None:                                   # train mode: Dropout(0.25) after the fc ReLU (clam.py:70-71)
+        h = h * masks["enc"]
+    s = clam_attention_scores(h, sd, att, gate, masks)
     if attention_only:
         return s.unsqueeze(0)
     m, p = softmax_pool(s, h)

@@ -281,6 +281,89 @@ def test_clam_golden(golden, gate, dropout, subtyping):
             assert_close(o3[2][i]["instance_loss"], g[f"inst_loss{i}"], FP32_OUT, f"batched inst{i}")
 
 
+@pytest.mark.parametrize("gate", [True, False])
+def test_clam_train_mode_dropout(gate):
+    """MuRCL builds CLAM_SB with dropout=True and trains in model.train() (train_MuRCL.py:85,202).  The kernel draws
+    its own keep masks (torch's Philox stream cannot be reproduced), so the masks are read back from the saved
+    activations and handed to the oracle: forward and backward must then agree at the fp32 tolerance."""
+    from murcl_b200 import ops
+    from murcl_b200.dropin import clam
+    in_dim, n = 48, 700
+    sd = synth.clam_state(in_dim, "small", gate, True, 2, seed=61)
+    m = _load(clam.CLAM_SB(gate=gate, size_arg="small", dropout=True, n_classes=2, in_dim=in_dim, precision="fp32"), sd)
+    m.train()
+    feats, _, _ = synth.make_bags([n], in_dim, 3, seed=62)
+    x = feats[0].to(DEV).requires_grad_(True)
+    ops._debug_save = {}
+    try:
+        out, _ = m(x.unsqueeze(0))
+        saved = ops._debug_save
+    finally:
+        ops._debug_save = None
+    q = 1.0 / 0.75
+    h_d, uv_d = saved["hs"][1].float().cpu(), saved["uv"].float().cpu()
+    D = 256
+    masks = {"enc": (h_d != 0).float() * q, "attn_a": (uv_d[:, :D] != 0).float() * q}
+    if gate:
+        masks["attn_b"] = (uv_d[:, D:] != 0).float() * q
+    keep = float((uv_d != 0).float().mean())
+    assert abs(keep - 0.75) < 0.01, f"keep fraction {keep}"
+    sdl = leaf_state(sd)
+    xr = feats[0].clone().requires_grad_(True)
+    want, _ = O.clam_sb_bag(xr, sdl, gate=gate, dropout_layers=True, masks=masks)
+    assert_close(out, want, FP32_OUT, "train-mode M")
+    cot = torch.randn(1, 512, generator=synth.gen(63))
+    (want * cot).sum().backward()
+    (out * cot.to(DEV)).sum().backward()
+    gr = _grads(m)
+    for k, p in sdl.items():
+        if p.grad is None or k.startswith(("classifiers", "instance")):
+            continue
+        assert_close(gr[k], p.grad, FP32_GRAD, k, floor=1e-1 if _zero_grad_key(k) else 1e-6)
+    assert_close(x.grad, xr.grad, FP32_GRAD, "dx")
+    # a second forward draws different masks; eval() is deterministic
+    out2, _ = m(x.detach().unsqueeze(0))
+    assert not torch.equal(out2, out.detach())
+    m.eval()
+    with torch.no_grad():
+        e1, _ = m(x.detach().unsqueeze(0))
+        e2, _ = m(x.detach().unsqueeze(0))
+    assert torch.equal(e1, e2)
+
+
+def test_abmil_train_mode_dropout():
+    from murcl_b200 import ops
+    from murcl_b200.dropin import abmil
+    sd = synth.abmil_state(40, 64, 32, 2, seed=64)
+    m = _load(abmil.ABMIL(40, L=64, D=32, dropout=0.3, precision="fp32"), sd).train()
+    feats, _, _ = synth.make_bags([500, 120], 40, 3, seed=65)
+    ops._debug_save = {}
+    try:
+        out, _ = m([f.to(DEV) for f in feats])
+        saved = ops._debug_save
+    finally:
+        ops._debug_save = None
+    q = 1.0 / 0.7
+    sdl = leaf_state(sd)
+    wants, lo = [], 0
+    for f in feats:
+        hi = lo + f.shape[0]
+        masks = {"enc0": (saved["hs"][1][lo:hi].float().cpu() != 0).float() * q,
+                 "enc1": (saved["hs"][2][lo:hi].float().cpu() != 0).float() * q}
+        wants.append(O.abmil_bag(f, sdl, masks))
+        lo = hi
+    want = torch.cat(wants, 0)
+    assert_close(out, want, FP32_OUT, "train-mode out")
+    cot = torch.randn(want.shape, generator=synth.gen(66))
+    (want * cot).sum().backward()
+    (out * cot.to(DEV)).sum().backward()
+    gr = _grads(m)
+    for k, p in sdl.items():
+        if p.grad is None or k.startswith("fc."):
+            continue
+        assert_close(gr[k], p.grad, FP32_GRAD, k, floor=1e-1 if _zero_grad_key(k) else 1e-6)
+
+
 def test_clam_big_and_errors(golden):
     from murcl_b200.dropin import clam
     g = golden("clam_big")
