@@ -135,6 +135,47 @@ __device__ __forceinline__ void act_slab(float (&v)[N], int act, int col0, int n
   }
 }
 
+// ---- cluster / cta_group::2 helpers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {      // same smem offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data lands in the issuing CTA's smem, the transaction bytes are counted on the barrier
+// at `bar_cluster_addr` (the leader CTA's barrier).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c_inner,
+                                                int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {             // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -183,9 +224,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a
 
 constexpr int SLAB_BYTES = 32 * 128;        // one epilogue warp's staging slab: 32 rows x 128 B
 
-template <int BN, int EPI>
+// CG = cta_group: 1 = one SM per 128 x BN tile; 2 = a CTA pair shares a 256 x BN tile (each CTA holds its 128 rows of A
+// and HALF of B, the MMA unit exchanges the B halves), which halves the B bytes each SM pulls through L2 and reads from
+// shared memory per MMA - the limiter of the 1-CTA kernel.
+template <int BN, int EPI, int CG>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLABS_PER_WARP = (EPI == 1) ? 2 : 1;          // output slab (+ ReLU-mask slab for the input grad)
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
@@ -195,11 +239,14 @@ struct Cfg {
                                     BN * 4 /*column-sum accumulator*/;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
+template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_mask, const Params p) {
-  using C = Cfg<BN, EPI>;
+  using C = Cfg<BN, EPI, CG>;
+  static_assert(CG == 1 || !A_MN, "the CTA-pair kernel takes a K-major A operand");
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B atoms need 1024 B alignment
@@ -223,23 +270,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_WARPS);          // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), NUM_EPI_WARPS * CG);     // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(mask_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
   }
+  if (CG == 2) cluster_sync_all();         // barrier inits of both CTAs are visible before any remote arrive / TMA
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * p.splits;     // m_tiles counts 128*CG-row tiles
+  const int64_t tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int k_blocks_full = (int)((p.k_chunk + BLOCK_K - 1) / BLOCK_K);
 
   auto tile_coords = [&](int64_t t, int& mb, int& nb, int& sp) {
@@ -260,18 +314,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp, nkb;
         int64_t k0;
         tile_coords(t, mb, nb, sp);
         k_range(sp, k0, nkb);
-        const int m0 = mb * BLOCK_M, n0 = nb * BN;
+        const int m0 = (mb * CG + (int)cta_rank) * BLOCK_M;                   // this CTA's 128 rows of the tile
+        const int n0 = nb * BN + (int)cta_rank * (BN / CG);                    // this CTA's share of the B rows
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t a_dst = tiles + s * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
-          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
           const int kk = (int)(k0 + (int64_t)kb * BLOCK_K);
+          if (CG == 2) {
+            // both CTAs load their halves; all bytes are counted on the LEADER's full barrier (it issues the MMAs)
+            if (leader) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+            const uint32_t fb = mapa(full_bar(s), 0);
+            tma_load_2d_2sm(a_dst, &map_a, fb, kk, m0);
+            if (!B_MN) {
+              tma_load_2d_2sm(b_dst, &map_b, fb, kk, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / CG / 64; ++j) tma_load_2d_2sm(b_dst + j * 8192, &map_b, fb, n0 + 64 * j, kk);
+            }
+            if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            continue;
+          }
+          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(a_dst, &map_a, full_bar(s), kk, m0);                    // box {64 k, 128 rows}
           } else {
@@ -291,12 +360,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, A_MN, B_MN);
+    // ================= MMA issuer (the leader CTA of a pair issues for both) =================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BN, A_MN, B_MN);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp, nkb;
         int64_t k0;
         tile_coords(t, mb, nb, sp);
@@ -315,12 +384,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // MN-major: 16 k-rows = two 8-row groups of 1024 B; LBO = 8192 B between 64-wide MN blocks.
             const uint64_t adesc = A_MN ? make_smem_desc(a_src + k * 2048, 8192, 1024) : make_smem_desc(a_src + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc(b_src + k * 2048, 8192, 1024) : make_smem_desc(b_src + k * 32, 16, 1024);
-            tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (CG == 1) tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else tcgen05_mma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar(s));                    // smem slot reusable once these MMAs retire
+          if (CG == 1) tcgen05_commit(empty_bar(s));       // smem slot reusable once these MMAs retire
+          else tcgen05_commit_2sm(empty_bar(s));           // ... in both CTAs
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
-        tcgen05_commit(tfull_bar(as));                     // accumulator complete
+        if (CG == 1) tcgen05_commit(tfull_bar(as));        // accumulator complete
+        else tcgen05_commit_2sm(tfull_bar(as));
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
@@ -355,20 +427,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (has_mask && lane == 0) {                            // mask slab of the first work item of this warp
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp;
         tile_coords(t, mb, nb, sp);
-        if ((int64_t)mb * BLOCK_M + quarter * 32 < p.M && nb * BN + half * SLAB_COLS < p.N) {
+        if (((int64_t)mb * CG + cta_rank) * BLOCK_M + quarter * 32 < p.M && nb * BN + half * SLAB_COLS < p.N) {
           mbar_expect_tx(mask_bar(ew), SLAB_BYTES);
-          tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb * BN + half * SLAB_COLS, mb * BLOCK_M + quarter * 32);
+          tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb * BN + half * SLAB_COLS,
+                      (mb * CG + (int)cta_rank) * BLOCK_M + quarter * 32);
           break;
         }
       }
     }
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
       int mb, nb, sp;
       tile_coords(t, mb, nb, sp);
-      const int64_t row0 = (int64_t)mb * BLOCK_M + quarter * 32;
+      const int64_t row0 = ((int64_t)mb * CG + cta_rank) * BLOCK_M + quarter * 32;
       const int64_t row = row0 + lane;
       const int n0 = nb * BN;
       mbar_wait(tfull_bar(as), aph);
@@ -459,18 +532,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int nc0 = c0 + 2 * SLAB_COLS;
                 bool found = (nc0 < BN) && (n0 + nc0 < p.N);
                 while (!found) {
-                  nt += gridDim.x;
+                  nt += tile_step;
                   if (nt >= total_tiles) break;
                   nc0 = half * SLAB_COLS;
                   int mb2, nb2, sp2;
                   tile_coords(nt, mb2, nb2, sp2);
-                  found = ((int64_t)mb2 * BLOCK_M + quarter * 32 < p.M) && (nb2 * BN + nc0 < p.N);
+                  found = (((int64_t)mb2 * CG + cta_rank) * BLOCK_M + quarter * 32 < p.M) && (nb2 * BN + nc0 < p.N);
                 }
                 if (found) {
                   int mb2, nb2, sp2;
                   tile_coords(nt, mb2, nb2, sp2);
                   mbar_expect_tx(mask_bar(ew), SLAB_BYTES);
-                  tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb2 * BN + nc0, mb2 * BLOCK_M + quarter * 32);
+                  tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb2 * BN + nc0,
+                              (mb2 * CG + (int)cta_rank) * BLOCK_M + quarter * 32);
                 }
               }
             }
@@ -516,7 +590,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));          // this warp has drained its quarter of the accumulator
+      if (lane == 0) {                                     // this warp has drained its part of the accumulator
+        if (CG == 1) mbar_arrive(tempty_bar(as));
+        else mbar_arrive_cluster(mapa(tempty_bar(as), 0)); // the leader's MMA thread waits for both CTAs
+      }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
     if (want_colsum && acc_nb >= 0) flush_colacc(acc_nb);
@@ -524,10 +601,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: neither CTA may leave while the other still uses its smem/TMEM
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -572,11 +650,11 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
   return MURCL_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT>
+template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mm, const Params& p,
                   cudaStream_t st) {
-  using C = Cfg<BN, EPI>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT>;
+  using C = Cfg<BN, EPI, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT, CG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -587,8 +665,26 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     configured = true;
   }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mc, mm, p);
+  const int slots = sm_count() / CG;                          // persistent: one CTA (or CTA pair) per SM (pair)
+  const int grid = (int)(total < slots ? total : slots) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mm, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc_kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return MURCL_ECUDA;
+  }
   return check_launch("gemm_tc_kernel");
 }
 
@@ -597,6 +693,16 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace tc
 
 using namespace tc;
+
+// The CTA-pair kernel is used for the instance-level layers (many 256-row tiles, N a multiple of 256).
+static bool pair_ok(int64_t M, int N) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MURCL_DISABLE_CTA_PAIR");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1 && M >= 4096 && N % 256 == 0;
+}
 
 static bool tc_enabled() {
   static int v = -1;
@@ -627,10 +733,11 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
     return MURCL_EINVAL;
   }
   const int BN = (N % 256 == 0) ? 256 : 128;
+  const bool pair = pair_ok(M, N);
   CUtensorMap ma, mb;
   int rc = make_map(&ma, x, M, K, BLOCK_K, BLOCK_M);
   if (rc != MURCL_OK) return rc;
-  rc = make_map(&mb, w, N, K, BLOCK_K, BN);
+  rc = make_map(&mb, w, N, K, BLOCK_K, pair ? BN / 2 : BN);      // a CTA of a pair loads half of the B tile
   if (rc != MURCL_OK) return rc;
   CUtensorMap mc;
   const int eb = out_dtype == MURCL_BF16 ? 2 : 4;
@@ -644,6 +751,11 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
   p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = y; p.bias = bias; p.act = act;
   p.splits = 1; p.k_chunk = ((int64_t)K + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
+  if (pair) {
+    p.m_tiles = ceil_div(M, 2 * BLOCK_M);
+    return out_dtype == MURCL_BF16 ? launch<256, false, false, EPI_FWD, __nv_bfloat16, 2>(ma, mb, mc, mc, p, st)
+                                   : launch<256, false, false, EPI_FWD, float, 2>(ma, mb, mc, mc, p, st);
+  }
   if (out_dtype == MURCL_BF16)
     return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st)
                      : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st);
@@ -660,6 +772,7 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   }
   // C = dx [M, K_in]; A = dy [M, N] K-major (reduction over N); B(n'=k_in, k'=n) = w[n, k_in]: MN-major, rows = n.
   const int BN = (K % 256 == 0) ? 256 : 128;
+  const bool pair = pair_ok(M, K);
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dy, M, N, BLOCK_K, BLOCK_M);
   if (rc != MURCL_OK) return rc;
@@ -680,6 +793,10 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   if (row_vec != nullptr && !aligned16(row_vec)) {
     set_error("linear_bwd_input(tcgen05): row_vec must be 16-byte aligned");
     return MURCL_EINVAL;
+  }
+  if (pair) {
+    p.m_tiles = ceil_div(M, 2 * BLOCK_M);
+    return launch<256, false, true, EPI_DGRAD, __nv_bfloat16, 2>(ma, mb, mc, mm, p, st);
   }
   return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st)
                    : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st);

@@ -130,7 +130,7 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
     y = torch.empty((M, N), device=x.device, dtype=out_dtype)
     if bias is not None:
         _chk(bias, "linear_fwd.bias", torch.float32)
-    with _Timed("linear_fwd", 2.0 * M * N * K):
+    with _Timed("linear_fwd" if M >= 4096 else "head_fwd", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_fwd(_p(x), _p(w), _p(bias), _p(y), M, N, K, act, _dt(x), _DT[out_dtype], _backend(),
                                            _s()), "murcl_linear_fwd")
     return y
@@ -147,7 +147,7 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
     dx = torch.empty((M, K), device=dy.device, dtype=dy.dtype)
     if relu_src is not None:
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
-    with _Timed("linear_bwd_input", 2.0 * M * N * K):
+    with _Timed("linear_bwd_input" if M >= 4096 else "head_bwd_input", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
                                                  _p(row_seg), _p(col_sum), float(out_scale), _dt(dy), _backend(), _s()),
               "murcl_linear_bwd_input")
@@ -163,7 +163,7 @@ def linear_bwd_weight(dy, x, want_bias=True):
     db = torch.empty((N,), device=dy.device, dtype=torch.float32) if want_bias else None
     nws = int(lib.murcl_linear_bwd_weight_workspace(M, N, K))
     ws = torch.empty((max(nws, 1),), device=dy.device, dtype=torch.float32)
-    with _Timed("linear_bwd_weight", 2.0 * M * N * K):
+    with _Timed("linear_bwd_weight" if M >= 4096 else "head_bwd_weight", 2.0 * M * N * K):
         check(lib.murcl_linear_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), M, N, K, _dt(dy), _backend(), _p(ws), _s()),
               "murcl_linear_bwd_weight")
     return dw, db

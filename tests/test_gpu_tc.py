@@ -30,7 +30,8 @@ def _mk(M, N, K, seed):
     return x, w, b, dy
 
 
-SHAPES = [(4096, 512, 512), (1000, 128, 512), (131, 384, 1024), (2048, 256, 64), (777, 512, 200), (128, 128, 64)]
+SHAPES = [(4096, 512, 512), (1000, 128, 512), (131, 384, 1024), (2048, 256, 64), (777, 512, 200), (128, 128, 64),
+          (5000, 256, 512), (8200, 512, 128), (40000, 512, 512)]      # the last three exercise the CTA-pair kernel + row tails
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
