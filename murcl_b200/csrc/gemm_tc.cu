@@ -732,7 +732,8 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
     set_error("linear_fwd(tcgen05): operands must be 16-byte aligned");
     return MURCL_EINVAL;
   }
-  const int BN = (N % 256 == 0) ? 256 : 128;
+  // batch-sized layers (M = a few 128-row tiles) use 64-wide column tiles so that more SMs take part
+  const int BN = (M <= 512 && N % 64 == 0) ? 64 : (N % 256 == 0) ? 256 : 128;
   const bool pair = pair_ok(M, N);
   CUtensorMap ma, mb;
   int rc = make_map(&ma, x, M, K, BLOCK_K, BLOCK_M);
@@ -756,6 +757,9 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
     return out_dtype == MURCL_BF16 ? launch<256, false, false, EPI_FWD, __nv_bfloat16, 2>(ma, mb, mc, mc, p, st)
                                    : launch<256, false, false, EPI_FWD, float, 2>(ma, mb, mc, mc, p, st);
   }
+  if (BN == 64)
+    return out_dtype == MURCL_BF16 ? launch<64, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st)
+                                   : launch<64, false, false, EPI_FWD, float>(ma, mb, mc, mc, p, st);
   if (out_dtype == MURCL_BF16)
     return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st)
                      : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st);
@@ -771,7 +775,7 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
     return MURCL_EINVAL;
   }
   // C = dx [M, K_in]; A = dy [M, N] K-major (reduction over N); B(n'=k_in, k'=n) = w[n, k_in]: MN-major, rows = n.
-  const int BN = (K % 256 == 0) ? 256 : 128;
+  const int BN = (M <= 512 && K % 64 == 0) ? 64 : (K % 256 == 0) ? 256 : 128;
   const bool pair = pair_ok(M, K);
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dy, M, N, BLOCK_K, BLOCK_M);
@@ -798,6 +802,7 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
     p.m_tiles = ceil_div(M, 2 * BLOCK_M);
     return launch<256, false, true, EPI_DGRAD, __nv_bfloat16, 2>(ma, mb, mc, mm, p, st);
   }
+  if (BN == 64) return launch<64, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st);
   return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st)
                    : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st);
 }

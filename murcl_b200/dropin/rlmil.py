@@ -89,6 +89,35 @@ class ActorCritic(nn.Module):
                 action = mean
         return action.detach()
 
+    def act_views(self, states, memories, restart_batch=False, training=True):
+        """``act`` for several independent views in one batched pass (same math per view: rows do not interact).
+        Used by the fused pre-training step; halves the number of small launches."""
+        n, b = len(states), states[0].size(0)
+        with torch.no_grad():
+            if restart_batch:
+                for m in memories:
+                    del m.hidden[:]
+                    m.hidden.append(torch.zeros(1, b, self.hidden_state_dim, device=states[0].device))
+            state = torch.cat([s.flatten(1).float() for s in states], 0).contiguous()
+            enc = self._encode(state)
+            h_prev = torch.cat([m.hidden[-1][0] for m in memories], 0).contiguous()
+            h = ops.gru_step(enc, h_prev, *_gru_params(self.gru), dtype=_dtype(self))
+            logits = ops.linear(h, self.actor[0].weight, self.actor[0].bias)
+            eps = torch.randn(logits.shape, device=logits.device, dtype=torch.float32)
+            action, logprob, mean = ops.actor_head(logits, eps, self.action_std)
+            outs = []
+            for v, m in enumerate(memories):
+                sl = slice(v * b, (v + 1) * b)
+                m.hidden.append(h[sl].unsqueeze(0))
+                if training:
+                    m.states.append(states[v])
+                    m.actions.append(action[sl])
+                    m.logprobs.append(logprob[sl])
+                    outs.append(action[sl].detach())
+                else:
+                    outs.append(mean[sl].detach())
+        return outs
+
     def evaluate(self, state, action):
         """rlmil.py:99-127: log-prob, value and entropy of stored (state, action) sequences ``[T, B, ...]``."""
         seq_l, batch_size = state.size(0), state.size(1)
@@ -127,6 +156,10 @@ class PPO:
 
     def select_action(self, state, memory, restart_batch=False, training=True):
         return self.policy_old.act(state, memory, restart_batch, training)
+
+    def select_action_views(self, states, memories, restart_batch=False, training=True):
+        """``select_action`` for the two views of a patch-step (train_MuRCL.py:262-265) in one batched pass."""
+        return self.policy_old.act_views(states, memories, restart_batch, training)
 
     def update(self, memory):
         """PPO-clip update of rlmil.py:152-184 (discounted rewards, K epochs, policy_old <- policy)."""
@@ -172,6 +205,28 @@ class Full_layer(torch.nn.Module):
             self.fc_3 = nn.Linear(self.feature_num * 3, class_num)
             self.fc_4 = nn.Linear(self.feature_num * 4, class_num)
             self.fc_5 = nn.Linear(self.feature_num * 5, class_num)
+
+    def forward_views(self, xs, restart=False):
+        """``[self(x, restart) for x in xs]`` (train_MuRCL.py:243,272) with the view-independent dense layers batched:
+        the input projection of all views is one GEMM, the recurrent part keeps the reference's single hidden chain
+        (each call continues from the state the previous call left; ``restart`` resets it for every view), and the
+        output layer is one GEMM over all views."""
+        if not self.fc_rnn:
+            return [self.forward(x, restart) for x in xs]
+        n, b = len(xs), xs[0].size(0)
+        dt = _dtype(self)
+        w_ih, w_hh, b_ih, b_hh = _gru_params(self.rnn)
+        gi_all = ops.linear(torch.cat([x.float() for x in xs], 0).contiguous(), w_ih, b_ih, ops.ACT_NONE, dt)
+        hs = []
+        h = None if restart or self.hidden is None else self.hidden[0]
+        for v in range(n):
+            h_prev = torch.zeros(b, self.hidden_state_dim, device=xs[0].device) if restart else h
+            gh = ops.linear(h_prev, w_hh, b_hh, ops.ACT_NONE, dt)
+            h = ops.gru_cell(gi_all[v * b:(v + 1) * b], gh, h_prev)
+            hs.append(h)
+        self.hidden = h.unsqueeze(0)
+        out = ops.linear(torch.cat(hs, 0), self.fc.weight, self.fc.bias, ops.ACT_NONE, dt)
+        return [out[v * b:(v + 1) * b] for v in range(n)]
 
     def forward(self, x, restart=False):
         if self.fc_rnn:

@@ -343,6 +343,11 @@ class _GRUCell(torch.autograd.Function):
         return dgi, dgh, dh_prev
 
 
+def gru_cell(gi, gh, h_prev):
+    """Fused GRU cell on precomputed gate pre-activations (differentiable)."""
+    return _GRUCell.apply(gi, gh, h_prev)
+
+
 def gru_step(x, h_prev, w_ih, w_hh, b_ih, b_hh, dtype: torch.dtype = torch.float32):
     """One nn.GRU time step (gate order r,z,n) built from two dense layers and the fused cell kernel."""
     gi = linear(x, w_ih, b_ih, ACT_NONE, dtype)

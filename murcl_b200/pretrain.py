@@ -75,11 +75,17 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         else:
             actions = None
             if stage == 3 and t >= 1:
-                actions = [ppo.select_action(s, m, restart_batch=(t == 1)) for s, m in zip(states, memories)]
+                if hasattr(ppo, "select_action_views"):
+                    actions = ppo.select_action_views(states, memories, restart_batch=(t == 1))
+                else:
+                    actions = [ppo.select_action(s, m, restart_batch=(t == 1)) for s, m in zip(states, memories)]
             draw = draw_patch_step(B, K, alpha, dev, actions)
         x_all = pack_views(store, draw, feat_size, dt, slot_bag)
         outputs, states = encode_views(model, x_all)
-        outputs = [fc(o, restart=(t == 0)) for o in outputs]
+        if hasattr(fc, "forward_views"):
+            outputs = fc.forward_views(outputs, restart=(t == 0))
+        else:
+            outputs = [fc(o, restart=(t == 0)) for o in outputs]
         loss = criterion(outputs[0], outputs[1])
         losses.append(loss)
         sim = criterion.last_cosine.view(1, -1)          # by-product of the loss kernel (train_MuRCL.py:253,282)

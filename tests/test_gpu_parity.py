@@ -240,6 +240,22 @@ def test_abmil_full_size(golden, precision, tol_out, tol_grad):
         assert_close(gr[k], p.grad, tol_grad, k, floor=1e-1 if _zero_grad_key(k) else 1e-7)
 
 
+def test_large_bag_stress_cfg5():
+    """BASELINE config 5 shape: one bag of N=100k patches x 1024-d, bf16 fused pooling (CLAM_SB small).  The
+    forward is compared with the fp32 oracle at the bf16 tolerance; a ragged second bag rides along."""
+    from murcl_b200.dropin import clam
+    sd = synth.clam_state(1024, "small", True, False, 2, seed=71, peak=3.0)
+    m = _load(clam.CLAM_SB(gate=True, size_arg="small", in_dim=1024, precision="bf16"), sd).eval()
+    feats, _, _ = synth.make_bags([100000, 2500], 1024, 3, seed=72)
+    with torch.no_grad():
+        want = torch.cat([O.clam_sb_bag(f, sd, gate=True)[0] for f in feats], 0)
+    out, _ = m([f.to(DEV) for f in feats])
+    assert_close(out, want, BF16_OUT, "100k-patch bag")
+    out.sum().backward()
+    g = m.attention_net[0].weight.grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+
+
 @pytest.mark.parametrize("gate", [True, False])
 @pytest.mark.parametrize("dropout", [False, True])
 @pytest.mark.parametrize("subtyping", [False, True])
