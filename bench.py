@@ -36,7 +36,7 @@ UNIT = "bags/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="murcl", choices=["murcl", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MURCL_PRECISION", "bf16"), choices=["bf16", "fp32"])
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--clusters", type=int, default=10)
     ap.add_argument("--min-patches", type=int, default=500)
     ap.add_argument("--max-patches", type=int, default=15500)
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-bags", type=int, default=8, help="slides in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -92,7 +92,7 @@ class Clocks:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:

@@ -85,6 +85,70 @@ __global__ void __launch_bounds__(256) ntx_coef_kernel(float* __restrict__ gram,
   gram[i] = c;
 }
 
+// Small-batch contractions (2B <= 1024, the single-GPU case): 32x32 output tiles, 256 threads, 2x2 outputs per
+// thread, operands staged in shared memory.  Many small CTAs instead of a handful of 128x128 GEMM tiles.
+__global__ void __launch_bounds__(256) ntx_gram_small_kernel(const float* __restrict__ zn, int R, int d, float* __restrict__ gram) {
+  extern __shared__ float sm[];                       // [32][d+1] rows of tile a, [32][d+1] rows of tile b
+  const int ld = d + 1;
+  float* sa = sm;
+  float* sb = sm + 32 * ld;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * d; i += blockDim.x) {
+    const int r = i / d, c = i % d;
+    sa[r * ld + c] = (a0 + r < R) ? zn[(int64_t)(a0 + r) * d + c] : 0.f;
+    sb[r * ld + c] = (b0 + r < R) ? zn[(int64_t)(b0 + r) * d + c] : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;         // 16 x 16 threads, 2 x 2 outputs each
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k = 0; k < d; ++k) {
+    const float x0 = sa[(ty * 2) * ld + k], x1 = sa[(ty * 2 + 1) * ld + k];
+    const float y0 = sb[(tx * 2) * ld + k], y1 = sb[(tx * 2 + 1) * ld + k];
+    acc[0][0] = fmaf(x0, y0, acc[0][0]); acc[0][1] = fmaf(x0, y1, acc[0][1]);
+    acc[1][0] = fmaf(x1, y0, acc[1][0]); acc[1][1] = fmaf(x1, y1, acc[1][1]);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int a = a0 + ty * 2 + i, b = b0 + tx * 2 + j;
+      if (a < R && b < R) gram[(int64_t)a * R + b] = acc[i][j];
+    }
+}
+
+// cz[a, j] = sum_b C[a, b] * zn[b, j]
+__global__ void __launch_bounds__(256) ntx_cz_small_kernel(const float* __restrict__ coef, const float* __restrict__ zn, int R,
+                                                           int d, float* __restrict__ cz) {
+  __shared__ float sc[32][33];                        // C tile [a][b]
+  __shared__ float sz[32][33];                        // zn tile [b][j]
+  const int a0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int b0 = 0; b0 < R; b0 += 32) {
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      const int r = i >> 5, c = i & 31;
+      sc[r][c] = (a0 + r < R && b0 + c < R) ? coef[(int64_t)(a0 + r) * R + b0 + c] : 0.f;
+      sz[r][c] = (b0 + r < R && j0 + c < d) ? zn[(int64_t)(b0 + r) * d + j0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float x0 = sc[ty * 2][k], x1 = sc[ty * 2 + 1][k];
+      const float y0 = sz[k][tx * 2], y1 = sz[k][tx * 2 + 1];
+      acc[0][0] = fmaf(x0, y0, acc[0][0]); acc[0][1] = fmaf(x0, y1, acc[0][1]);
+      acc[1][0] = fmaf(x1, y0, acc[1][0]); acc[1][1] = fmaf(x1, y1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int a = a0 + ty * 2 + i, c = j0 + tx * 2 + j;
+      if (a < R && c < d) cz[(int64_t)a * d + c] = acc[i][j];
+    }
+}
+
 // dz_a from g_a = (C zn)_a * inv_tau / R through the normalisation; one warp per row.
 __global__ void __launch_bounds__(256) ntx_finish_kernel(const float* __restrict__ cz, const float* __restrict__ zn,
                                                          const float* __restrict__ inv_norm, int rows, int d, float scale,
@@ -135,7 +199,13 @@ int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float*
   int rc = check_launch("ntx_normalize_kernel");
   if (rc != MURCL_OK) return rc;
   // Gram matrix: [R,d] x [R,d]^T -> [R,R]
-  rc = simt_linear_fwd(zn, zn, nullptr, gram, R, R, d, MURCL_ACT_NONE, MURCL_F32, MURCL_F32, st, scratch, scratch_floats);
+  const bool small = R <= 1024 && (size_t)(64 * (d + 1)) * sizeof(float) <= 48 * 1024;
+  if (small) {
+    ntx_gram_small_kernel<<<dim3(ceil_div(R, 32), ceil_div(R, 32)), 256, sizeof(float) * 64 * (d + 1), st>>>(zn, R, d, gram);
+    rc = check_launch("ntx_gram_small_kernel");
+  } else {
+    rc = simt_linear_fwd(zn, zn, nullptr, gram, R, R, d, MURCL_ACT_NONE, MURCL_F32, MURCL_F32, st, scratch, scratch_floats);
+  }
   if (rc != MURCL_OK) return rc;
   ntx_rows_kernel<<<R, 256, 0, st>>>(gram, B, inv_tau, lse, row_loss, cos_pair);
   rc = check_launch("ntx_rows_kernel");
@@ -147,7 +217,12 @@ int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float*
   rc = check_launch("ntx_coef_kernel");
   if (rc != MURCL_OK) return rc;
   // C zn: [R,R] x [R,d] -> [R,d]   (dx = dy . w with dy = C, w = zn)
-  rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, 1.f, MURCL_F32, st, scratch, scratch_floats);
+  if (small) {
+    ntx_cz_small_kernel<<<dim3(ceil_div(d, 32), ceil_div(R, 32)), 256, 0, st>>>(gram, zn, R, d, cz);
+    rc = check_launch("ntx_cz_small_kernel");
+  } else {
+    rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, 1.f, MURCL_F32, st, scratch, scratch_floats);
+  }
   if (rc != MURCL_OK) return rc;
   ntx_finish_kernel<<<ceil_div(R, 8), 256, 0, st>>>(cz, zn, inv_norm, R, d, inv_tau / (float)R, dz);
   return check_launch("ntx_finish_kernel");

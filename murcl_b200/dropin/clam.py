@@ -88,18 +88,18 @@ class CLAM_SB(nn.Module):
         initialize_weights(self)
 
     def relocate(self):
-        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self.attention_net = self.attention_net.to(device)
-        self.classifiers = self.classifiers.to(device)
-        self.instance_classifiers = self.instance_classifiers.to(device)
+        """Move the sub-modules to the GPU when there is one (clam.py:86-90)."""
+        target = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        for name in ("attention_net", "classifiers", "instance_classifiers"):
+            setattr(self, name, getattr(self, name).to(target))
 
     @staticmethod
     def create_positive_targets(length, device):
-        return torch.full((length,), 1, device=device).long()
+        return torch.ones(length, dtype=torch.long, device=device)
 
     @staticmethod
     def create_negative_targets(length, device):
-        return torch.full((length,), 0, device=device).long()
+        return torch.zeros(length, dtype=torch.long, device=device)
 
     # ------------------------------------------------------------------------------------------
     def _meta(self, rows):

@@ -14,21 +14,17 @@ from .. import ops
 
 
 class Memory:
+    """Rollout buffer of one view (rlmil.py:7-22): parallel lists, one entry per patch-step."""
+
+    FIELDS = ("actions", "states", "logprobs", "rewards", "is_terminals", "hidden")
+
     def __init__(self):
-        self.actions = []
-        self.states = []
-        self.logprobs = []
-        self.rewards = []
-        self.is_terminals = []
-        self.hidden = []
+        for name in self.FIELDS:
+            setattr(self, name, [])
 
     def clear_memory(self):
-        del self.actions[:]
-        del self.states[:]
-        del self.logprobs[:]
-        del self.rewards[:]
-        del self.is_terminals[:]
-        del self.hidden[:]
+        for name in self.FIELDS:
+            getattr(self, name).clear()
 
 
 def _gru_params(gru: nn.GRU):
@@ -162,30 +158,27 @@ class PPO:
         return self.policy_old.act_views(states, memories, restart_batch, training)
 
     def update(self, memory):
-        """PPO-clip update of rlmil.py:152-184 (discounted rewards, K epochs, policy_old <- policy)."""
-        rewards = []
-        discounted_reward = 0
-        for reward in reversed(memory.rewards):
-            discounted_reward = reward + (self.gamma * discounted_reward)
-            rewards.insert(0, discounted_reward)
-        rewards = torch.cat(rewards, 0).cuda()
-        rewards = (rewards - rewards.mean()) / (rewards.std() + 1e-5)
+        """PPO-clip update (rlmil.py:152-184): discounted returns normalised over the whole rollout, K epochs of the
+        clipped surrogate + 0.5 * value MSE - 0.01 * entropy, then policy_old <- policy."""
+        returns, running = [], 0
+        for reward in memory.rewards[::-1]:
+            running = reward + self.gamma * running
+            returns.append(running)
+        returns = torch.cat(returns[::-1], 0).cuda()
+        returns = (returns - returns.mean()) / (returns.std() + 1e-5)
 
-        old_states = torch.stack(memory.states, 0).cuda().detach()
-        old_actions = torch.stack(memory.actions, 0).cuda().detach()
-        old_logprobs = torch.stack(memory.logprobs, 0).cuda().detach()
-
+        states, actions, old_logprobs = (torch.stack(seq, 0).cuda().detach()
+                                         for seq in (memory.states, memory.actions, memory.logprobs))
+        lo, hi = 1 - self.eps_clip, 1 + self.eps_clip
         for _ in range(self.K_epochs):
-            logprobs, state_values, dist_entropy = self.policy.evaluate(old_states, old_actions)
-            ratios = torch.exp(logprobs - old_logprobs.detach())
-            advantages = rewards - state_values.detach()
-            surr1 = ratios * advantages
-            surr2 = torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages
-            loss = -torch.min(surr1, surr2) + 0.5 * self.MseLoss(state_values, rewards) - 0.01 * dist_entropy
+            logprobs, values, entropy = self.policy.evaluate(states, actions)
+            ratio = (logprobs - old_logprobs).exp()
+            advantage = returns - values.detach()
+            surrogate = torch.min(ratio * advantage, ratio.clamp(lo, hi) * advantage)
+            loss = 0.5 * self.MseLoss(values, returns) - surrogate - 0.01 * entropy
             self.optimizer.zero_grad()
             loss.mean().backward()
             self.optimizer.step()
-
         self.policy_old.load_state_dict(self.policy.state_dict())
 
 
