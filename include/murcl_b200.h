@@ -84,9 +84,11 @@ int murcl_pack_gather(const void* feats, int feat_dtype, int D, const int32_t* s
 /* ---- dense layers: every nn.Linear on the path (abmil.py:12-32, clam.py:18-77,
  *      dsmil.py:9,54-59, rlmil.py:40-53,199-200) ----------------------------------------- */
 
-/* y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]).  x,w in `dtype`; y in `out_dtype`; bias fp32/NULL. */
+/* y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]).  x,w in `dtype`; y in `out_dtype`; bias fp32/NULL.
+ * relu_bits (may be NULL; needs act = RELU, N % 64 == 0): receives one bit per output, bit (n % 64) of word
+ * [(n / 64) * M + m] = (y[m,n] > 0) - 1/16 of the bytes of a bf16 activation, consumed by murcl_linear_bwd_input. */
 int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K,
-                     int act, int dtype, int out_dtype, int backend, void* stream);
+                     int act, int dtype, int out_dtype, int backend, uint64_t* relu_bits, void* stream);
 
 /* dx[M,K] = dy[M,N] . w[N,K]; when relu_src != NULL (shape [M,K], storage `dtype`) the result is
  * multiplied by (relu_src > 0), i.e. it is the gradient w.r.t. the previous layer's
@@ -95,11 +97,12 @@ int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, i
  * the caller) the column sums of the stored result are accumulated into it: dx is the next layer's dZ, so this
  * is that layer's bias gradient, produced without another pass over dx.  out_scale (0 or 1 = none) multiplies
  * the masked result: it is 1/(1-p) when relu_src was dropped out after its ReLU (clam.py:70-71), since the zeros
- * of relu_src then mark "inactive OR dropped". */
+ * of relu_src then mark "inactive OR dropped".  relu_bits (may be NULL, needs K % 64 == 0) is the bit mask
+ * murcl_linear_fwd wrote for that activation; when given it replaces the read of relu_src. */
 int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K,
                            const void* relu_src, const float* row_scale, const float* row_vec,
-                           const int32_t* row_seg, float* col_sum, float out_scale, int dtype, int backend,
-                           void* stream);
+                           const int32_t* row_seg, float* col_sum, float out_scale, const uint64_t* relu_bits,
+                           int dtype, int backend, void* stream);
 
 /* dw[N,K] (fp32) = dy[M,N]^T . x[M,K], db[N] (fp32, may be NULL) = column sums of dy.
  * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats. */

@@ -30,8 +30,8 @@ SIGNATURES = {
     "murcl_csr_rank_patches": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "murcl_pack_select": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "murcl_pack_gather": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _p]),
-    "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p]),
-    "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _i, _i, _p]),
+    "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _p, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),
     "murcl_linear_bwd_weight": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _p, _p]),
     "murcl_attn_score_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p]),

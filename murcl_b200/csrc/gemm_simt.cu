@@ -29,6 +29,7 @@ struct GemmParams {
   const float* row_scale;   // [M] or null: C += row_scale[m] * row_vec[row_seg[m]*N + n]
   const float* row_vec;
   const int32_t* row_seg;
+  const unsigned long long* relu_bits;   // [N/64][M] bit mask (bit = activation > 0), alternative to relu_src
   float out_scale;          // applied last (1/(1-p) of a dropout that followed the masked ReLU); 0 means 1
   int64_t k_chunk;          // K range per blockIdx.z
   int64_t split_stride;     // elements between split outputs (C is fp32 workspace when gridDim.z > 1)
@@ -154,7 +155,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
       if (p.bias) v += p.bias[n];
       v = apply_act(v, p.act, n, p.N);
       if (rv) v = fmaf(rs, rv[n], v);
-      if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) v = 0.f;
+      if (p.relu_bits) {
+        if (!((p.relu_bits[(int64_t)(n >> 6) * p.M + m] >> (n & 63)) & 1ull)) v = 0.f;
+      } else if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) {
+        v = 0.f;
+      }
       if (p.out_scale != 0.f) v *= p.out_scale;
       Store<TC>::store(static_cast<TC*>(p.C) + m * p.ldc + n, v);
     }
@@ -183,9 +188,33 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __res
   if (p.bias) v += p.bias[n];
   v = apply_act(v, p.act, n, p.N);
   if (p.row_scale) v = fmaf(p.row_scale[m], p.row_vec[(int64_t)p.row_seg[m] * p.N + n], v);
-  if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) v = 0.f;
+  if (p.relu_bits) {
+    if (!((p.relu_bits[(int64_t)(n >> 6) * p.M + m] >> (n & 63)) & 1ull)) v = 0.f;
+  } else if (p.relu_src && !(Store<TC>::load(static_cast<const TC*>(p.relu_src) + m * p.ldc + n) > 0.f)) {
+    v = 0.f;
+  }
   if (p.out_scale != 0.f) v *= p.out_scale;
   Store<TC>::store(static_cast<TC*>(p.C) + m * p.ldc + n, v);
+}
+
+// bits[(n/64) * M + m] bit (n%64) = y[m,n] > 0   (the SIMT forward's companion to the tcgen05 epilogue's bit mask)
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bits_kernel(const T* __restrict__ y, int64_t M, int N, unsigned long long* __restrict__ bits) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slab = blockIdx.y;
+  if (m >= M) return;
+  unsigned long long b = 0ull;
+  const T* r = y + m * N + slab * 64;
+  for (int i = 0; i < 64; ++i)
+    if (Store<T>::load(r + i) > 0.f) b |= 1ull << i;
+  bits[(int64_t)slab * M + m] = b;
+}
+
+int launch_relu_bits(const void* y, int64_t M, int N, int dtype, unsigned long long* bits, cudaStream_t st) {
+  dim3 grid(ceil_div(M, 256), N / 64);
+  if (dtype == MURCL_F32) relu_bits_kernel<float><<<grid, 256, 0, st>>>((const float*)y, M, N, bits);
+  else relu_bits_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, M, N, bits);
+  return check_launch("relu_bits_kernel");
 }
 
 int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st) {
@@ -347,13 +376,13 @@ int simt_linear_fwd(const void* x, const void* w, const float* bias, void* y, in
 
 int simt_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
                           const float* row_scale, const float* row_vec, const int32_t* row_seg, float out_scale, int dtype,
-                          cudaStream_t st, float* ws, int64_t ws_floats) {
+                          cudaStream_t st, float* ws, int64_t ws_floats, const unsigned long long* relu_bits) {
   GemmParams p{};
   // C = dx [M, K]; reduction over N; A = dy [M,N] k-contiguous; B(n'=k_in, k'=n) = w[n, k_in] n'-contiguous.
   p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
   p.relu_src = relu_src; p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.k_chunk = N;
-  p.out_scale = out_scale;
-  if (N <= SKINNY_N) {
+  p.out_scale = out_scale; p.relu_bits = relu_bits;
+  if (N <= SKINNY_N && relu_bits == nullptr) {
     const int grid = ceil_div(M, 8);
     if (dtype == MURCL_F32)
       skinny_dgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)w, (float*)dx, M, N, K,

@@ -53,6 +53,8 @@ struct Params {
   const int32_t* row_seg;
   float* col_sum;     // EPI_DGRAD: accumulated column sums of the stored result (may be null)
   float out_scale;    // EPI_DGRAD: final scale (1/(1-p) of a dropout that followed the masked ReLU)
+  unsigned long long* bits_out;        // EPI_FWD + ReLU: 1 bit per output (y > 0), layout [N/64][M] (may be null)
+  const unsigned long long* bits_in;   // EPI_DGRAD: the same bit mask instead of re-reading relu_src (may be null)
   int splits;
   int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
   int64_t split_stride;
@@ -408,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int SLAB_COLS = 128 / (int)sizeof(TOUT);      // 64 bf16 or 32 fp32 columns = 128 B per row
     int as = 0;
     uint32_t aph = 0, mph = 0;
-    const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr;
+    const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr && p.bits_in == nullptr;
     const bool want_colsum = (EPI == EPI_DGRAD) && sizeof(TOUT) == 2 && p.col_sum != nullptr;
     int acc_nb = -1;
     const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
@@ -497,6 +499,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             act_slab<sizeof(TOUT) == 2, SLAB_COLS>(v, p.act, col0, p.N);
+            if (sizeof(TOUT) == 2 && p.bits_out != nullptr && row < p.M) {
+              // one 64-bit word per (row, 64-column slab); consecutive rows are consecutive words -> coalesced
+              unsigned int lo = 0u, hi = 0u;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                lo |= (v[i] > 0.f ? 1u : 0u) << i;
+                hi |= (v[(32 + i) % SLAB_COLS] > 0.f ? 1u : 0u) << i;
+              }
+              p.bits_out[(int64_t)(col0 >> 6) * p.M + row] = ((unsigned long long)hi << 32) | lo;
+            }
           } else {
             if (rv != nullptr) {
 #pragma unroll
@@ -506,6 +518,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   v[i] = fmaf(rs, g4.x, v[i]); v[i + 1] = fmaf(rs, g4.y, v[i + 1]);
                   v[i + 2] = fmaf(rs, g4.z, v[i + 2]); v[i + 3] = fmaf(rs, g4.w, v[i + 3]);
                 }
+              }
+            }
+            if (p.bits_in != nullptr) {
+              const unsigned long long bits = row < p.M ? __ldg(p.bits_in + (int64_t)(col0 >> 6) * p.M + row) : 0ull;
+              const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (!((lo >> i) & 1u)) v[i] = 0.f;
+                if (!((hi >> i) & 1u)) v[(32 + i) % SLAB_COLS] = 0.f;
+              }
+              if (p.out_scale != 1.f) {
+#pragma unroll
+                for (int i = 0; i < SLAB_COLS; ++i) v[i] *= p.out_scale;
               }
             }
             if (has_mask) {
@@ -727,7 +752,7 @@ bool tc_bwd_weight_supported(int64_t M, int N, int K, int dtype) {
 }
 
 int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act, int out_dtype,
-                  cudaStream_t st) {
+                  unsigned long long* relu_bits, cudaStream_t st) {
   if (!aligned16(x) || !aligned16(w) || !aligned16(y)) {
     set_error("linear_fwd(tcgen05): operands must be 16-byte aligned");
     return MURCL_EINVAL;
@@ -749,7 +774,7 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
     return MURCL_EINVAL;
   }
   Params p{};
-  p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = y; p.bias = bias; p.act = act;
+  p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = y; p.bias = bias; p.act = act; p.bits_out = relu_bits;
   p.splits = 1; p.k_chunk = ((int64_t)K + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
   if (pair) {
@@ -769,7 +794,7 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
 
 int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
                         const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum,
-                        float out_scale, cudaStream_t st) {
+                        float out_scale, const unsigned long long* relu_bits, cudaStream_t st) {
   if (!aligned16(dy) || !aligned16(w) || !aligned16(dx) || (relu_src && !aligned16(relu_src))) {
     set_error("linear_bwd_input(tcgen05): operands must be 16-byte aligned");
     return MURCL_EINVAL;
@@ -786,7 +811,7 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   p.M = M; p.N = K; p.K = N; p.ldc = K; p.C = dx;
   p.relu_src = static_cast<const __nv_bfloat16*>(relu_src);
   p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg; p.col_sum = col_sum;
-  p.out_scale = out_scale;
+  p.out_scale = out_scale; p.bits_in = relu_bits;
   p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
   CUtensorMap mc, mm;

@@ -6,16 +6,18 @@ namespace murcl {
 int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t,
                     float* ws = nullptr, int64_t ws_floats = 0);
 int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                          const int32_t*, float, int, cudaStream_t, float* ws = nullptr, int64_t ws_floats = 0);
+                          const int32_t*, float, int, cudaStream_t, float* ws = nullptr, int64_t ws_floats = 0,
+                          const unsigned long long* relu_bits = nullptr);
+int launch_relu_bits(const void* y, int64_t M, int N, int dtype, unsigned long long* bits, cudaStream_t st);
 int64_t simt_linear_bwd_weight_workspace(int64_t, int, int);
 int simt_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, float*, cudaStream_t);
 
 bool tc_fwd_supported(int64_t M, int N, int K, int dtype, int out_dtype);
 bool tc_bwd_input_supported(int64_t M, int N, int K, int dtype);
 bool tc_bwd_weight_supported(int64_t M, int N, int K, int dtype);
-int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, cudaStream_t);
+int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, unsigned long long*, cudaStream_t);
 int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                        const int32_t*, float*, float, cudaStream_t);
+                        const int32_t*, float*, float, const unsigned long long*, cudaStream_t);
 int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
 int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t);
 
@@ -29,25 +31,30 @@ static bool valid_dtype(int d) { return d == MURCL_F32 || d == MURCL_BF16; }
 extern "C" {
 
 int murcl_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t M, int N, int K, int act,
-                     int dtype, int out_dtype, int backend, void* stream) {
+                     int dtype, int out_dtype, int backend, uint64_t* relu_bits, void* stream) {
   MURCL_REQUIRE(x && w && y, "linear_fwd: null pointer");
   MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
   MURCL_REQUIRE(valid_dtype(dtype) && valid_dtype(out_dtype), "linear_fwd: bad dtype");
   MURCL_REQUIRE(act >= MURCL_ACT_NONE && act <= MURCL_ACT_TANH_SIGMOID, "linear_fwd: bad activation %d", act);
   MURCL_REQUIRE(act != MURCL_ACT_TANH_SIGMOID || (N % 2) == 0, "linear_fwd: gated activation needs even N");
+  MURCL_REQUIRE(relu_bits == nullptr || (act == MURCL_ACT_RELU && N % 64 == 0 && dtype == out_dtype),
+                "linear_fwd: the ReLU bit mask needs act=RELU, N %% 64 == 0 and matching storage types");
   if (M == 0) return MURCL_OK;
   const bool tc_ok = tc_fwd_supported(M, N, K, dtype, out_dtype);
   if (backend == MURCL_GEMM_TCGEN05 && !tc_ok) {
     set_error("linear_fwd: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d->%d", (long long)M, N, K, dtype, out_dtype);
     return MURCL_EUNSUPPORTED;
   }
-  if (backend != MURCL_GEMM_SIMT && tc_ok) return tc_linear_fwd(x, w, bias, y, M, N, K, act, out_dtype, as_stream(stream));
-  return simt_linear_fwd(x, w, bias, y, M, N, K, act, dtype, out_dtype, as_stream(stream));
+  if (backend != MURCL_GEMM_SIMT && tc_ok)
+    return tc_linear_fwd(x, w, bias, y, M, N, K, act, out_dtype, reinterpret_cast<unsigned long long*>(relu_bits), as_stream(stream));
+  int rc = simt_linear_fwd(x, w, bias, y, M, N, K, act, dtype, out_dtype, as_stream(stream));
+  if (rc != MURCL_OK || relu_bits == nullptr) return rc;
+  return launch_relu_bits(y, M, N, out_dtype, reinterpret_cast<unsigned long long*>(relu_bits), as_stream(stream));
 }
 
 int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
                            const float* row_scale, const float* row_vec, const int32_t* row_seg, float* col_sum,
-                           float out_scale, int dtype, int backend, void* stream) {
+                           float out_scale, const uint64_t* relu_bits, int dtype, int backend, void* stream) {
   MURCL_REQUIRE(dy && w && dx, "linear_bwd_input: null pointer");
   MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_input: bad shape");
   MURCL_REQUIRE(valid_dtype(dtype), "linear_bwd_input: bad dtype");
@@ -55,15 +62,19 @@ int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, i
                 "linear_bwd_input: row_scale, row_vec and row_seg must be given together");
   if (M == 0) return MURCL_OK;
   if (out_scale == 0.f) out_scale = 1.f;
-  MURCL_REQUIRE(out_scale == 1.f || relu_src != nullptr, "linear_bwd_input: out_scale is the dropout factor of a masked ReLU");
+  MURCL_REQUIRE(out_scale == 1.f || relu_src != nullptr || relu_bits != nullptr,
+                "linear_bwd_input: out_scale is the dropout factor of a masked ReLU");
+  MURCL_REQUIRE(relu_bits == nullptr || K % 64 == 0, "linear_bwd_input: the ReLU bit mask needs K %% 64 == 0");
+  const unsigned long long* bits = reinterpret_cast<const unsigned long long*>(relu_bits);
   const bool tc_ok = tc_bwd_input_supported(M, N, K, dtype);
   if (backend == MURCL_GEMM_TCGEN05 && !tc_ok) {
     set_error("linear_bwd_input: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d", (long long)M, N, K, dtype);
     return MURCL_EUNSUPPORTED;
   }
   if (backend != MURCL_GEMM_SIMT && tc_ok)
-    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, col_sum, out_scale, as_stream(stream));
-  int rc = simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, out_scale, dtype, as_stream(stream));
+    return tc_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, col_sum, out_scale, bits, as_stream(stream));
+  int rc = simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, out_scale, dtype, as_stream(stream),
+                                 nullptr, 0, bits);
   if (rc != MURCL_OK || col_sum == nullptr) return rc;
   return colsum_impl(dx, M, K, dtype, col_sum, as_stream(stream));       // same sums, separate pass
 }

@@ -17,7 +17,8 @@ namespace murcl {
 int simt_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, int, int, int, int, cudaStream_t,
                     float* ws, int64_t ws_floats);
 int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
-                          const int32_t*, float, int, cudaStream_t, float* ws, int64_t ws_floats);
+                          const int32_t*, float, int, cudaStream_t, float* ws, int64_t ws_floats,
+                          const unsigned long long* relu_bits);
 
 constexpr float COS_EPS = 1e-8f;
 
@@ -221,7 +222,7 @@ int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float*
     ntx_cz_small_kernel<<<dim3(ceil_div(d, 32), ceil_div(R, 32)), 256, 0, st>>>(gram, zn, R, d, cz);
     rc = check_launch("ntx_cz_small_kernel");
   } else {
-    rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, 1.f, MURCL_F32, st, scratch, scratch_floats);
+    rc = simt_linear_bwd_input(gram, zn, cz, R, R, d, nullptr, nullptr, nullptr, nullptr, 1.f, MURCL_F32, st, scratch, scratch_floats, nullptr);
   }
   if (rc != MURCL_OK) return rc;
   ntx_finish_kernel<<<ceil_div(R, 8), 256, 0, st>>>(cz, zn, inv_norm, R, d, inv_tau / (float)R, dz);

@@ -118,7 +118,9 @@ def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
+def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None, relu_bits=False):
+    """act(x w^T + bias).  ``relu_bits=True`` (ReLU layers, N % 64 == 0) also returns the 1-bit-per-output mask
+    ``[N/64, M]`` int64 that ``linear_bwd_input`` takes instead of re-reading the activation."""
     _chk(x, "linear_fwd.x"); _chk(w, "linear_fwd.w")
     if x.dtype != w.dtype:
         raise MurclError(f"linear_fwd: x is {x.dtype} but w is {w.dtype}")
@@ -130,13 +132,15 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None):
     y = torch.empty((M, N), device=x.device, dtype=out_dtype)
     if bias is not None:
         _chk(bias, "linear_fwd.bias", torch.float32)
+    bits = torch.empty((N // 64, M), device=x.device, dtype=torch.int64) if relu_bits else None
     with _Timed("linear_fwd" if M >= 4096 else "head_fwd", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_fwd(_p(x), _p(w), _p(bias), _p(y), M, N, K, act, _dt(x), _DT[out_dtype], _backend(),
-                                           _s()), "murcl_linear_fwd")
-    return y
+                                           _p(bits), _s()), "murcl_linear_fwd")
+    return (y, bits) if relu_bits else y
 
 
-def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None, col_sum=None, out_scale=1.0):
+def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None, col_sum=None, out_scale=1.0,
+                     relu_bits=None):
     _chk(dy, "linear_bwd_input.dy"); _chk(w, "linear_bwd_input.w")
     if dy.dtype != w.dtype:
         raise MurclError(f"linear_bwd_input: dy is {dy.dtype} but w is {w.dtype}")
@@ -149,7 +153,8 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
     with _Timed("linear_bwd_input" if M >= 4096 else "head_bwd_input", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
-                                                 _p(row_seg), _p(col_sum), float(out_scale), _dt(dy), _backend(), _s()),
+                                                 _p(row_seg), _p(col_sum), float(out_scale), _p(relu_bits), _dt(dy), _backend(),
+                                                 _s()),
               "murcl_linear_bwd_input")
     return dx
 
@@ -422,6 +427,7 @@ class _MILAggregate(torch.autograd.Function):
         B, gated = meta["B"], meta["gated"]
         D = wc.numel()
         hs = [cast(x.detach().contiguous(), dt)]
+        hbits = [None]                          # per activation: 1-bit ReLU mask (or None -> the backward reads h itself)
         enc_w = []
         drop = meta.get("drop")                 # train-mode dropout: {"enc": [p after layer 1..n], "attn": p}
         seeds = None
@@ -430,10 +436,15 @@ class _MILAggregate(torch.autograd.Function):
         for i in range(0, len(enc), 2):
             w = weight_as(enc[i], dt)
             enc_w.append(w)
-            h = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU)
-            if drop is not None and drop["enc"][i // 2] > 0:
-                dropout_(h, drop["enc"][i // 2], seeds[i // 2:i // 2 + 1])
+            dropped = drop is not None and drop["enc"][i // 2] > 0
+            if w.shape[0] % 64 == 0 and not dropped:
+                h, hb = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU, relu_bits=True)
+            else:
+                h, hb = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU), None
+            if dropped:
+                dropout_(h, drop["enc"][i // 2], seeds[i // 2:i // 2 + 1])   # mask = zeros of h (inactive or dropped)
             hs.append(h)
+            hbits.append(hb)
         H = hs[-1]
         wab_s = weight_as(wab, dt)
         uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
@@ -473,6 +484,7 @@ class _MILAggregate(torch.autograd.Function):
         ctx.D = D
         ctx.consumed = False
         ctx.x_dtype = x.dtype
+        ctx.hbits = hbits
         ctx.save_for_backward(offsets, row_seg, wab_s, wc_f, uv, p, M, *hs, *enc_w, *saved_inst)
         ctx.mark_non_differentiable(p, s, preds)
         return M, p, s, inst_loss, preds
@@ -498,14 +510,16 @@ class _MILAggregate(torch.autograd.Function):
         q_enc = [1.0 / (1.0 - pe) if drop is not None and pe > 0 else 1.0 for pe in (drop["enc"] if drop else [0.0] * n_enc)]
         dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated, q_attn)    # uv now holds d(pre-activation)
         dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
-        relu_src = H if n_enc > 0 else None
+        hbits = ctx.hbits
+        relu_src = H if (n_enc > 0 and hbits[n_enc] is None) else None
         inst = meta.get("inst")
         # bias gradients ride along as fused column sums of each dZ (the instance-loss scatter below changes dZ
         # after the fact, so that case takes the separate column-sum pass)
         fuse_db = n_enc > 0 and inst is None
         db_next = torch.zeros((n_enc, L), device=uv.device, dtype=torch.float32) if fuse_db else None
         dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg, col_sum=db_next[n_enc - 1] if fuse_db else None,
-                              out_scale=q_enc[n_enc - 1] if n_enc > 0 else 1.0)      # + p_n dM[b] direct term, ReLU mask
+                              out_scale=q_enc[n_enc - 1] if n_enc > 0 else 1.0,
+                              relu_bits=hbits[n_enc] if n_enc > 0 else None)       # + p_n dM[b] direct term, ReLU mask
         d_inst_w = d_inst_b = None
         if inst is not None:
             idx, rows, dlogits, iw = rest
@@ -527,8 +541,9 @@ class _MILAggregate(torch.autograd.Function):
                 db = db_next[l - 1]
             grads_enc = [dw, db] + grads_enc
             if l > 1:
-                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1], col_sum=db_next[l - 2] if fuse_db else None,
-                                      out_scale=q_enc[l - 2])
+                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1] if hbits[l - 1] is None else None,
+                                      col_sum=db_next[l - 2] if fuse_db else None, out_scale=q_enc[l - 2],
+                                      relu_bits=hbits[l - 1])
             elif ctx.needs_input_grad[0]:
                 dz = linear_bwd_input(dz, enc_w[0])
         dx = None

@@ -45,6 +45,13 @@ def test_tc_forward(M, N, K):
     y16 = ops.linear_fwd(xd, wd, bd, ops.ACT_RELU)
     assert y16.dtype == torch.bfloat16
     assert_close(y16.float(), torch.relu(ref).float(), 4e-3, "bf16 relu out")
+    if N % 64 == 0:
+        # 1-bit ReLU mask written by the forward epilogue, consumed by the input-gradient epilogue
+        y2, bits = ops.linear_fwd(xd, wd, bd, ops.ACT_RELU, relu_bits=True)
+        assert torch.equal(y2, y16)
+        n_idx = torch.arange(N, device=DEV)
+        got = ((bits[n_idx // 64] >> (n_idx % 64).unsqueeze(1)) & 1).t().bool()
+        assert torch.equal(got, y16 > 0)
     if N % 2 == 0:
         yg = ops.linear_fwd(xd, wd, bd, ops.ACT_TANH_SIGMOID, torch.float32)
         want = torch.cat([torch.tanh(ref[:, : N // 2]), torch.sigmoid(ref[:, N // 2:])], 1)
@@ -71,6 +78,14 @@ def test_tc_input_grad(M, N, K):
     dx2 = ops.linear_bwd_input(dy.to(DEV), w.to(DEV), relu_src.to(DEV), rs.to(DEV), rv.to(DEV), seg.to(DEV))
     assert_close(dx2.float(), ref2.float(), 4e-3, "row term + mask")
     assert bool(((dx2 == 0) | (relu_src.to(DEV) > 0)).all())
+    if K % 64 == 0:
+        m_idx = torch.arange(M).unsqueeze(1)
+        mask = relu_src > 0
+        words = torch.zeros(K // 64, M, dtype=torch.int64)
+        for kk in range(K):
+            words[kk // 64] |= mask[:, kk].to(torch.int64) << (kk % 64)
+        dx4 = ops.linear_bwd_input(dy.to(DEV), w.to(DEV), None, rs.to(DEV), rv.to(DEV), seg.to(DEV), relu_bits=words.to(DEV))
+        assert torch.equal(dx4, dx2), "bit-mask path must equal the relu_src path"
     # fused column sums of the stored (bf16-rounded) result = bias gradient of the next layer
     cs = torch.zeros(K, device=DEV)
     dx3 = ops.linear_bwd_input(dy.to(DEV), w.to(DEV), relu_src.to(DEV), rs.to(DEV), rv.to(DEV), seg.to(DEV), col_sum=cs)

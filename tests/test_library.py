@@ -37,7 +37,7 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     rc = lib.murcl_pack_gather(None, 0, 8, None, 1, 4, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.murcl_last_error()
-    rc = lib.murcl_linear_fwd(1, 1, None, 1, 4, 0, 4, 0, 0, 0, 0, None)
+    rc = lib.murcl_linear_fwd(1, 1, None, 1, 4, 0, 4, 0, 0, 0, 0, None, None)
     assert rc == -1
     rc = lib.murcl_ntxent_fwd_bwd(1, 0, 4, 1.0, 1, None, None, 1, None)
     assert rc == -1
