@@ -501,11 +501,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             act_slab<sizeof(TOUT) == 2, SLAB_COLS>(v, p.act, col0, p.N);
             if (sizeof(TOUT) == 2 && p.bits_out != nullptr && row < p.M) {
               // one 64-bit word per (row, 64-column slab); consecutive rows are consecutive words -> coalesced
+              // after the ReLU v >= +0, so (v > 0) is the sign bit of the integer negation of its bit pattern;
+              // a funnel shift appends one sign bit per instruction (2 ops per element)
               unsigned int lo = 0u, hi = 0u;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                lo |= (v[i] > 0.f ? 1u : 0u) << i;
-                hi |= (v[(32 + i) % SLAB_COLS] > 0.f ? 1u : 0u) << i;
+              for (int i = 31; i >= 0; --i) {
+                lo = __funnelshift_l(0u - __float_as_uint(v[i]), lo, 1);
+                hi = __funnelshift_l(0u - __float_as_uint(v[(32 + i) % SLAB_COLS]), hi, 1);
               }
               p.bits_out[(int64_t)(col0 >> 6) * p.M + row] = ((unsigned long long)hi << 32) | lo;
             }

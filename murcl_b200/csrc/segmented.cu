@@ -124,19 +124,27 @@ __global__ void __launch_bounds__(256) dsmil_scores_bwd_rows_kernel(const float*
   }
 }
 
-// dq[crit[b,c],:] += sum_n da[n,c] * q[n,:] * inv_sqrt   (one CTA per (bag, class); thread per column)
+// dq[crit[b,c],:] += sum_n da[n,c] * q[n,:] * inv_sqrt.  grid (bag, class, row slice): thread per column, each CTA
+// reduces its slice of the bag's rows and adds it atomically (several slices / classes may share the target row).
 __global__ void __launch_bounds__(128) dsmil_scores_bwd_crit_kernel(const float* __restrict__ q, const float* __restrict__ da,
                                                                     const int32_t* __restrict__ crit,
                                                                     const int64_t* __restrict__ offsets, int C, int Dq,
                                                                     float inv_sqrt, float* __restrict__ dq) {
   const int b = blockIdx.x, c = blockIdx.y;
   const int64_t lo = offsets[b], hi = offsets[b + 1];
+  const int64_t len = hi - lo;
+  const int64_t r0 = lo + len * blockIdx.z / gridDim.z, r1 = lo + len * (blockIdx.z + 1) / gridDim.z;
   const int64_t target = crit[(int64_t)b * C + c];
-  if (target < 0) return;
+  if (target < 0 || r0 >= r1) return;
   for (int d = threadIdx.x; d < Dq; d += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t n = lo; n < hi; ++n) acc = fmaf(da[n * C + c], q[n * Dq + d], acc);
-    atomicAdd(&dq[target * Dq + d], acc * inv_sqrt);
+    float a0 = 0.f, a1 = 0.f;
+    int64_t n = r0;
+    for (; n + 1 < r1; n += 2) {
+      a0 = fmaf(da[n * C + c], q[n * Dq + d], a0);
+      a1 = fmaf(da[(n + 1) * C + c], q[(n + 1) * Dq + d], a1);
+    }
+    if (n < r1) a0 = fmaf(da[n * C + c], q[n * Dq + d], a0);
+    atomicAdd(&dq[target * Dq + d], (a0 + a1) * inv_sqrt);
   }
 }
 
@@ -206,7 +214,10 @@ int murcl_dsmil_scores_bwd(const float* q, const float* da, const int32_t* crit,
   dsmil_scores_bwd_rows_kernel<<<ceil_div(n_rows, 8), 256, 0, st>>>(q, da, crit, row_seg, n_rows, C, Dq, inv, dq);
   int rc = check_launch("dsmil_scores_bwd_rows_kernel");
   if (rc != MURCL_OK) return rc;
-  dsmil_scores_bwd_crit_kernel<<<dim3(B, C), 128, 0, st>>>(q, da, crit, offsets, C, Dq, inv, dq);
+  int slices = (int)((n_rows / (B > 0 ? B : 1) + 255) / 256);          // ~256 rows per CTA
+  if (slices < 1) slices = 1;
+  if (slices > 1024) slices = 1024;
+  dsmil_scores_bwd_crit_kernel<<<dim3(B, C, slices), 128, 0, st>>>(q, da, crit, offsets, C, Dq, inv, dq);
   return check_launch("dsmil_scores_bwd_crit_kernel");
 }
 
