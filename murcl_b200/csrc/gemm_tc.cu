@@ -55,6 +55,7 @@ struct Params {
   float out_scale;    // EPI_DGRAD: final scale (1/(1-p) of a dropout that followed the masked ReLU)
   unsigned long long* bits_out;        // EPI_FWD + ReLU: 1 bit per output (y > 0), layout [N/64][M] (may be null)
   const unsigned long long* bits_in;   // EPI_DGRAD: the same bit mask instead of re-reading relu_src (may be null)
+  int debug;          // MURCL_DEBUG_EPI bit mask (timing experiments only; results are wrong when set)
   int splits;
   int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
   int64_t split_stride;
@@ -98,6 +99,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -202,8 +204,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 layout: address>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout type [61,64) with 2 = SWIZZLE_128B).
@@ -233,7 +235,8 @@ template <int BN, int EPI, int CG>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLABS_PER_WARP = (EPI == 1) ? 2 : 1;          // output slab (+ ReLU-mask slab for the input grad)
+  static constexpr int SLABS_PER_WARP = (EPI == 2) ? 0 : 2;   // (the split-K kernel stores directly) two output slabs (double-buffered stores); the input grad's TMA-loaded
+                                             // ReLU-mask slab takes the place of the second one when it is in use
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: powers of two
@@ -403,8 +406,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) belong to this warp
     const int ew = warp - 2;                               // 0..7
     const int half = ew >> 2;                              // the two warps of a quarter take alternate column slabs
-    const uint32_t out_slab = staging + (uint32_t)ew * (C::SLABS_PER_WARP * SLAB_BYTES);
-    const uint32_t mask_slab = out_slab + SLAB_BYTES;      // only carved for EPI_DGRAD
+    const uint32_t slab_base = staging + (uint32_t)ew * (C::SLABS_PER_WARP * SLAB_BYTES);
+    const uint32_t mask_slab = slab_base + SLAB_BYTES;     // second slab doubles as the ReLU-mask slab (mask mode)
+    uint32_t out_slab = slab_base;
+    uint32_t slab_flip = 0;
     const uint32_t my_row_off = (uint32_t)lane * 128u;
     const uint32_t swz = (uint32_t)(lane & 7);             // 128B swizzle: 16-byte chunk index ^= row & 7
     constexpr int SLAB_COLS = 128 / (int)sizeof(TOUT);      // 64 bf16 or 32 fp32 columns = 128 B per row
@@ -455,6 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c0 = half * 32; c0 < BN; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(t_row + (uint32_t)c0, r);
+          tmem_ld_wait();
           const int col0 = n0 + c0;
           if (row < p.M && col0 < p.N) {
             float* dst = static_cast<float*>(p.C) + (int64_t)sp * p.split_stride + row * p.ldc + col0;
@@ -481,14 +487,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int col0 = n0 + c0;
           if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this slab is in range
           float v[SLAB_COLS];
+          if (p.debug & 4) {
 #pragma unroll
-          for (int j = 0; j < SLAB_COLS / 32; ++j) {
-            uint32_t r[32];
-            tmem_ld32(t_row + (uint32_t)(c0 + 32 * j), r);
+            for (int i = 0; i < SLAB_COLS; ++i) v[i] = 1.f;
+          } else {
+            uint32_t r[SLAB_COLS / 32][32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[32 * j + i] = __uint_as_float(r[i]);
+            for (int j = 0; j < SLAB_COLS / 32; ++j) tmem_ld32(t_row + (uint32_t)(c0 + 32 * j), r[j]);   // both in flight
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < SLAB_COLS / 32; ++j)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[32 * j + i] = __uint_as_float(r[j][i]);
           }
-          if (EPI == EPI_FWD) {
+          if (EPI == EPI_FWD && !(p.debug & 2)) {
             if (p.bias != nullptr) {
 #pragma unroll
               for (int i = 0; i < SLAB_COLS; i += 4) {
@@ -511,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
               p.bits_out[(int64_t)(col0 >> 6) * p.M + row] = ((unsigned long long)hi << 32) | lo;
             }
-          } else {
+          } else if (EPI == EPI_DGRAD) {
             if (rv != nullptr) {
 #pragma unroll
               for (int i = 0; i < SLAB_COLS; i += 4) {
@@ -576,8 +588,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
+          if (p.debug & 1) continue;                        // timing experiment: no staging, no store
           // stage the slab (swizzled like the TMA box) and hand it to the bulk-store engine
-          if (lane == 0) bulk_wait_read0();                 // previous store has finished reading the slab
+          if (has_mask) {
+            if (lane == 0) bulk_wait_read0();               // single output slab: the previous store has read it
+          } else {
+            out_slab = slab_base + slab_flip * SLAB_BYTES;  // two output slabs: only the store before last must be done
+            slab_flip ^= 1u;
+            if (lane == 0) bulk_wait_read1();
+          }
           __syncwarp();
           if (sizeof(TOUT) == 2) {
 #pragma unroll
@@ -691,6 +710,13 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     }
     configured = true;
   }
+  static int debug = -1;
+  if (debug < 0) {
+    const char* e = getenv("MURCL_DEBUG_EPI");
+    debug = e ? atoi(e) : 0;
+  }
+  Params pp = p;
+  pp.debug = debug;
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   const int slots = sm_count() / CG;                          // persistent: one CTA (or CTA pair) per SM (pair)
   const int grid = (int)(total < slots ? total : slots) * CG;
@@ -706,7 +732,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mm, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mm, pp);
   if (e != cudaSuccess) {
     set_error("gemm_tc_kernel launch failed: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1, std::memory_order_relaxed);
