@@ -56,6 +56,7 @@ struct Params {
   unsigned long long* bits_out;        // EPI_FWD + ReLU: 1 bit per output (y > 0), layout [N/64][M] (may be null)
   const unsigned long long* bits_in;   // EPI_DGRAD: the same bit mask instead of re-reading relu_src (may be null)
   int debug;          // MURCL_DEBUG_EPI bit mask (timing experiments only; results are wrong when set)
+  unsigned long long* trace;   // debug & 8: CTA 0 writes %globaltimer stamps per tile: [tile][mma_start, mma_end, epi_start, epi_end]
   int splits;
   int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
   int64_t split_stride;
@@ -154,8 +155,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Relaxed: the arrive only hands the (already drained, tcgen05.wait::ld + fence) accumulator back to the MMA issuer;
+// a release at cluster scope would also wait for this warp's outstanding global stores (~1.7 us per tile, measured).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a CTA pair: data lands in the issuing CTA's smem, the transaction bytes are counted on the barrier
 // at `bar_cluster_addr` (the leader CTA's barrier).
@@ -244,6 +247,13 @@ struct Cfg {
                                     BN * 4 /*column-sum accumulator*/;
 };
 
+#define MURCL_STAMP(slot)                                                                         \
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && c0 == 0) {                              \
+    unsigned long long ts_;                                                                     \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));                                     \
+    p.trace[(int64_t)24 * 2048 + ((t - tile_first) / tile_step) * 8 + (slot)] = ts_;            \
+  }
+
 template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -301,15 +311,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * p.splits;     // m_tiles counts 128*CG-row tiles
-  const int64_t tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  // 32-bit tile arithmetic: 64-bit div/mod is ~1000 cycles for the lone MMA-issuing lane, once per tile, on the
+  // critical path (measured as a 0.6 us bubble between tiles)
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;                  // m_tiles counts 128*CG-row tiles
+  const int tile_first = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
   const int k_blocks_full = (int)((p.k_chunk + BLOCK_K - 1) / BLOCK_K);
 
-  auto tile_coords = [&](int64_t t, int& mb, int& nb, int& sp) {
-    nb = (int)(t % p.n_tiles);
-    const int64_t r = t / p.n_tiles;
-    mb = (int)(r % p.m_tiles);
-    sp = (int)(r / p.m_tiles);
+  auto tile_coords = [&](int t, int& mb, int& nb, int& sp) {
+    const unsigned ut = (unsigned)t, nt = (unsigned)p.n_tiles, mt = (unsigned)p.m_tiles;
+    const unsigned r = ut / nt;
+    nb = (int)(ut - r * nt);
+    sp = (int)(r / mt);
+    mb = (int)(r - (unsigned)sp * mt);
   };
   auto k_range = [&](int sp, int64_t& k0, int& nkb) {
     k0 = (int64_t)sp * p.k_chunk;
@@ -323,7 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp, nkb;
         int64_t k0;
         tile_coords(t, mb, nb, sp);
@@ -374,13 +387,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BN, A_MN, B_MN);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp, nkb;
         int64_t k0;
         tile_coords(t, mb, nb, sp);
         k_range(sp, k0, nkb);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tcgen05_fence_after();
+        if (p.trace && blockIdx.x == 0) {
+          unsigned long long ts;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+          p.trace[((t - tile_first) / tile_step) * 24 + 0] = ts;
+        }
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(s), ph);
@@ -402,6 +420,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (CG == 1) tcgen05_commit(tfull_bar(as));        // accumulator complete
         else tcgen05_commit_2sm(tfull_bar(as));
+        if (p.trace && blockIdx.x == 0) {
+          unsigned long long ts;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+          p.trace[((t - tile_first) / tile_step) * 24 + 1] = ts;      // all MMAs of the tile ISSUED
+        }
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
@@ -438,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (has_mask && lane == 0) {                            // mask slab of the first work item of this warp
-      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+      for (int t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp;
         tile_coords(t, mb, nb, sp);
         if (((int64_t)mb * CG + cta_rank) * BLOCK_M + quarter * 32 < p.M && nb * BN + half * SLAB_COLS < p.N) {
@@ -449,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-    for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+    for (int t = tile_first; t < total_tiles; t += tile_step) {
       int mb, nb, sp;
       tile_coords(t, mb, nb, sp);
       const int64_t row0 = ((int64_t)mb * CG + cta_rank) * BLOCK_M + quarter * 32;
@@ -457,6 +480,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n0 = nb * BN;
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        p.trace[((t - tile_first) / tile_step) * 24 + 2] = ts;        // accumulator complete, epilogue starts
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
       if (EPI == EPI_SPLIT) {
         // fp32 partial sums straight to the split workspace (few tiles per launch: not worth staging)
@@ -490,6 +518,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c0 = half * SLAB_COLS; c0 < BN; c0 += 2 * SLAB_COLS) {
           const int col0 = n0 + c0;
           if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this slab is in range
+          MURCL_STAMP(0)
           float v[SLAB_COLS];
           if (p.debug & 4) {
 #pragma unroll
@@ -504,13 +533,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[32 * j + i] = __uint_as_float(r[j][i]);
           }
+          MURCL_STAMP(1)
           if (EPI == EPI_FWD && !(p.debug & 2)) {
             if (p.bias != nullptr) {
+              if (col0 + SLAB_COLS <= p.N) {                // whole slab in range: branch-free, loads issued back to back
+                float4 b4[SLAB_COLS / 4];
 #pragma unroll
-              for (int i = 0; i < SLAB_COLS; i += 4) {
-                if (col0 + i < p.N) {                       // N % 8 == 0
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                for (int i = 0; i < SLAB_COLS / 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+#pragma unroll
+                for (int i = 0; i < SLAB_COLS / 4; ++i) {
+                  v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < SLAB_COLS; i += 4) {
+                  if (col0 + i < p.N) {                     // N % 8 == 0
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                  }
                 }
               }
             }
@@ -519,22 +559,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               // one 64-bit word per (row, 64-column slab); consecutive rows are consecutive words -> coalesced
               // after the ReLU v >= +0, so (v > 0) is the sign bit of the integer negation of its bit pattern;
               // a funnel shift appends one sign bit per instruction (2 ops per element)
-              unsigned int lo = 0u, hi = 0u;
+              // four independent 16-bit chains (a single 32-long dependent chain is latency bound)
+              unsigned int q0 = 0u, q1 = 0u, q2 = 0u, q3 = 0u;
 #pragma unroll
-              for (int i = 31; i >= 0; --i) {
-                lo = __funnelshift_l(0u - __float_as_uint(v[i]), lo, 1);
-                hi = __funnelshift_l(0u - __float_as_uint(v[(32 + i) % SLAB_COLS]), hi, 1);
+              for (int i = 15; i >= 0; --i) {
+                q0 = __funnelshift_l(0u - __float_as_uint(v[i]), q0, 1);
+                q1 = __funnelshift_l(0u - __float_as_uint(v[16 + i]), q1, 1);
+                q2 = __funnelshift_l(0u - __float_as_uint(v[(32 + i) % SLAB_COLS]), q2, 1);
+                q3 = __funnelshift_l(0u - __float_as_uint(v[(48 + i) % SLAB_COLS]), q3, 1);
               }
+              const unsigned int lo = q0 | (q1 << 16), hi = q2 | (q3 << 16);
               p.bits_out[(int64_t)(col0 >> 6) * p.M + row] = ((unsigned long long)hi << 32) | lo;
             }
           } else if (EPI == EPI_DGRAD) {
             if (rv != nullptr) {
+              if (col0 + SLAB_COLS <= p.N) {
+                float4 g4[SLAB_COLS / 4];
 #pragma unroll
-              for (int i = 0; i < SLAB_COLS; i += 4) {
-                if (col0 + i < p.N) {
-                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(rv + col0 + i));
-                  v[i] = fmaf(rs, g4.x, v[i]); v[i + 1] = fmaf(rs, g4.y, v[i + 1]);
-                  v[i + 2] = fmaf(rs, g4.z, v[i + 2]); v[i + 3] = fmaf(rs, g4.w, v[i + 3]);
+                for (int i = 0; i < SLAB_COLS / 4; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(rv + col0) + i);
+#pragma unroll
+                for (int i = 0; i < SLAB_COLS / 4; ++i) {
+                  v[4 * i] = fmaf(rs, g4[i].x, v[4 * i]); v[4 * i + 1] = fmaf(rs, g4[i].y, v[4 * i + 1]);
+                  v[4 * i + 2] = fmaf(rs, g4[i].z, v[4 * i + 2]); v[4 * i + 3] = fmaf(rs, g4[i].w, v[4 * i + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < SLAB_COLS; i += 4) {
+                  if (col0 + i < p.N) {
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(rv + col0 + i));
+                    v[i] = fmaf(rs, g4.x, v[i]); v[i + 1] = fmaf(rs, g4.y, v[i + 1]);
+                    v[i + 2] = fmaf(rs, g4.z, v[i + 2]); v[i + 3] = fmaf(rs, g4.w, v[i + 3]);
+                  }
                 }
               }
             }
@@ -571,7 +626,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
               __syncwarp();                                 // every lane is done with the mask slab
               if (lane == 0) {                              // prefetch the next slab this warp will process
-                int64_t nt = t;
+                int nt = t;
                 int nc0 = c0 + 2 * SLAB_COLS;
                 bool found = (nc0 < BN) && (n0 + nc0 < p.N);
                 while (!found) {
@@ -592,6 +647,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
+          MURCL_STAMP(2)
           if (p.debug & 1) continue;                        // timing experiment: no staging, no store
           // stage the slab (swizzled like the TMA box) and hand it to the bulk-store engine
           if (has_mask) {
@@ -615,12 +671,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                            __float_as_uint(v[(4 * c + 1) % SLAB_COLS]), __float_as_uint(v[(4 * c + 2) % SLAB_COLS]),
                            __float_as_uint(v[(4 * c + 3) % SLAB_COLS]));
           }
+          MURCL_STAMP(3)
           fence_async_smem();
           __syncwarp();
+          MURCL_STAMP(4)
           if (lane == 0) {
             tma_store_2d(&map_c, out_slab, col0, (int)row0);   // rows >= M and cols >= N are clipped by the tensor map
             bulk_commit();
           }
+          MURCL_STAMP(5)
           if (want_colsum) {
             // column sums of the slab as stored (bf16-rounded): lane owns the 4-byte word `lane` of every row
             float s0 = 0.f, s1 = 0.f;
@@ -637,6 +696,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             atomicAdd(&colacc[c0 + 2 * lane + 1], s1);
           }
         }
+      }
+      if (p.trace && blockIdx.x < 2 && lane == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        p.trace[((t - tile_first) / tile_step) * 24 + 4 + blockIdx.x * 8 + ew] = ts;   // per-warp end, CTAs 0 and 1
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -721,6 +785,12 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   Params pp = p;
   pp.debug = debug;
+  static unsigned long long* trace_buf = nullptr;
+  if (debug & 8) {
+    if (!trace_buf) cudaMalloc(&trace_buf, sizeof(unsigned long long) * 24 * 4096);
+    cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * 24 * 4096, st);
+    pp.trace = trace_buf;
+  }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   const int slots = sm_count() / CG;                          // persistent: one CTA (or CTA pair) per SM (pair)
   const int grid = (int)(total < slots ? total : slots) * CG;
@@ -741,6 +811,30 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     set_error("gemm_tc_kernel launch failed: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return MURCL_ECUDA;
+  }
+  if (debug & 8) {
+    cudaStreamSynchronize(st);
+    static int printed = 0;
+    if (printed < 3 && (int64_t)p.m_tiles * p.n_tiles * p.splits > 500) {
+      ++printed;
+      unsigned long long h[24 * 12];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[trace] BN=%d CG=%d EPI=%d tiles/CTA timeline (ns rel. to first):\n", BN, CG, EPI);
+      for (int i = 4; i < 10; ++i) {
+        fprintf(stderr, "  tile %2d: mma_start %7lld issued %7lld epi_start %7lld | warp ends cta0:", i,
+                (long long)(h[24 * i] - h[0]), (long long)(h[24 * i + 1] - h[0]), (long long)(h[24 * i + 2] - h[0]));
+        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", (long long)(h[24 * i + 4 + w] - h[0]));
+        fprintf(stderr, " | cta1:");
+        for (int w = 0; w < 8; ++w) fprintf(stderr, " %lld", (long long)(h[24 * i + 12 + w] - h[0]));
+        fprintf(stderr, "\n");
+      }
+      unsigned long long g[8 * 12];
+      cudaMemcpy(g, trace_buf + (size_t)24 * 2048, sizeof(g), cudaMemcpyDeviceToHost);
+      for (int i = 4; i < 10; ++i)
+        fprintf(stderr, "  tile %2d warp0 slab0 phases (ns): tmem %lld  math %lld  wait+sts %lld  fence %lld  store-issue %lld\n", i,
+                (long long)(g[8 * i + 1] - g[8 * i]), (long long)(g[8 * i + 2] - g[8 * i + 1]), (long long)(g[8 * i + 3] - g[8 * i + 2]),
+                (long long)(g[8 * i + 4] - g[8 * i + 3]), (long long)(g[8 * i + 5] - g[8 * i + 4]));
+    }
   }
   return check_launch("gemm_tc_kernel");
 }
