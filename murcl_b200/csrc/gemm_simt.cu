@@ -52,7 +52,7 @@ __device__ __forceinline__ void load8(const T* base, int64_t ld, int64_t major, 
 }
 
 template <typename TA, typename TB, typename TC, bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
+__global__ void __launch_bounds__(256, 2) gemm_simt_kernel(GemmParams p) {
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   const TA* A = static_cast<const TA*>(p.A);
