@@ -89,7 +89,7 @@ def clam_state(in_dim: int, size_arg: str = "small", gate: bool = True, dropout:
     return sd
 
 
-def dsmil_state(dim_feat: int, num_classes: int = 2, seed: int = SEED, peak: float = 8.0) -> Dict[str, torch.Tensor]:
+def dsmil_state(dim_feat: int, num_classes: int = 2, seed: int = SEED, peak: float = 1.5) -> Dict[str, torch.Tensor]:
     """State dict with MILNet's parameter names (models/dsmil.py:6-62,103-119)."""
     g = gen(seed)
     sd = {}
