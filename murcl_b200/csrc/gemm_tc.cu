@@ -2,13 +2,15 @@
 //
 //   C[m,n] = sum_k A(m,k) * B(n,k)      bf16 operands, fp32 accumulators in tensor memory
 //
-// One persistent CTA per SM, 6 warps:
-//   warp 0  TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (STAGES deep), mbarrier tx-count
-//   warp 1  MMA issuer     one lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16), tcgen05.commit frees
-//                          smem slots and publishes the accumulator; also owns tcgen05.alloc/dealloc
-//   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> 128B-swizzled smem slab
-//                          (32 rows x 128 B per warp) -> cp.async.bulk.tensor store; the ReLU-mask operand of the
-//                          input-gradient epilogue arrives the same way (TMA load of the matching slab)
+// One persistent CTA per SM (or CTA pair per SM pair), 18 warps:
+//   warps 0-15 epilogue    four per TMEM lane quarter, each taking every fourth 128-byte column slab: tcgen05.ld 32 lanes x 32
+//                          columns -> registers -> fused epilogue (bias/activation/ReLU bits, or pooling row term / ReLU mask /
+//                          scale / column sums) -> 128B-swizzled smem slab (32 rows x 128 B) -> cp.async.bulk.tensor store.
+//                          Sixteen warps (<= 112 registers each, a slab passes through the registers in two 32-column halves)
+//                          give every scheduler four epilogue warps to hide the tcgen05.ld / L2 latencies behind each other.
+//   warp 16    TMA producer cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (STAGES deep), mbarrier tx-count
+//   warp 17    MMA issuer   one lane issues tcgen05.mma.kind::f16 (128*CG x BN x 16), tcgen05.commit frees smem slots and
+//                          publishes the accumulator; also owns tcgen05.alloc/dealloc
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Operand majors (UMMA "K-major" = reduction index contiguous in memory, "MN-major" = output index contiguous):
@@ -32,7 +34,7 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;               // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;           // two per TMEM lane quarter, splitting the columns
+constexpr int NUM_EPI_WARPS = 16;          // four per TMEM lane quarter, splitting the column slabs
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int SMEM_BUDGET = 224 * 1024;
@@ -229,21 +231,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a
          ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
-constexpr int SLAB_BYTES = 32 * 128;        // one epilogue warp's staging slab: 32 rows x 128 B
-
 // CG = cta_group: 1 = one SM per 128 x BN tile; 2 = a CTA pair shares a 256 x BN tile (each CTA holds its 128 rows of A
 // and HALF of B, the MMA unit exchanges the B halves), which halves the B bytes each SM pulls through L2 and reads from
-// shared memory per MMA - the limiter of the 1-CTA kernel.
-template <int BN, int EPI, int CG>
+// shared memory per MMA.
+// BSTAT = B-stationary: the whole reduction extent (<= 8 k-blocks) of the CTA's B tile stays resident in shared memory and
+// only A streams through the ring.  The persistent schedule gives a CTA (pair) the same column tile every time
+// (tile step % n_tiles == 0), so B is loaded once per launch: L2 -> SM operand traffic per MMA halves again.  The L2
+// slice bandwidth (~6300 B/clk chip-wide) is what bounded the streaming kernel (measured: 8 k-blocks in 4.4 us).
+template <int BN, int EPI, int CG, int TOUT_BYTES, bool BSTAT>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLABS_PER_WARP = (EPI == 2) ? 0 : 2;   // (the split-K kernel stores directly) two output slabs (double-buffered stores); the input grad's TMA-loaded
-                                             // ReLU-mask slab takes the place of the second one when it is in use
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int MAX_RES_KB = 8;                                        // resident k-blocks (reduction <= 512)
+  static constexpr int BRES_BYTES = BSTAT ? MAX_RES_KB * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = BSTAT ? A_BYTES : A_BYTES + B_BYTES;
+  // one staging unit per epilogue warp: 32 rows x 32 columns (64-byte rows of bf16, 128-byte rows of fp32);
+  // the split-K kernel stores directly
+  static constexpr int UNIT_BYTES = 32 * 32 * TOUT_BYTES;
+  static constexpr int STAGING_BYTES = (EPI == 2) ? 0 : NUM_EPI_WARPS * UNIT_BYTES;
+  static constexpr int RING_BYTES = SMEM_BUDGET - STAGING_BYTES - BRES_BYTES;
+  static constexpr int STAGES = RING_BYTES / STAGE_BYTES > 8 ? 8 : RING_BYTES / STAGE_BYTES;
+  static_assert(STAGES >= 3, "operand ring too shallow");
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+  static constexpr int SMEM_BYTES = BRES_BYTES + STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                     BN * 4 /*column-sum accumulator*/;
 };
 
@@ -254,25 +263,27 @@ struct Cfg {
     p.trace[(int64_t)24 * 2048 + ((t - tile_first) / tile_step) * 8 + (slot)] = ts_;            \
   }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG>
+template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG, bool BSTAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_mask, const Params p) {
-  using C = Cfg<BN, EPI, CG>;
+               const __grid_constant__ CUtensorMap map_c, const Params p) {
+  using C = Cfg<BN, EPI, CG, (int)sizeof(TOUT), BSTAT>;
   static_assert(CG == 1 || !A_MN, "the CTA-pair kernel takes a K-major A operand");
+  static_assert(!BSTAT || (!A_MN && EPI != EPI_SPLIT), "B-stationary: forward / input-gradient kernels only");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t bres = (raw + 1023u) & ~1023u;                        // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t tiles = bres + C::BRES_BYTES;                         // resident B k-blocks (BSTAT), then the operand ring
   const uint32_t staging = tiles + C::STAGES * C::STAGE_BYTES;        // 1024 B aligned (stage sizes are multiples of 1024)
   const uint32_t bars = staging + C::STAGING_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
-  auto mask_bar = [&](int w) { return bars + 8u * (2 * C::STAGES + 4 + w); };
-  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4 + NUM_EPI_WARPS);
+  const uint32_t bres_bar = bars + 8u * (2 * C::STAGES + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 5);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
   float* colacc = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw));     // [BN] per-CTA column sums
 
@@ -291,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), NUM_EPI_WARPS * CG);     // one arrival per epilogue warp (of both CTAs of a pair)
     }
-    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(mask_bar(w), 1);
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
@@ -336,6 +347,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      if (BSTAT && tile_first < total_tiles) {
+        // the CTA's column tile never changes (host: tile step % n_tiles == 0): fetch its B k-blocks once
+        int mb, nb, sp, nkb;
+        int64_t k0;
+        tile_coords(tile_first, mb, nb, sp);
+        k_range(sp, k0, nkb);
+        const int n0 = nb * BN + (int)cta_rank * (BN / CG);
+        if (CG == 1 || leader) mbar_expect_tx(bres_bar, (uint32_t)(CG * nkb * C::B_BYTES));
+        const uint32_t bb = (CG == 2) ? mapa(bres_bar, 0) : bres_bar;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t b_dst = bres + kb * C::B_BYTES;
+          const int kk = kb * BLOCK_K;
+          if (!B_MN) {
+            if (CG == 2) tma_load_2d_2sm(b_dst, &map_b, bb, kk, n0);
+            else tma_load_2d(b_dst, &map_b, bb, kk, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / CG / 64; ++j) {
+              if (CG == 2) tma_load_2d_2sm(b_dst + j * 8192, &map_b, bb, n0 + 64 * j, kk);
+              else tma_load_2d(b_dst + j * 8192, &map_b, bb, n0 + 64 * j, kk);
+            }
+          }
+        }
+      }
       for (int t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp, nkb;
         int64_t k0;
@@ -348,6 +383,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t a_dst = tiles + s * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           const int kk = (int)(k0 + (int64_t)kb * BLOCK_K);
+          if (BSTAT) {                                                        // only A streams
+            if (CG == 2) {
+              if (leader) mbar_expect_tx(full_bar(s), 2 * A_BYTES);
+              tma_load_2d_2sm(a_dst, &map_a, mapa(full_bar(s), 0), kk, m0);
+            } else {
+              mbar_expect_tx(full_bar(s), A_BYTES);
+              tma_load_2d(a_dst, &map_a, full_bar(s), kk, m0);
+            }
+            if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            continue;
+          }
           if (CG == 2) {
             // both CTAs load their halves; all bytes are counted on the LEADER's full barrier (it issues the MMAs)
             if (leader) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
@@ -387,6 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BN, A_MN, B_MN);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
+      if (BSTAT && tile_first < total_tiles) mbar_wait(bres_bar, 0u);   // the resident B tile has landed (both halves of a pair)
       for (int t = tile_first; t < total_tiles; t += tile_step) {
         int mb, nb, sp, nkb;
         int64_t k0;
@@ -404,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
           const uint32_t a_src = tiles + s * C::STAGE_BYTES;
-          const uint32_t b_src = a_src + A_BYTES;
+          const uint32_t b_src = BSTAT ? bres + kb * C::B_BYTES : a_src + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // K-major: 16 k-elements = 32 B inside the 128 B swizzle span; SBO = 1024 B between 8-row groups.
@@ -429,48 +476,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue warps (0..7) =================
+    // ================= epilogue warps (0..15) =================
+    // Work unit = 32 rows (this warp's TMEM lane quarter) x 32 columns: one tcgen05.ld.32x32b.x32, one staging unit, one
+    // bulk tensor store.  The four warps of a quarter take every fourth unit.
     const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) belong to this warp
-    const int ew = warp;                                   // 0..7
-    const int half = ew >> 2;                              // the two warps of a quarter take alternate column slabs
-    const uint32_t slab_base = staging + (uint32_t)ew * (C::SLABS_PER_WARP * SLAB_BYTES);
-    const uint32_t mask_slab = slab_base + SLAB_BYTES;     // second slab doubles as the ReLU-mask slab (mask mode)
-    uint32_t out_slab = slab_base;
-    uint32_t slab_flip = 0;
-    const uint32_t my_row_off = (uint32_t)lane * 128u;
-    const uint32_t swz = (uint32_t)(lane & 7);             // 128B swizzle: 16-byte chunk index ^= row & 7
-    constexpr int SLAB_COLS = 128 / (int)sizeof(TOUT);      // 64 bf16 or 32 fp32 columns = 128 B per row
+    const int ew = warp;                                   // 0..15
+    const int part = ew >> 2;
+    const uint32_t out_unit = staging + (uint32_t)ew * C::UNIT_BYTES;
+    // bf16: 64-byte rows, SWIZZLE_64B (16-byte chunk index ^= (row >> 1) & 3); fp32: 128-byte rows, SWIZZLE_128B (^= row & 7)
+    const uint32_t my_row_off = (uint32_t)lane * (32u * (uint32_t)sizeof(TOUT));
+    const uint32_t swz = sizeof(TOUT) == 2 ? (uint32_t)((lane >> 1) & 3) : (uint32_t)(lane & 7);
+    constexpr int EPI_THREADS = 32 * NUM_EPI_WARPS;
     int as = 0;
-    uint32_t aph = 0, mph = 0;
+    uint32_t aph = 0;
     const bool has_mask = (EPI == EPI_DGRAD) && p.relu_src != nullptr && p.bits_in == nullptr;
     const bool want_colsum = (EPI == EPI_DGRAD) && sizeof(TOUT) == 2 && p.col_sum != nullptr;
     int acc_nb = -1;
-    const int etid = threadIdx.x;                           // 0..255: the epilogue threads come first
+    const int etid = threadIdx.x;                           // 0..511: the epilogue threads come first
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); };
     auto flush_colacc = [&](int nb_flush) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");        // all epilogue warps have added their slabs
-      for (int i = etid; i < BN; i += 32 * NUM_EPI_WARPS) {
+      epi_sync();                                           // all epilogue warps have added their units
+      for (int i = etid; i < BN; i += EPI_THREADS) {
         const int col = nb_flush * BN + i;
         const float sum = colacc[i];
         if (col < p.N && sum != 0.f) atomicAdd(p.col_sum + col, sum);
         colacc[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      epi_sync();
     };
     if (want_colsum) {
-      for (int i = etid; i < BN; i += 32 * NUM_EPI_WARPS) colacc[i] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    if (has_mask && lane == 0) {                            // mask slab of the first work item of this warp
-      for (int t = tile_first; t < total_tiles; t += tile_step) {
-        int mb, nb, sp;
-        tile_coords(t, mb, nb, sp);
-        if (((int64_t)mb * CG + cta_rank) * BLOCK_M + quarter * 32 < p.M && nb * BN + half * SLAB_COLS < p.N) {
-          mbar_expect_tx(mask_bar(ew), SLAB_BYTES);
-          tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb * BN + half * SLAB_COLS,
-                      (mb * CG + (int)cta_rank) * BLOCK_M + quarter * 32);
-          break;
-        }
-      }
+      for (int i = etid; i < BN; i += EPI_THREADS) colacc[i] = 0.f;
+      epi_sync();
     }
     for (int t = tile_first; t < total_tiles; t += tile_step) {
       int mb, nb, sp;
@@ -489,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (EPI == EPI_SPLIT) {
         // fp32 partial sums straight to the split workspace (few tiles per launch: not worth staging)
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        for (int c0 = part * 32; c0 < BN; c0 += 128) {
           uint32_t r[32];
           tmem_ld32(t_row + (uint32_t)c0, r);
           tmem_ld_wait();
@@ -515,38 +551,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           acc_nb = nb;
         }
 #pragma unroll 1
-        for (int c0 = half * SLAB_COLS; c0 < BN; c0 += 2 * SLAB_COLS) {
+        for (int c0 = part * 32; c0 < BN; c0 += 128) {
           const int col0 = n0 + c0;
-          if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this slab is in range
+          if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this unit is in range
           MURCL_STAMP(0)
-          float v[SLAB_COLS];
-          if (p.debug & 4) {
-#pragma unroll
-            for (int i = 0; i < SLAB_COLS; ++i) v[i] = 1.f;
-          } else {
-            uint32_t r[SLAB_COLS / 32][32];
-#pragma unroll
-            for (int j = 0; j < SLAB_COLS / 32; ++j) tmem_ld32(t_row + (uint32_t)(c0 + 32 * j), r[j]);   // both in flight
+          // ReLU bit masks: one 64-bit word per (row, 64 columns), layout [N/64][M]; a unit owns one 32-bit half of a word.
+          // Consecutive rows are consecutive words: the per-lane accesses of a warp stay within 256 contiguous bytes.
+          const int64_t bit_word = (((int64_t)(col0 >> 6) * p.M + row) << 1) + ((col0 >> 5) & 1);
+          float v[32];
+          {
+            uint32_t r[32];
+            tmem_ld32(t_row + (uint32_t)c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < SLAB_COLS / 32; ++j)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[32 * j + i] = __uint_as_float(r[j][i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           }
-          MURCL_STAMP(1)
-          if (EPI == EPI_FWD && !(p.debug & 2)) {
+          if (EPI == EPI_FWD) {
             if (p.bias != nullptr) {
-              if (col0 + SLAB_COLS <= p.N) {                // whole slab in range: branch-free, loads issued back to back
-                float4 b4[SLAB_COLS / 4];
+              if (col0 + 32 <= p.N) {                       // whole unit in range: branch-free, loads issued back to back
+                float4 b4[8];
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS / 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+                for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS / 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                   v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w;
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS; i += 4) {
+                for (int i = 0; i < 32; i += 4) {
                   if (col0 + i < p.N) {                     // N % 8 == 0
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
                     v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
@@ -554,37 +586,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
               }
             }
-            act_slab<sizeof(TOUT) == 2, SLAB_COLS>(v, p.act, col0, p.N);
+            act_slab<sizeof(TOUT) == 2, 32>(v, p.act, col0, p.N);
             if (sizeof(TOUT) == 2 && p.bits_out != nullptr && row < p.M) {
-              // one 64-bit word per (row, 64-column slab); consecutive rows are consecutive words -> coalesced
               // after the ReLU v >= +0, so (v > 0) is the sign bit of the integer negation of its bit pattern;
-              // a funnel shift appends one sign bit per instruction (2 ops per element)
-              // four independent 16-bit chains (a single 32-long dependent chain is latency bound)
-              unsigned int q0 = 0u, q1 = 0u, q2 = 0u, q3 = 0u;
+              // a funnel shift appends one sign bit per instruction; two independent 16-bit chains
+              unsigned int q0 = 0u, q1 = 0u;
 #pragma unroll
               for (int i = 15; i >= 0; --i) {
                 q0 = __funnelshift_l(0u - __float_as_uint(v[i]), q0, 1);
                 q1 = __funnelshift_l(0u - __float_as_uint(v[16 + i]), q1, 1);
-                q2 = __funnelshift_l(0u - __float_as_uint(v[(32 + i) % SLAB_COLS]), q2, 1);
-                q3 = __funnelshift_l(0u - __float_as_uint(v[(48 + i) % SLAB_COLS]), q3, 1);
               }
-              const unsigned int lo = q0 | (q1 << 16), hi = q2 | (q3 << 16);
-              p.bits_out[(int64_t)(col0 >> 6) * p.M + row] = ((unsigned long long)hi << 32) | lo;
+              reinterpret_cast<unsigned int*>(p.bits_out)[bit_word] = q0 | (q1 << 16);
             }
           } else if (EPI == EPI_DGRAD) {
             if (rv != nullptr) {
-              if (col0 + SLAB_COLS <= p.N) {
-                float4 g4[SLAB_COLS / 4];
+              if (col0 + 32 <= p.N) {
+                float4 g4[8];
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS / 4; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(rv + col0) + i);
+                for (int i = 0; i < 8; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(rv + col0) + i);
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS / 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                   v[4 * i] = fmaf(rs, g4[i].x, v[4 * i]); v[4 * i + 1] = fmaf(rs, g4[i].y, v[4 * i + 1]);
                   v[4 * i + 2] = fmaf(rs, g4[i].z, v[4 * i + 2]); v[4 * i + 3] = fmaf(rs, g4[i].w, v[4 * i + 3]);
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS; i += 4) {
+                for (int i = 0; i < 32; i += 4) {
                   if (col0 + i < p.N) {
                     const float4 g4 = __ldg(reinterpret_cast<const float4*>(rv + col0 + i));
                     v[i] = fmaf(rs, g4.x, v[i]); v[i + 1] = fmaf(rs, g4.y, v[i + 1]);
@@ -594,110 +621,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (p.bits_in != nullptr) {
-              const unsigned long long bits = row < p.M ? __ldg(p.bits_in + (int64_t)(col0 >> 6) * p.M + row) : 0ull;
-              const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+              const unsigned int w = row < p.M ? __ldg(reinterpret_cast<const unsigned int*>(p.bits_in) + bit_word) : 0u;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (!((lo >> i) & 1u)) v[i] = 0.f;
-                if (!((hi >> i) & 1u)) v[(32 + i) % SLAB_COLS] = 0.f;
-              }
-              if (p.out_scale != 1.f) {
-#pragma unroll
-                for (int i = 0; i < SLAB_COLS; ++i) v[i] *= p.out_scale;
-              }
-            }
-            if (has_mask) {
-              mbar_wait(mask_bar(ew), mph);                 // slab fetched ahead (issued one slab earlier)
-              mph ^= 1u;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {                 // bf16 mask slab: 8 chunks of 8 columns per row
-                const uint4 q = ld_shared_v4(mask_slab + my_row_off + (((uint32_t)c ^ swz) << 4));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+              for (int i = 0; i < 32; ++i)
+                if (!((w >> i) & 1u)) v[i] = 0.f;
+            } else if (has_mask) {
+              // no bit mask from the forward pass: read the ReLU output itself (64 contiguous bytes per row)
+              if (row < p.M) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.relu_src + row * p.ldc + col0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(h[j]);
-                  if (!(f.x > 0.f)) v[8 * c + 2 * j] = 0.f;
-                  if (!(f.y > 0.f)) v[8 * c + 2 * j + 1] = 0.f;
-                }
-              }
-              if (p.out_scale != 1.f) {
+                  if (col0 + 8 * j < p.N) {
+                    const uint4 q = __ldg(src + j);
+                    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-                for (int i = 0; i < SLAB_COLS; ++i) v[i] *= p.out_scale;
-              }
-              __syncwarp();                                 // every lane is done with the mask slab
-              if (lane == 0) {                              // prefetch the next slab this warp will process
-                int nt = t;
-                int nc0 = c0 + 2 * SLAB_COLS;
-                bool found = (nc0 < BN) && (n0 + nc0 < p.N);
-                while (!found) {
-                  nt += tile_step;
-                  if (nt >= total_tiles) break;
-                  nc0 = half * SLAB_COLS;
-                  int mb2, nb2, sp2;
-                  tile_coords(nt, mb2, nb2, sp2);
-                  found = (((int64_t)mb2 * CG + cta_rank) * BLOCK_M + quarter * 32 < p.M) && (nb2 * BN + nc0 < p.N);
-                }
-                if (found) {
-                  int mb2, nb2, sp2;
-                  tile_coords(nt, mb2, nb2, sp2);
-                  mbar_expect_tx(mask_bar(ew), SLAB_BYTES);
-                  tma_load_2d(mask_slab, &map_mask, mask_bar(ew), nb2 * BN + nc0,
-                              (mb2 * CG + (int)cta_rank) * BLOCK_M + quarter * 32);
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(hh[e]);
+                      if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+                      if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+                    }
+                  }
                 }
               }
             }
+            if ((p.bits_in != nullptr || has_mask) && p.out_scale != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= p.out_scale;
+            }
           }
-          MURCL_STAMP(2)
-          if (p.debug & 1) continue;                        // timing experiment: no staging, no store
-          // stage the slab (swizzled like the TMA box) and hand it to the bulk-store engine
-          if (has_mask) {
-            if (lane == 0) bulk_wait_read0();               // single output slab: the previous store has read it
-          } else {
-            out_slab = slab_base + slab_flip * SLAB_BYTES;  // two output slabs: only the store before last must be done
-            slab_flip ^= 1u;
-            if (lane == 0) bulk_wait_read1();
-          }
+          MURCL_STAMP(1)
+          if (lane == 0) bulk_wait_read0();                 // this warp's previous store has read the staging unit
           __syncwarp();
+          MURCL_STAMP(2)
+          // stage (swizzled like the TMA box) and hand the unit to the bulk-store engine
           if (sizeof(TOUT) == 2) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              st_shared_v4(out_slab + my_row_off + (((uint32_t)c ^ swz) << 4), pack_bf16(v[8 * c], v[8 * c + 1]),
+            for (int c = 0; c < 4; ++c)
+              st_shared_v4(out_unit + my_row_off + (((uint32_t)c ^ swz) << 4), pack_bf16(v[8 * c], v[8 * c + 1]),
                            pack_bf16(v[8 * c + 2], v[8 * c + 3]), pack_bf16(v[8 * c + 4], v[8 * c + 5]),
                            pack_bf16(v[8 * c + 6], v[8 * c + 7]));
           } else {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              st_shared_v4(out_slab + my_row_off + (((uint32_t)c ^ swz) << 4), __float_as_uint(v[4 * c % SLAB_COLS]),
-                           __float_as_uint(v[(4 * c + 1) % SLAB_COLS]), __float_as_uint(v[(4 * c + 2) % SLAB_COLS]),
-                           __float_as_uint(v[(4 * c + 3) % SLAB_COLS]));
+              st_shared_v4(out_unit + my_row_off + (((uint32_t)c ^ swz) << 4), __float_as_uint(v[4 * c]),
+                           __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
           }
           MURCL_STAMP(3)
           fence_async_smem();
           __syncwarp();
           MURCL_STAMP(4)
           if (lane == 0) {
-            tma_store_2d(&map_c, out_slab, col0, (int)row0);   // rows >= M and cols >= N are clipped by the tensor map
+            tma_store_2d(&map_c, out_unit, col0, (int)row0);   // rows >= M and cols >= N are clipped by the tensor map
             bulk_commit();
           }
           MURCL_STAMP(5)
           if (want_colsum) {
-            // column sums of the slab as stored (bf16-rounded): lane owns the 4-byte word `lane` of every row
+            // column sums of the unit as stored (bf16-rounded): lane owns the 4-byte word (lane & 15) of every second row
             float s0 = 0.f, s1 = 0.f;
+            const uint32_t wi = (uint32_t)lane & 15u;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t r = 2u * (uint32_t)j + ((uint32_t)lane >> 4);
               uint32_t wv;
-              const uint32_t addr = out_slab + (uint32_t)r * 128u + (((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) | (((uint32_t)lane & 3u) << 2));
+              const uint32_t addr = out_unit + r * 64u + ((((wi >> 2) ^ ((r >> 1) & 3u)) << 4) | ((wi & 3u) << 2));
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(addr) : "memory");
               const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&wv));
               s0 += f.x;
               s1 += f.y;
             }
-            atomicAdd(&colacc[c0 + 2 * lane], s0);
-            atomicAdd(&colacc[c0 + 2 * lane + 1], s1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            if (lane < 16) {
+              atomicAdd(&colacc[c0 + 2 * lane], s0);
+              atomicAdd(&colacc[c0 + 2 * lane + 1], s1);
+            }
           }
         }
       }
-      if (p.trace && blockIdx.x < 2 && lane == 0) {
+      if (p.trace && blockIdx.x < 2 && lane == 0 && ew < 8) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
         p.trace[((t - tile_first) / tile_step) * 24 + 4 + blockIdx.x * 8 + ew] = ts;   // per-warp end, CTAs 0 and 1
@@ -741,9 +742,10 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D row-major tensor [rows, cols] (cols contiguous) of 2-byte (bf16) or 4-byte (fp32) elements;
-// box = {box_cols, box_rows}, 128B swizzle, zero OOB fill on loads / clipping on stores.
+// box = {box_cols, box_rows}, 128B swizzle (64B for the bf16 store units), zero OOB fill on loads / clipping on stores.
+static int make_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int elem_bytes);
 static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
-                    int elem_bytes = 2) {
+                    int elem_bytes = 2, bool swizzle64 = false) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -755,7 +757,8 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] box {%d,%d}", (int)r, (long long)rows, (long long)cols,
               box_cols, box_rows);
@@ -764,11 +767,36 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
   return MURCL_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG = 1>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mm, const Params& p,
+// the epilogue's staging unit: 32 rows x 32 columns
+static int make_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int elem_bytes) {
+  return make_map(map, base, rows, cols, 32, 32, elem_bytes, elem_bytes == 2);
+}
+
+static int bstat_mode() {          // MURCL_DISABLE_BSTAT=1: always stream B (A/B comparison)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MURCL_DISABLE_BSTAT");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v;
+}
+
+// B-stationary applies when the reduction fits the resident k-blocks and the persistent grid can be made a multiple of
+// the column-tile count (so a CTA keeps its column tile).
+template <int CG>
+static bool bstat_ok(const Params& p) {
+  if (!bstat_mode() || p.splits != 1 || p.K > 8 * BLOCK_K) return false;
+  const int slots = sm_count() / CG;
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles;
+  // worth it only when B is reused: a CTA must see several tiles
+  return p.n_tiles <= slots && total >= 2 * (int64_t)slots;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, typename TOUT, int CG = 1, bool BSTAT = false>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p,
                   cudaStream_t st) {
-  using C = Cfg<BN, EPI, CG>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT, CG>;
+  using C = Cfg<BN, EPI, CG, (int)sizeof(TOUT), BSTAT>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT, CG, BSTAT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -792,7 +820,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     pp.trace = trace_buf;
   }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
-  const int slots = sm_count() / CG;                          // persistent: one CTA (or CTA pair) per SM (pair)
+  int slots = sm_count() / CG;                                // persistent: one CTA (or CTA pair) per SM (pair)
+  if (BSTAT) slots -= slots % p.n_tiles;                      // a CTA keeps its column tile: step % n_tiles == 0
   const int grid = (int)(total < slots ? total : slots) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -806,7 +835,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mm, pp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, pp);
   if (e != cudaSuccess) {
     set_error("gemm_tc_kernel launch failed: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -819,7 +848,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
       ++printed;
       unsigned long long h[24 * 12];
       cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[trace] BN=%d CG=%d EPI=%d tiles/CTA timeline (ns rel. to first):\n", BN, CG, EPI);
+      fprintf(stderr, "[trace] BN=%d CG=%d EPI=%d BSTAT=%d tiles/CTA timeline (ns rel. to first):\n", BN, CG, EPI, (int)BSTAT);
       for (int i = 4; i < 10; ++i) {
         fprintf(stderr, "  tile %2d: mma_start %7lld issued %7lld epi_start %7lld | warp ends cta0:", i,
                 (long long)(h[24 * i] - h[0]), (long long)(h[24 * i + 1] - h[0]), (long long)(h[24 * i + 2] - h[0]));
@@ -831,7 +860,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
       unsigned long long g[8 * 12];
       cudaMemcpy(g, trace_buf + (size_t)24 * 2048, sizeof(g), cudaMemcpyDeviceToHost);
       for (int i = 4; i < 10; ++i)
-        fprintf(stderr, "  tile %2d warp0 slab0 phases (ns): tmem %lld  math %lld  wait+sts %lld  fence %lld  store-issue %lld\n", i,
+        fprintf(stderr, "  tile %2d warp0 unit0 phases (ns): tmem-ld+math %lld  store-wait %lld  sts %lld  fence %lld  store-issue %lld\n", i,
                 (long long)(g[8 * i + 1] - g[8 * i]), (long long)(g[8 * i + 2] - g[8 * i + 1]), (long long)(g[8 * i + 3] - g[8 * i + 2]),
                 (long long)(g[8 * i + 4] - g[8 * i + 3]), (long long)(g[8 * i + 5] - g[8 * i + 4]));
     }
@@ -893,7 +922,7 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
   if (rc != MURCL_OK) return rc;
   CUtensorMap mc;
   const int eb = out_dtype == MURCL_BF16 ? 2 : 4;
-  rc = make_map(&mc, y, M, N, 128 / eb, 32, eb);                 // store slab: 32 rows x 128 B
+  rc = make_store_map(&mc, y, M, N, eb);
   if (rc != MURCL_OK) return rc;
   if (bias != nullptr && !aligned16(bias)) {
     set_error("linear_fwd(tcgen05): bias must be 16-byte aligned");
@@ -905,17 +934,20 @@ int tc_linear_fwd(const void* x, const void* w, const float* bias, void* y, int6
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
   if (pair) {
     p.m_tiles = ceil_div(M, 2 * BLOCK_M);
-    return out_dtype == MURCL_BF16 ? launch<256, false, false, EPI_FWD, __nv_bfloat16, 2>(ma, mb, mc, mc, p, st)
-                                   : launch<256, false, false, EPI_FWD, float, 2>(ma, mb, mc, mc, p, st);
+    if (out_dtype == MURCL_BF16 && bstat_ok<2>(p)) return launch<256, false, false, EPI_FWD, __nv_bfloat16, 2, true>(ma, mb, mc, p, st);
+    return out_dtype == MURCL_BF16 ? launch<256, false, false, EPI_FWD, __nv_bfloat16, 2>(ma, mb, mc, p, st)
+                                   : launch<256, false, false, EPI_FWD, float, 2>(ma, mb, mc, p, st);
   }
+  if (BN == 128 && out_dtype == MURCL_BF16 && bstat_ok<1>(p))
+    return launch<128, false, false, EPI_FWD, __nv_bfloat16, 1, true>(ma, mb, mc, p, st);
   if (BN == 64)
-    return out_dtype == MURCL_BF16 ? launch<64, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st)
-                                   : launch<64, false, false, EPI_FWD, float>(ma, mb, mc, mc, p, st);
+    return out_dtype == MURCL_BF16 ? launch<64, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, p, st)
+                                   : launch<64, false, false, EPI_FWD, float>(ma, mb, mc, p, st);
   if (out_dtype == MURCL_BF16)
-    return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st)
-                     : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, mc, p, st);
-  return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, mc, mc, p, st)
-                   : launch<128, false, false, EPI_FWD, float>(ma, mb, mc, mc, p, st);
+    return BN == 256 ? launch<256, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, p, st)
+                     : launch<128, false, false, EPI_FWD, __nv_bfloat16>(ma, mb, mc, p, st);
+  return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, mc, p, st)
+                   : launch<128, false, false, EPI_FWD, float>(ma, mb, mc, p, st);
 }
 
 int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int N, int K, const void* relu_src,
@@ -940,10 +972,8 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   p.out_scale = out_scale; p.bits_in = relu_bits;
   p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
-  CUtensorMap mc, mm;
-  rc = make_map(&mc, dx, M, K, 64, 32);
-  if (rc != MURCL_OK) return rc;
-  rc = make_map(&mm, relu_src ? relu_src : dx, M, K, 64, 32);
+  CUtensorMap mc;
+  rc = make_store_map(&mc, dx, M, K, 2);
   if (rc != MURCL_OK) return rc;
   if (row_vec != nullptr && !aligned16(row_vec)) {
     set_error("linear_bwd_input(tcgen05): row_vec must be 16-byte aligned");
@@ -951,11 +981,13 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
   }
   if (pair) {
     p.m_tiles = ceil_div(M, 2 * BLOCK_M);
-    return launch<256, false, true, EPI_DGRAD, __nv_bfloat16, 2>(ma, mb, mc, mm, p, st);
+    if (bstat_ok<2>(p)) return launch<256, false, true, EPI_DGRAD, __nv_bfloat16, 2, true>(ma, mb, mc, p, st);
+    return launch<256, false, true, EPI_DGRAD, __nv_bfloat16, 2>(ma, mb, mc, p, st);
   }
-  if (BN == 64) return launch<64, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st);
-  return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st)
-                   : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, mm, p, st);
+  if (BN == 128 && bstat_ok<1>(p)) return launch<128, false, true, EPI_DGRAD, __nv_bfloat16, 1, true>(ma, mb, mc, p, st);
+  if (BN == 64) return launch<64, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, p, st);
+  return BN == 256 ? launch<256, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, p, st)
+                   : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, p, st);
 }
 
 static void wgrad_plan(int64_t M, int N, int K, int& BN, int& splits, int64_t& k_chunk) {
@@ -1000,8 +1032,8 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
   p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
-  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, ma, p, st)
-                 : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, ma, p, st);
+  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
+                 : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
   if (rc != MURCL_OK) return rc;
   const int64_t n = (int64_t)N * K;
   return launch_splitk_reduce(workspace, splits, n, dw, n, st);

@@ -31,7 +31,9 @@ def _mk(M, N, K, seed):
 
 
 SHAPES = [(4096, 512, 512), (1000, 128, 512), (131, 384, 1024), (2048, 256, 64), (777, 512, 200), (128, 128, 64),
-          (5000, 256, 512), (8200, 512, 128), (40000, 512, 512)]      # the last three exercise the CTA-pair kernel + row tails
+          (5000, 256, 512), (8200, 512, 128), (40000, 512, 512),      # these three exercise the CTA-pair kernel + row tails
+          # B-stationary variants (many tiles per CTA): 1-CTA 128-wide tiles, a ragged reduction, 3 column tiles (grid 147)
+          (40000, 128, 512), (40000, 512, 200), (40000, 384, 512)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
