@@ -130,6 +130,23 @@ int64_t murcl_seg_wsum_workspace(int64_t n_rows, int B, int C, int L);
 int murcl_seg_wsum(const float* p, const void* h, const int64_t* offsets, int64_t n_rows, int B, int C, int L,
                    int dtype, float* out, float* workspace, void* stream);
 
+/* Fused attention pooling, forward (abmil.py:36-45; clam.py:37-60,170): one pass over the rows h [n_rows, L] of B bags
+ * computes  uv = act(h wab^T + bab)  (tanh, or tanh | sigmoid when gated; [n_rows, D*(1+gated)], bf16, saved for the
+ * backward pass; NULL = do not keep),  s = wc . g(uv) + bc  (raw scores, fp32 [n_rows]),  p = post_scale_b * softmax_bag(s)
+ * (fp32 [n_rows]),  M[b] = sum_n p[n] h[n]  (fp32 [B, L])  and  stats[b] = (max, sum exp).  Each 128-row tile of h is
+ * staged once in shared memory by TMA, multiplied on the tensor cores (tcgen05, fp32 TMEM accumulators), gated, projected
+ * to scores and pooled with tile-local online-softmax statistics from the same shared-memory tile; a per-bag merge kernel
+ * folds the tile records and writes p.  Replaces murcl_linear_fwd + murcl_attn_score_fwd + murcl_seg_softmax +
+ * murcl_seg_wsum for C == 1.  Supported when murcl_attnpool_supported(...) != 0: bf16, L <= 512 and L % 64 == 0,
+ * D % 64 == 0, D*(1+gated) % 128 == 0 and <= 512.  workspace: murcl_attnpool_workspace(n_rows, B, L) floats.
+ * offsets int64 [B+1]; row_seg int32 [n_rows] (bag of every row, murcl_row_segments). */
+int murcl_attnpool_supported(int L, int D, int gated, int dtype);
+int64_t murcl_attnpool_workspace(int64_t n_rows, int B, int L);
+int murcl_attnpool_fwd(const void* h, const void* wab, const float* bab, const float* wc, const float* bc,
+                       const int64_t* offsets, const int32_t* row_seg, int64_t n_rows, int B, int L, int D, int gated,
+                       int inv_sqrt_n, int dtype, void* uv, float* s, float* p, float* M, float* stats, float* workspace,
+                       void* stream);
+
 /* Backward of p = post_scale*softmax(s), M = p^T h w.r.t. s:  ds[n,c] = p[n,c]*(dM[b,c].h[n] - k[b,c])
  * with k[b,c] = (dM[b,c].M[b,c]) / post_scale_b.  row_seg[n] = bag of row n. */
 int murcl_pool_bwd_scores(const float* p, const void* h, const float* dM, const float* M, const int64_t* offsets,

@@ -215,6 +215,36 @@ def seg_wsum(p, h, offsets, B, C):
     return out
 
 
+def attnpool_supported(L, D, gated, dtype) -> bool:
+    """The fused attention-pooling kernel covers bf16 rows with L <= 512 and D*(1+gated) <= 512 (a multiple of 128);
+    ``MURCL_DISABLE_ATTNPOOL=1`` forces the separate projection / score / softmax / weighted-sum kernels."""
+    if os.environ.get("MURCL_DISABLE_ATTNPOOL", "0") == "1" or dtype != torch.bfloat16:
+        return False
+    return bool(_lib.load().murcl_attnpool_supported(int(L), int(D), int(gated), _lib.BF16))
+
+
+def attnpool_fwd(h, wab, bab, wc, bc, offsets, row_seg, B, D, gated, inv_sqrt_n, save_uv=True):
+    """Fused uv / scores / softmax / pooled bag vectors in one pass over ``h`` (murcl_attnpool_fwd).
+    Returns (uv or None, s [n], p [n], M [B, 1, L], stats [B, 1, 2])."""
+    _chk(h, "attnpool_fwd.h", torch.bfloat16); _chk(wab, "attnpool_fwd.wab", torch.bfloat16)
+    n_rows, L = h.shape
+    nc = D * (2 if gated else 1)
+    if tuple(wab.shape) != (nc, L):
+        raise MurclError(f"attnpool_fwd: projection weight {tuple(wab.shape)} != ({nc}, {L})")
+    lib = _lib.load()
+    dev = h.device
+    uv = torch.empty((n_rows, nc), device=dev, dtype=torch.bfloat16) if save_uv else None
+    s = torch.empty((n_rows,), device=dev, dtype=torch.float32)
+    p = torch.empty((n_rows,), device=dev, dtype=torch.float32)
+    M = torch.empty((B, 1, L), device=dev, dtype=torch.float32)
+    stats = torch.empty((B, 1, 2), device=dev, dtype=torch.float32)
+    ws = torch.empty((max(int(lib.murcl_attnpool_workspace(n_rows, B, L)), 1),), device=dev, dtype=torch.float32)
+    check(lib.murcl_attnpool_fwd(_p(h), _p(wab), _p(bab), _p(wc), _p(bc), _p(offsets), _p(row_seg), n_rows, B, L, D,
+                                 int(gated), int(inv_sqrt_n), _lib.BF16, _p(uv) if uv is not None else None, _p(s), _p(p),
+                                 _p(M), _p(stats), _p(ws), _s()), "murcl_attnpool_fwd")
+    return uv, s, p, M, stats
+
+
 def pool_bwd_scores(p, h, dM, M, offsets, row_seg, B, C, inv_sqrt_n):
     n_rows, L = h.shape
     _chk(dM, "pool_bwd_scores.dM", torch.float32); _chk(M, "pool_bwd_scores.M", torch.float32)
@@ -447,16 +477,23 @@ class _MILAggregate(torch.autograd.Function):
             hbits.append(hb)
         H = hs[-1]
         wab_s = weight_as(wab, dt)
-        uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
-        if drop is not None and drop["attn"] > 0:
-            dropout_(uv, drop["attn"], seeds[-1:])
-        if _debug_save is not None:
-            _debug_save.update(hs=[h.clone() for h in hs], uv=uv.clone())
         wc_f = wc.detach().reshape(-1).contiguous().float()
         bc_f = bc.detach().reshape(-1).contiguous().float()
-        s = attn_score_fwd(uv, wc_f, bc_f, D, gated)
-        p, _ = seg_softmax(s, offsets, B, 1, meta["inv_sqrt_n"])
-        M = seg_wsum(p, H, offsets, B, 1).reshape(B, -1)
+        attn_drop = drop is not None and drop["attn"] > 0
+        if not attn_drop and attnpool_supported(H.shape[1], D, gated, H.dtype):
+            # one pass over H: projection (tcgen05) + gating + score + online softmax + weighted sum
+            uv, s, p, M, _ = attnpool_fwd(H, wab_s, bab.detach().contiguous().float(), wc_f, bc_f, offsets, row_seg, B, D,
+                                          gated, meta["inv_sqrt_n"])
+            M = M.reshape(B, -1)
+        else:
+            uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
+            if attn_drop:
+                dropout_(uv, drop["attn"], seeds[-1:])
+            s = attn_score_fwd(uv, wc_f, bc_f, D, gated)
+            p, _ = seg_softmax(s, offsets, B, 1, meta["inv_sqrt_n"])
+            M = seg_wsum(p, H, offsets, B, 1).reshape(B, -1)
+        if _debug_save is not None:
+            _debug_save.update(hs=[h.clone() for h in hs], uv=uv.clone())
         inst = meta.get("inst")
         inst_loss = s.new_zeros((0,))
         preds = s.new_zeros((0,), dtype=torch.int32)

@@ -1,0 +1,113 @@
+"""Fused attention pooling (murcl_attnpool_fwd: tcgen05 projection + gating + scores + online softmax + weighted sum in
+one pass over H) against (a) the separate projection / score / softmax / weighted-sum kernels it replaces and (b) an fp64
+evaluation of the same bf16 inputs (abmil.py:36-45, clam.py:37-60,170)."""
+import math
+import os
+
+import pytest
+import torch
+
+from murcl_b200 import synth
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+RAGGED = [1, 5, 127, 128, 129, 300, 1000, 64, 2, 2049]
+CASES = [
+    # L, D, gated, inv_sqrt_n, sizes
+    (512, 128, False, True, RAGGED),              # ABMIL
+    (512, 256, True, False, RAGGED),              # CLAM_SB small, gated: 512 projection columns = 4 column passes
+    (512, 256, False, False, [700, 3, 1500]),     # CLAM_SB small, not gated
+    (256, 64, True, False, [130, 126, 1]),        # narrow rows: 4 k-blocks, one column pass
+    (512, 128, False, True, [1024] * 24),         # tile-aligned bags (the pre-training layout), more tiles than SMs
+]
+
+
+def _inputs(L, D, gated, sizes, seed):
+    g = synth.gen(seed)
+    n = sum(sizes)
+    nc = D * (2 if gated else 1)
+    h = torch.clamp_min(0.5 * torch.randn(n, L, generator=g) + 0.2, 0).bfloat16()
+    wab = (torch.randn(nc, L, generator=g) * (2.0 / math.sqrt(L))).bfloat16()
+    bab = 0.3 * torch.randn(nc, generator=g)
+    wc = torch.randn(D, generator=g) * (3.0 / math.sqrt(D))
+    bc = torch.randn(1, generator=g)
+    offsets = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64)
+    return h, wab, bab, wc, bc, offsets
+
+
+def _reference(h, wab, bab, wc, bc, offsets, D, gated, inv_sqrt_n):
+    z = h.double() @ wab.double().t() + bab.double()
+    g = torch.tanh(z[:, :D]) * torch.sigmoid(z[:, D:]) if gated else torch.tanh(z)
+    s = g @ wc.double() + bc.double()
+    p = torch.empty_like(s)
+    M = []
+    for b in range(len(offsets) - 1):
+        lo, hi = int(offsets[b]), int(offsets[b + 1])
+        pb = torch.softmax(s[lo:hi], 0)
+        if inv_sqrt_n:
+            pb = pb / math.sqrt(hi - lo)
+        p[lo:hi] = pb
+        M.append(pb @ h[lo:hi].double())
+    return s, p, torch.stack(M)
+
+
+@pytest.mark.parametrize("L,D,gated,inv_sqrt_n,sizes", CASES)
+def test_attnpool_matches_separate_kernels_and_fp64(L, D, gated, inv_sqrt_n, sizes):
+    from murcl_b200 import ops
+    assert ops.attnpool_supported(L, D, gated, torch.bfloat16)
+    h, wab, bab, wc, bc, offsets = _inputs(L, D, gated, sizes, 11 * L + D + len(sizes))
+    B = len(sizes)
+    hd, wd, bd, wcd, bcd, od = (t.to(DEV) for t in (h, wab, bab, wc, bc, offsets))
+    row_seg = ops.row_segments(od, hd.shape[0])
+    uv, s, p, M, stats = ops.attnpool_fwd(hd, wd, bd, wcd, bcd, od, row_seg, B, D, gated, inv_sqrt_n)
+    # (a) the kernels it replaces: same MMA order, same MUFU activations -> the saved activations agree to the bit
+    os.environ["MURCL_GEMM"] = "tcgen05"
+    try:
+        uv2 = ops.linear_fwd(hd, wd, bd, ops.ACT_TANH_SIGMOID if gated else ops.ACT_TANH)
+    finally:
+        os.environ.pop("MURCL_GEMM", None)
+    mism = (uv != uv2).float().mean().item()
+    assert mism < 1e-3, f"saved activations differ from the GEMM path in {mism:.2e} of the entries"
+    assert_close(uv.float(), uv2.float(), 1e-3, "uv")
+    s2 = ops.attn_score_fwd(uv, wcd, bcd, D, gated)
+    p2, st2 = ops.seg_softmax(s2, od, B, 1, inv_sqrt_n)
+    M2 = ops.seg_wsum(p2, hd, od, B, 1)
+    assert_close(s, s2, 2e-6, "scores vs separate kernel")
+    assert_close(p, p2, 2e-5, "weights vs separate kernels")
+    assert_close(M, M2, 2e-5, "pooled vs separate kernels")
+    assert_close(stats[:, 0, 0], st2[:, 0, 0], 1e-6, "row max")
+    # (b) fp64 evaluation of the same bf16 inputs (MUFU tanh + bf16 rounding of the activations: bf16-mode budget)
+    s_ref, p_ref, M_ref = _reference(h, wab, bab, wc, bc, offsets, D, gated, inv_sqrt_n)
+    assert_close(s.cpu(), s_ref.float(), 2e-2, "scores vs fp64")
+    assert_close(M.cpu().reshape(B, L), M_ref.float(), 2e-2, "pooled vs fp64")
+    for b in range(B):
+        lo, hi = int(offsets[b]), int(offsets[b + 1])
+        tot = p[lo:hi].double().sum().item() * (math.sqrt(hi - lo) if inv_sqrt_n else 1.0)
+        assert abs(tot - 1.0) < 1e-5, f"bag {b}: weights sum to {tot}"
+
+
+def test_attnpool_without_saved_activations_and_empty_bag():
+    """Inference form (uv = NULL) and a bag with no rows between two others."""
+    from murcl_b200 import ops
+    L, D = 512, 128
+    sizes = [200, 0, 333]
+    h, wab, bab, wc, bc, offsets = _inputs(L, D, False, sizes, 5)
+    hd, wd, bd, wcd, bcd, od = (t.to(DEV) for t in (h, wab, bab, wc, bc, offsets))
+    row_seg = ops.row_segments(od, hd.shape[0])
+    uv, s, p, M, stats = ops.attnpool_fwd(hd, wd, bd, wcd, bcd, od, row_seg, 3, D, False, True, save_uv=False)
+    assert uv is None
+    _, s1, p1, M1, _ = ops.attnpool_fwd(hd, wd, bd, wcd, bcd, od, row_seg, 3, D, False, True, save_uv=True)
+    assert torch.equal(s, s1) and torch.equal(p, p1) and torch.equal(M, M1)
+    assert float(M[1].abs().max()) == 0.0 and float(stats[1, 0, 1]) == 0.0
+    s_ref, p_ref, M_ref = _reference(h, wab, bab, wc, bc, torch.tensor([0, 200, 200, 533]), D, False, True)
+    assert_close(M.cpu()[[0, 2]].reshape(2, L), M_ref.float()[[0, 2]], 2e-2, "pooled vs fp64")
+
+
+def test_attnpool_rejects_unsupported_shapes():
+    from murcl_b200 import ops
+    assert not ops.attnpool_supported(1024, 128, False, torch.bfloat16)      # rows wider than the resident tile
+    assert not ops.attnpool_supported(512, 384, True, torch.bfloat16)        # 768 projection columns > TMEM
+    assert not ops.attnpool_supported(512, 128, False, torch.float32)        # fp32 mode keeps the exact SIMT path
+    assert ops.attnpool_supported(512, 384, False, torch.bfloat16)

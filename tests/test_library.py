@@ -102,3 +102,15 @@ def test_clam_instance_plan_layout():
     R.sizes = [5, 30]
     with pytest.raises(RuntimeError):
         m._instance_plan(R, [1, 0])
+
+
+def test_attnpool_supported_shapes():
+    """Host-side shape gate of the fused attention-pooling kernel (no device work)."""
+    from murcl_b200 import _lib
+    lib = _lib.load()
+    assert lib.murcl_attnpool_supported(512, 128, 0, _lib.BF16) == 1      # ABMIL
+    assert lib.murcl_attnpool_supported(512, 256, 1, _lib.BF16) == 1      # CLAM_SB small, gated
+    assert lib.murcl_attnpool_supported(512, 384, 1, _lib.BF16) == 0      # CLAM_SB big, gated: 768 columns
+    assert lib.murcl_attnpool_supported(1024, 128, 0, _lib.BF16) == 0
+    assert lib.murcl_attnpool_supported(512, 128, 0, _lib.F32) == 0
+    assert lib.murcl_attnpool_workspace(1000, 3, 512) == (8 + 3 + 1) * 516
