@@ -220,6 +220,10 @@ def attnpool_supported(L, D, gated, dtype) -> bool:
     ``MURCL_DISABLE_ATTNPOOL=1`` forces the separate projection / score / softmax / weighted-sum kernels."""
     if os.environ.get("MURCL_DISABLE_ATTNPOOL", "0") == "1" or dtype != torch.bfloat16:
         return False
+    # with more than 256 projection columns the kernel re-streams the row tile and the weights once per 128 columns
+    # (L2-bandwidth bound) and has a single TMEM accumulator stage: the CTA-pair GEMM + separate kernels are as fast
+    if D * (2 if gated else 1) > 256 and os.environ.get("MURCL_FORCE_ATTNPOOL", "0") != "1":
+        return False
     return bool(_lib.load().murcl_attnpool_supported(int(L), int(D), int(gated), _lib.BF16))
 
 

@@ -55,8 +55,8 @@ def _reference(h, wab, bab, wc, bc, offsets, D, gated, inv_sqrt_n):
 
 @pytest.mark.parametrize("L,D,gated,inv_sqrt_n,sizes", CASES)
 def test_attnpool_matches_separate_kernels_and_fp64(L, D, gated, inv_sqrt_n, sizes):
-    from murcl_b200 import ops
-    assert ops.attnpool_supported(L, D, gated, torch.bfloat16)
+    from murcl_b200 import ops, _lib
+    assert _lib.load().murcl_attnpool_supported(L, D, int(gated), _lib.BF16) == 1
     h, wab, bab, wc, bc, offsets = _inputs(L, D, gated, sizes, 11 * L + D + len(sizes))
     B = len(sizes)
     hd, wd, bd, wcd, bcd, od = (t.to(DEV) for t in (h, wab, bab, wc, bc, offsets))
@@ -110,4 +110,5 @@ def test_attnpool_rejects_unsupported_shapes():
     assert not ops.attnpool_supported(1024, 128, False, torch.bfloat16)      # rows wider than the resident tile
     assert not ops.attnpool_supported(512, 384, True, torch.bfloat16)        # 768 projection columns > TMEM
     assert not ops.attnpool_supported(512, 128, False, torch.float32)        # fp32 mode keeps the exact SIMT path
-    assert ops.attnpool_supported(512, 384, False, torch.bfloat16)
+    assert ops.attnpool_supported(512, 256, False, torch.bfloat16)
+    assert not ops.attnpool_supported(512, 256, True, torch.bfloat16)        # supported by the kernel, not preferred (512 columns)

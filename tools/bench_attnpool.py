@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Time the fused attention-pooling forward against the separate kernels on the pre-training shape
+(256 bags x 1024 rows x 512, D = 128) and on a gated CLAM shape.  CUDA events, L2 flushed between repetitions."""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from murcl_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, reps=10):
+    """Back-to-back launches between two events: the queue hides the host-side launch cost (allocations, tensor-map
+    encoding); the 268 MB input is larger than L2, so every call streams it from HBM again."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def main():
+    reps = int(os.environ.get("REPS", "20"))
+    for (B, FS, L, D, gated) in ((256, 1024, 512, 128, False), (64, 4096, 512, 256, True)):
+        n = B * FS
+        nc = D * (2 if gated else 1)
+        g = torch.Generator(device="cpu"); g.manual_seed(1)
+        h = torch.clamp_min(0.5 * torch.randn(n, L, generator=g) + 0.2, 0).bfloat16().to(DEV)
+        wab = (torch.randn(nc, L, generator=g) / math.sqrt(L)).bfloat16().to(DEV)
+        bab = torch.randn(nc, generator=g).to(DEV)
+        wc = (torch.randn(D, generator=g) / math.sqrt(D)).to(DEV)
+        bc = torch.randn(1, generator=g).to(DEV)
+        off = (torch.arange(B + 1, dtype=torch.int64) * FS).to(DEV)
+        seg = ops.row_segments(off, n)
+
+        def fused():
+            return ops.attnpool_fwd(h, wab, bab, wc, bc, off, seg, B, D, gated, True)
+
+        def separate():
+            uv = ops.linear_fwd(h, wab, bab, ops.ACT_TANH_SIGMOID if gated else ops.ACT_TANH)
+            s = ops.attn_score_fwd(uv, wc, bc, D, gated)
+            p, _ = ops.seg_softmax(s, off, B, 1, True)
+            return ops.seg_wsum(p, h, off, B, 1)
+
+        tf, ts = timeit(fused, reps), timeit(separate, reps)
+        byts = n * (L * 2 + nc * 2 + 8)
+        print(f"B={B} FS={FS} L={L} D={D} gated={gated}: fused {tf:.1f} us ({byts / tf / 1e3:.0f} GB/s algorithmic), "
+              f"separate kernels {ts:.1f} us")
+
+
+if __name__ == "__main__":
+    main()
