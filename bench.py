@@ -224,10 +224,12 @@ def roofline_probe(job, store, peaks):
     from murcl_b200 import ops
     log = []
     ops.set_profile(log)
+    torch.cuda.nvtx.range_push("murcl_probe_step")      # ncu --nvtx --nvtx-include "murcl_probe_step/" profiles exactly this step
     try:
         job.step(store)
         torch.cuda.synchronize()
     finally:
+        torch.cuda.nvtx.range_pop()
         ops.set_profile(None)
     by = {}
     for name, flops, e0, e1 in log:
@@ -252,7 +254,14 @@ def roofline_probe(job, store, peaks):
             traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
         except (ValueError, OSError):
             traffic = None
-    fam = {k: {"launches": v[2], "ms": round(v[1], 3), "tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1)} for k, v in by.items()}
+    fam = {k: {"launches": v[2], "ms": round(v[1], 3), "tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1)} for k, v in by.items()
+           if k != "attnpool_fwd"}
+    hbm = peaks.get("hbm_gbs") or 6500.0
+    if "attnpool_fwd" in by:     # the fused attention-pooling forward is HBM-bound: its record carries algorithmic bytes
+        v = by["attnpool_fwd"]
+        gbs = v[0] / (v[1] * 1e-3) / 1e9
+        fam["attnpool_fwd"] = {"launches": v[2], "ms": round(v[1], 3), "bound": "hbm", "algorithmic_gbs": round(gbs, 1),
+                               "frac_of_hbm_peak": round(gbs / hbm, 3)}
     return {"bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
             "traffic": traffic,
             "kernel": "gemm_tc_kernel (tcgen05) on the instance-level dense layers: murcl_linear_fwd / bwd_input / bwd_weight, "

@@ -349,6 +349,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t row0 = ((int64_t)mb * CG + cta_rank) * BLOCK_M + quarter * 32;
       const int64_t row = row0 + lane;
       const int n0 = nb * BN;
+      // per-row operands of the pooling term: two dependent global loads, issued before the accumulator wait so that their
+      // latency is hidden behind it (the wait is a compiler barrier: loads placed after it would start after it)
+      float rs = 0.f;
+      const float* rv = nullptr;
+      if (EPI == EPI_DGRAD && p.row_scale != nullptr && row < p.M) {
+        rs = __ldg(p.row_scale + row);
+        rv = p.row_vec + (int64_t)__ldg(p.row_seg + row) * p.N;
+      }
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -375,12 +383,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       } else {
-        float rs = 0.f;
-        const float* rv = nullptr;
-        if (EPI == EPI_DGRAD && p.row_scale != nullptr && row < p.M) {
-          rs = p.row_scale[row];
-          rv = p.row_vec + (int64_t)p.row_seg[row] * p.N;
-        }
         if (want_colsum && nb != acc_nb) {                 // new column tile: flush the CTA's partial sums
           if (acc_nb >= 0) flush_colacc(acc_nb);
           acc_nb = nb;
@@ -393,6 +395,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // ReLU bit masks: one 64-bit word per (row, 64 columns), layout [N/64][M]; a unit owns one 32-bit half of a word.
           // Consecutive rows are consecutive words: the per-lane accesses of a warp stay within 256 contiguous bytes.
           const int64_t bit_word = (((int64_t)(col0 >> 6) * p.M + row) << 1) + ((col0 >> 5) & 1);
+          // the ReLU bit word is requested BEFORE the TMEM load, whose wait is a compiler barrier - otherwise its L2 latency
+          // would be exposed after it, once per unit (hoisting the 8 float4 operand loads as well costs spills: slower)
+          const bool whole = col0 + 32 <= p.N;               // warp-uniform
+          unsigned int wbits = 0u;
+          if (EPI == EPI_DGRAD && p.bits_in != nullptr && row < p.M)
+            wbits = __ldg(reinterpret_cast<const unsigned int*>(p.bits_in) + bit_word);
           float v[32];
           {
             uint32_t r[32];
@@ -403,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (EPI == EPI_FWD) {
             if (p.bias != nullptr) {
-              if (col0 + 32 <= p.N) {                       // whole unit in range: branch-free, loads issued back to back
+              if (whole) {                                  // whole unit in range: branch-free, loads issued back to back
                 float4 b4[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
@@ -435,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else if (EPI == EPI_DGRAD) {
             if (rv != nullptr) {
-              if (col0 + 32 <= p.N) {
+              if (whole) {
                 float4 g4[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(rv + col0) + i);
@@ -456,10 +464,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (p.bits_in != nullptr) {
-              const unsigned int w = row < p.M ? __ldg(reinterpret_cast<const unsigned int*>(p.bits_in) + bit_word) : 0u;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (!((w >> i) & 1u)) v[i] = 0.f;
+                if (!((wbits >> i) & 1u)) v[i] = 0.f;
             } else if (has_mask) {
               // no bit mask from the forward pass: read the ReLU output itself (64 contiguous bytes per row)
               if (row < p.M) {

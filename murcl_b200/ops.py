@@ -243,9 +243,11 @@ def attnpool_fwd(h, wab, bab, wc, bc, offsets, row_seg, B, D, gated, inv_sqrt_n,
     M = torch.empty((B, 1, L), device=dev, dtype=torch.float32)
     stats = torch.empty((B, 1, 2), device=dev, dtype=torch.float32)
     ws = torch.empty((max(int(lib.murcl_attnpool_workspace(n_rows, B, L)), 1),), device=dev, dtype=torch.float32)
-    check(lib.murcl_attnpool_fwd(_p(h), _p(wab), _p(bab), _p(wc), _p(bc), _p(offsets), _p(row_seg), n_rows, B, L, D,
-                                 int(gated), int(inv_sqrt_n), _lib.BF16, _p(uv) if uv is not None else None, _p(s), _p(p),
-                                 _p(M), _p(stats), _p(ws), _s()), "murcl_attnpool_fwd")
+    # profile record: "flops" slot carries the algorithmic HBM bytes of this HBM-bound kernel (h once, uv, s, p)
+    with _Timed("attnpool_fwd", float(n_rows) * (L * 2 + (nc * 2 if save_uv else 0) + 8)):
+        check(lib.murcl_attnpool_fwd(_p(h), _p(wab), _p(bab), _p(wc), _p(bc), _p(offsets), _p(row_seg), n_rows, B, L, D,
+                                     int(gated), int(inv_sqrt_n), _lib.BF16, _p(uv) if uv is not None else None, _p(s), _p(p),
+                                     _p(M), _p(stats), _p(ws), _s()), "murcl_attnpool_fwd")
     return uv, s, p, M, stats
 
 
