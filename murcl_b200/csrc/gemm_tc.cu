@@ -398,6 +398,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // the ReLU bit word is requested BEFORE the TMEM load, whose wait is a compiler barrier - otherwise its L2 latency
           // would be exposed after it, once per unit (hoisting the 8 float4 operand loads as well costs spills: slower)
           const bool whole = col0 + 32 <= p.N;               // warp-uniform
+          // the unit's 128-byte line of the bias / pooling row vector: pulled into L1 now, read after the TMEM wait
+          if (EPI == EPI_FWD && p.bias != nullptr) prefetch_l1(p.bias + col0);
+          if (EPI == EPI_DGRAD && rv != nullptr) prefetch_l1(rv + col0);
           unsigned int wbits = 0u;
           if (EPI == EPI_DGRAD && p.bits_in != nullptr && row < p.M)
             wbits = __ldg(reinterpret_cast<const unsigned int*>(p.bits_in) + bit_word);

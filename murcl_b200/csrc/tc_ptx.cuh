@@ -38,6 +38,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 // L2 eviction-priority policies for data with a known reuse pattern (createpolicy, PTX ISA "cache eviction priority hints").
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
