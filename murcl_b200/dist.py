@@ -8,6 +8,10 @@ parameters and scatters ~268 MB of features per forward call.  Here (SURVEY.md s
     rank evaluates NT-Xent on the global ``2B x 2B`` matrix; the backward needs no collective - a rank keeps
     the gradient rows of its own samples;
   * ONE all-reduce(sum) per optimiser step carries all parameter gradients as a single flat bucket.
+
+Intra-bag sharding (BASELINE config 5: one 100k-patch bag over 2/4/8 GPUs): the rows of every bag are
+split across the ranks; each rank pools its own rows and ONE all-gather of ``3 + L`` floats per bag merges the partial
+results (online-softmax merge) - ``sharded_attention_pool``.  The backward pass needs no collective.
 """
 from __future__ import annotations
 
@@ -83,3 +87,89 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None) -> int:
     for g, synced in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
         g.copy_(synced)
     return flat.numel() * flat.element_size()
+
+
+# ------------------------------------------------------------------------------------------------
+# intra-bag sharding: attention pooling of bags whose ROWS are split across the ranks
+# ------------------------------------------------------------------------------------------------
+def merge_pool_partials(m: torch.Tensor, l: torch.Tensor, M_loc: torch.Tensor, n: torch.Tensor, group=None):
+    """Online-softmax merge of per-rank pooling partials of the same ``B`` bags.
+
+    ``m``, ``l`` [B]: max and sum-exp of the rank's scores of each bag (``-inf`` / 0 where the rank holds no row of it);
+    ``M_loc`` [B, L]: sum over the rank's rows of ``softmax_local(s) * h`` (normalised with the LOCAL ``l``);
+    ``n`` [B]: the rank's row counts.  Returns ``(M, scale, n_total)``: the globally normalised pooled vectors, the factor
+    ``l_r e^{m_r - m} / l`` that turns this rank's local softmax weights into global ones, and the global row counts.
+    One all-gather of ``3 + L`` floats per bag; without an initialised process group it is the identity."""
+    B, L = M_loc.shape
+    packed = torch.cat([m.reshape(B, 1), l.reshape(B, 1), n.reshape(B, 1).to(M_loc.dtype), M_loc], 1).contiguous()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        allp = torch.empty((world * B, 3 + L), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(allp, packed, group=group)
+        allp = allp.view(world, B, 3 + L)
+    else:
+        rank, allp = 0, packed.unsqueeze(0)
+    m_r, l_r, n_r, M_r = allp[..., 0], allp[..., 1], allp[..., 2], allp[..., 3:]
+    m_g = m_r.max(0).values                                                   # [B]
+    safe = torch.where(torch.isfinite(m_g), m_g, torch.zeros_like(m_g))      # bags with no rows anywhere
+    w_r = l_r * torch.exp(m_r - safe)                                         # [W, B]; exp(-inf) = 0 for empty shards
+    l_g = w_r.sum(0)
+    inv = torch.where(l_g > 0, 1.0 / l_g, torch.zeros_like(l_g))
+    M = (w_r.unsqueeze(-1) * M_r).sum(0) * inv.unsqueeze(-1)
+    return M, w_r[rank] * inv, n_r.sum(0)
+
+
+class _KernelPoolFns:
+    """The CUDA kernels behind the local part of the sharded pooling (murcl_seg_softmax, murcl_seg_wsum,
+    murcl_pool_bwd_scores, murcl_pool_bwd_direct).  Tests on CPU substitute a torch implementation."""
+
+    @staticmethod
+    def local_pool(h, s, offsets, row_seg, B):
+        from . import ops
+        p, stats = ops.seg_softmax(s.contiguous(), offsets, B, 1, False)
+        M = ops.seg_wsum(p, h, offsets, B, 1).reshape(B, -1)
+        return p, stats[:, 0, 0], stats[:, 0, 1], M
+
+    @staticmethod
+    def backward(p, h, dM, M, offsets, row_seg, B):
+        from . import ops
+        L = h.shape[1]
+        ds = ops.pool_bwd_scores(p, h, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, False)
+        dh = torch.empty_like(h)
+        ops.pool_bwd_direct(p, dM, row_seg, 1, L, dh, False)
+        return dh, ds
+
+
+class _ShardedAttentionPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, s, offsets, row_seg, inv_sqrt_n, group, fns):
+        B = offsets.numel() - 1
+        hd, sd = h.detach().contiguous(), s.detach().contiguous().float()
+        p_loc, m, l, M_loc = fns.local_pool(hd, sd, offsets, row_seg, B)
+        n_loc = (offsets[1:] - offsets[:-1]).to(torch.float32)
+        M, scale, n_tot = merge_pool_partials(m, l, M_loc, n_loc, group)
+        post = torch.rsqrt(n_tot.clamp_min(1.0)) if inv_sqrt_n else torch.ones_like(n_tot)   # abmil.py:41 on the GLOBAL count
+        p = (p_loc * scale[row_seg.long()]).contiguous()                      # global softmax weights of the local rows
+        ctx.save_for_backward(hd, p, M, post, offsets, row_seg)
+        ctx.fns = fns
+        ctx.mark_non_differentiable(p)
+        return M * post.unsqueeze(1), p * post[row_seg.long()]
+
+    @staticmethod
+    def backward(ctx, dout, _dp):
+        h, p, M, post, offsets, row_seg = ctx.saved_tensors
+        B = offsets.numel() - 1
+        dM = (dout.float() * post.unsqueeze(1)).contiguous()                  # gradient w.r.t. the un-scaled pooled vectors
+        dh, ds = ctx.fns.backward(p, h, dM, M.contiguous(), offsets, row_seg, B)
+        return dh, ds, None, None, None, None, None
+
+
+def sharded_attention_pool(h: torch.Tensor, s: torch.Tensor, offsets: torch.Tensor, row_seg: torch.Tensor,
+                           inv_sqrt_n: bool = False, group=None, fns=None):
+    """Attention pooling ``M[b] = post_b * sum_n softmax_bag(s)[n] h[n]`` of ``B`` bags whose rows are split across the
+    ranks of ``group``: ``h`` [n_local, L] and ``s`` [n_local] are this rank's rows and raw scores, ``offsets`` [B+1] /
+    ``row_seg`` [n_local] their LOCAL CSR description (a rank may hold no row of a bag).  Returns ``(M [B, L], p [n_local])``
+    - the same on every rank for ``M``, the global attention weights of the local rows for ``p``.  Differentiable in
+    ``h`` and ``s``; every rank must feed the same ``dM`` (a replicated head does), then no backward collective is needed
+    and the parameter gradients are summed by ``allreduce_grads`` as usual."""
+    return _ShardedAttentionPool.apply(h, s, offsets, row_seg, bool(inv_sqrt_n), group, fns or _KernelPoolFns)

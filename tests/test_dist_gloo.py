@@ -64,3 +64,74 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- intra-bag sharding: rows of every bag split across ranks ------------------------------------------------------
+class _TorchPoolFns:
+    """Torch stand-in for the local pooling kernels (the CUDA kernels do not run in this container)."""
+
+    @staticmethod
+    def local_pool(h, s, offsets, row_seg, B):
+        p = torch.zeros_like(s)
+        m = torch.full((B,), float("-inf"))
+        l = torch.zeros(B)
+        M = torch.zeros(B, h.shape[1])
+        for b in range(B):
+            lo, hi = int(offsets[b]), int(offsets[b + 1])
+            if hi > lo:
+                m[b] = s[lo:hi].max()
+                e = torch.exp(s[lo:hi] - m[b])
+                l[b] = e.sum()
+                p[lo:hi] = e / l[b]
+                M[b] = p[lo:hi] @ h[lo:hi]
+        return p, m, l, M
+
+    @staticmethod
+    def backward(p, h, dM, M, offsets, row_seg, B):
+        seg = row_seg.long()
+        k = (dM * M).sum(1)
+        ds = p * ((dM[seg] * h).sum(1) - k[seg])
+        return p.unsqueeze(1) * dM[seg], ds
+
+
+def _pool_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(3)
+    sizes = [37, 1, 12, 0, 5]                                # rows per bag (one empty bag, one single-row bag)
+    L = 16
+    H = [torch.randn(n, L, generator=g) for n in sizes]
+    S = [3.0 * torch.randn(n, generator=g) for n in sizes]
+    G = torch.randn(len(sizes), L, generator=g)              # upstream gradient, the same on every rank
+    ok = True
+    for inv_sqrt_n in (False, True):
+        # this rank's slice of every bag (rank 1 gets nothing of the single-row bag)
+        parts = [mdist.shard_range(n, rank, world) for n in sizes]
+        h = torch.cat([H[b][lo:hi] for b, (lo, hi) in enumerate(parts)]).requires_grad_(True)
+        s = torch.cat([S[b][lo:hi] for b, (lo, hi) in enumerate(parts)]).requires_grad_(True)
+        counts = torch.tensor([hi - lo for lo, hi in parts])
+        offsets = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)])
+        row_seg = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.int32), counts)
+        M, p = mdist.sharded_attention_pool(h, s, offsets, row_seg, inv_sqrt_n, fns=_TorchPoolFns)
+        (M * G).sum().backward()
+        # single-process reference on whole bags
+        Hf = [x.clone().requires_grad_(True) for x in H]
+        Sf = [x.clone().requires_grad_(True) for x in S]
+        ref = torch.stack([O.softmax_pool(Sf[b], Hf[b], sizes[b] ** -0.5 if inv_sqrt_n else 1.0)[0] if sizes[b] else torch.zeros(L)
+                           for b in range(len(sizes))])
+        (ref * G).sum().backward()
+        dh_ref = torch.cat([Hf[b].grad[lo:hi] for b, (lo, hi) in enumerate(parts) if sizes[b]])
+        ds_ref = torch.cat([Sf[b].grad[lo:hi] for b, (lo, hi) in enumerate(parts) if sizes[b]])
+        ok = ok and torch.allclose(M, ref, atol=1e-6) and torch.allclose(h.grad, dh_ref, atol=1e-6) \
+            and torch.allclose(s.grad, ds_ref, atol=1e-6)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_attention_pool_matches_whole_bags():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_pool_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}

@@ -112,3 +112,32 @@ def test_attnpool_rejects_unsupported_shapes():
     assert not ops.attnpool_supported(512, 128, False, torch.float32)        # fp32 mode keeps the exact SIMT path
     assert ops.attnpool_supported(512, 256, False, torch.bfloat16)
     assert not ops.attnpool_supported(512, 256, True, torch.bfloat16)        # supported by the kernel, not preferred (512 columns)
+
+
+def test_sharded_attention_pool_kernels_single_rank():
+    """dist.sharded_attention_pool on the CUDA kernels (no process group: the merge is the identity; the 2-rank merge
+    itself is covered on CPU by tests/test_dist_gloo.py and on 2 GPUs by tools/check_sharded_pool.py)."""
+    from murcl_b200 import dist as mdist, ops
+    from oracle import murcl_oracle as O
+    g = synth.gen(21)
+    sizes = [300, 1, 0, 77]
+    L = 512
+    H = [torch.randn(n, L, generator=g) for n in sizes]
+    S = [2.0 * torch.randn(n, generator=g) for n in sizes]
+    G = torch.randn(len(sizes), L, generator=g)
+    offsets = torch.tensor([0, 300, 301, 301, 378], dtype=torch.int64, device=DEV)
+    row_seg = ops.row_segments(offsets, 378)
+    for inv_sqrt_n in (False, True):
+        h = torch.cat(H).to(DEV).requires_grad_(True)
+        s = torch.cat(S).to(DEV).requires_grad_(True)
+        M, p = mdist.sharded_attention_pool(h, s, offsets, row_seg, inv_sqrt_n)
+        (M * G.to(DEV)).sum().backward()
+        Hf = [x.clone().requires_grad_(True) for x in H]
+        Sf = [x.clone().requires_grad_(True) for x in S]
+        ref = torch.stack([O.softmax_pool(Sf[b], Hf[b], sizes[b] ** -0.5 if inv_sqrt_n else 1.0)[0] if sizes[b] else torch.zeros(L)
+                           for b in range(len(sizes))])
+        (ref * G).sum().backward()
+        assert_close(M.cpu(), ref.detach(), 1e-5, "pooled")
+        assert_close(h.grad.cpu(), torch.cat([x.grad for x, n in zip(Hf, sizes) if n]), 1e-5, "dh")
+        # ds = p (dM.h - dM.M): a difference of two O(sqrt(L)) dot products in fp32 (measured 1.8e-5)
+        assert_close(s.grad.cpu(), torch.cat([x.grad for x, n in zip(Sf, sizes) if n]), 1e-4, "ds")
