@@ -114,3 +114,35 @@ def test_attnpool_supported_shapes():
     assert lib.murcl_attnpool_supported(1024, 128, 0, _lib.BF16) == 0
     assert lib.murcl_attnpool_supported(512, 128, 0, _lib.F32) == 0
     assert lib.murcl_attnpool_workspace(1000, 3, 512) == (8 + 3 + 1) * 516
+
+
+def test_attnpool_record_index_is_unique_per_tile_bag_incidence():
+    """The fused pooling kernel writes one partial record per (128-row tile, bag) incidence at index tile + bag and the
+    merge kernel reads records tile + bag for tile in [off[b] // 128, (off[b+1] - 1) // 128] (csrc/attnpool.cu).  Both
+    indices only grow along the rows, so the sum is unique and stays inside the (tiles + B + 1)-record workspace - also
+    with empty bags, bags smaller than a tile and boundaries that coincide with tile boundaries."""
+    import random
+    rng = random.Random(7)
+    for _ in range(200):
+        B = rng.randint(1, 12)
+        sizes = [rng.choice([0, 1, 5, 127, 128, 129, 256, 300, rng.randint(0, 700)]) for _ in range(B)]
+        off = [0]
+        for n in sizes:
+            off.append(off[-1] + n)
+        n_rows = off[-1]
+        tiles = (n_rows + 127) // 128
+        written = {}
+        for t in range(tiles):                                  # kernel side: segments of tile t
+            row0, last = t * 128, min(t * 128 + 127, n_rows - 1)
+            seg = lambda r: max(b for b in range(B) if off[b] <= r and sizes[b] > 0 and r < off[b + 1])
+            for b in range(seg(row0), seg(last) + 1):
+                r_begin, r_end = max(off[b] - row0, 0), min(off[b + 1] - row0, 128)
+                if r_end > r_begin:
+                    assert (t + b) not in written, "two incidences share a record"
+                    written[t + b] = (t, b)
+        for b in range(B):                                      # merge side
+            if sizes[b] == 0:
+                continue
+            for t in range(off[b] // 128, (off[b + 1] - 1) // 128 + 1):
+                assert written.get(t + b) == (t, b), "merge reads a record of another incidence"
+        assert all(k < tiles + B + 1 for k in written)
