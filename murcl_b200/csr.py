@@ -174,7 +174,11 @@ def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, per
 class HostBags:
     """A batch of slides staged in PINNED host memory in the CSR layout (what a data loader hands over)."""
 
-    def __init__(self, feat_list, labels_list, num_clusters: int, pin: bool = True, dtype: torch.dtype = torch.float32):
+    def __init__(self, feat_list, labels_list, num_clusters: int, pin: bool = True, dtype: torch.dtype = torch.float32,
+                 ranks_list=None):
+        """``labels_list[b][p]`` = cluster of patch p (``features_cluster_indices``); ``ranks_list[b][p]`` = position of
+        the patch inside its cluster's list.  Without ``ranks_list`` the lists are taken to be in ascending patch order
+        (how ``features_clustering.py:19-25`` writes them): rank = number of earlier patches with the same label."""
         sizes = [int(f.shape[-2]) for f in feat_list]
         d = int(feat_list[0].shape[-1])
         self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64).tolist()
@@ -191,7 +195,10 @@ class HostBags:
             self.patch_cluster[lo:hi] = lab.to(torch.int32)
             # rank of a patch inside its cluster = number of earlier patches with the same label
             onehot = torch.nn.functional.one_hot(lab, self.K)
-            self.patch_rank[lo:hi] = ((onehot.cumsum(0) - 1) * onehot).sum(1).to(torch.int32)
+            if ranks_list is not None and ranks_list[b] is not None:
+                self.patch_rank[lo:hi] = torch.as_tensor(ranks_list[b]).reshape(-1).to(torch.int32)
+            else:
+                self.patch_rank[lo:hi] = ((onehot.cumsum(0) - 1) * onehot).sum(1).to(torch.int32)
             self.cluster_sizes[b] = onehot.sum(0).to(torch.int32)
         if pin and torch.cuda.is_available():
             self.feats = self.feats.pin_memory()
@@ -199,6 +206,54 @@ class HostBags:
             self.patch_rank = self.patch_rank.pin_memory()
             self.cluster_sizes = self.cluster_sizes.pin_memory()
 
+    @classmethod
+    def from_files(cls, feature_files: Sequence[str], cluster_files: Sequence[str], num_clusters: int, pin: bool = True,
+                   dtype: torch.dtype = torch.float32) -> "HostBags":
+        """Slides from the reference's on-disk format (README.md:102-136): ``feature_files[b]`` is the ``.npz`` written by
+        ``wsi_processing/extract_features.py`` (array ``img_features`` [N, D], read at utils/datasets.py:89,150);
+        ``cluster_files[b]`` is either the ``.npz`` of ``features_clustering.py:10-16`` (array ``features_cluster_indices``
+        [N, 1]) or the ``.json`` inverted lists of ``features_clustering.py:19-25`` (K lists of patch ids, read at
+        utils/datasets.py:151,163).  JSON lists keep their order: a patch's rank is its position in its list."""
+        feats, labels, ranks = [], [], []
+        for ff, cf in zip(feature_files, cluster_files):
+            f, lab, rk = load_slide(ff, cf, num_clusters)
+            feats.append(f)
+            labels.append(lab)
+            ranks.append(rk)
+        return cls(feats, labels, num_clusters, pin=pin, dtype=dtype, ranks_list=ranks)
+
     @property
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.feats, self.patch_cluster, self.patch_rank, self.cluster_sizes))
+
+
+def load_slide(feature_file: str, cluster_file: str, num_clusters: int):
+    """One slide from disk -> (features fp32 [N, D], labels int32 [N], ranks int32 [N] or None).  See
+    ``HostBags.from_files`` for the formats.  Raises ``ValueError`` when the two files disagree."""
+    import json
+    feats = torch.as_tensor(np.load(feature_file)["img_features"], dtype=torch.float32)
+    if feats.dim() != 2:
+        raise ValueError(f"{feature_file}: img_features must be [N, D], got {tuple(feats.shape)}")
+    n = feats.shape[0]
+    if str(cluster_file).endswith(".json"):
+        with open(cluster_file) as fh:
+            lists = json.load(fh)
+        if len(lists) != num_clusters:
+            raise ValueError(f"{cluster_file}: {len(lists)} cluster lists, expected {num_clusters}")
+        labels = np.full((n,), -1, dtype=np.int32)
+        ranks = np.zeros((n,), dtype=np.int32)
+        for j, ids in enumerate(lists):
+            ids = np.asarray(ids, dtype=np.int64)
+            if ids.size and (ids.min() < 0 or ids.max() >= n):
+                raise ValueError(f"{cluster_file}: patch id out of range for {n} patches")
+            labels[ids] = j
+            ranks[ids] = np.arange(ids.size, dtype=np.int32)
+        if (labels < 0).any() or sum(len(ids) for ids in lists) != n:
+            raise ValueError(f"{cluster_file}: the cluster lists are not a partition of the {n} patches")
+        return feats, torch.from_numpy(labels), torch.from_numpy(ranks)
+    labels = np.load(cluster_file)["features_cluster_indices"].reshape(-1).astype(np.int32)
+    if labels.shape[0] != n:
+        raise ValueError(f"{cluster_file}: {labels.shape[0]} labels for {n} patches")
+    if labels.size and (labels.min() < 0 or labels.max() >= num_clusters):
+        raise ValueError(f"{cluster_file}: cluster label outside [0, {num_clusters})")
+    return feats, torch.from_numpy(labels), None

@@ -146,3 +146,49 @@ def test_attnpool_record_index_is_unique_per_tile_bag_incidence():
             for t in range(off[b] // 128, (off[b + 1] - 1) // 128 + 1):
                 assert written.get(t + b) == (t, b), "merge reads a record of another incidence"
         assert all(k < tiles + B + 1 for k in written)
+
+
+def test_host_bags_from_reference_file_formats(tmp_path):
+    """.npz features + .npz labels / .json inverted lists -> pinned CSR staging.  The ranks must
+    reproduce the positions get_feats slices (utils/datasets.py:293-296), also for a list that is not in ascending order."""
+    import json
+    import numpy as np
+    from murcl_b200 import synth
+    from murcl_b200.csr import HostBags, load_slide
+    from oracle import murcl_oracle as O
+    K, D = 4, 8
+    feats, clusters, labels = synth.make_bags([50, 7, 33], D, K, seed=12)
+    clusters[2][1] = clusters[2][1][::-1]                       # one list deliberately reversed (JSON slide only)
+    ffiles, cfiles = [], []
+    for b, (f, c, l) in enumerate(zip(feats, clusters, labels)):
+        ff = tmp_path / f"slide{b}.npz"
+        np.savez(ff, img_features=f.numpy())
+        if b == 1:                                              # label file as written by features_clustering.py:10-16
+            cf = tmp_path / f"slide{b}_clusters.npz"
+            np.savez(cf, features_cluster_indices=l.numpy().reshape(-1, 1))
+        else:                                                   # inverted lists as written by features_clustering.py:19-25
+            cf = tmp_path / f"slide{b}.json"
+            cf.write_text(json.dumps(c))
+        ffiles.append(str(ff)); cfiles.append(str(cf))
+    host = HostBags.from_files(ffiles, cfiles, K, pin=False)
+    assert host.offsets == [0, 50, 57, 90]
+    assert torch.equal(host.feats, torch.cat(feats))
+    assert torch.equal(host.patch_cluster, torch.cat(labels))
+    for b in range(3):
+        lo, hi = host.offsets[b], host.offsets[b + 1]
+        for j in range(K):
+            ids = clusters[b][j]
+            assert host.cluster_sizes[b, j] == len(ids)
+            # rank = position inside the list the reference slices
+            assert host.patch_rank[lo:hi][torch.tensor(ids, dtype=torch.long)].tolist() == list(range(len(ids)))
+    # the window selection driven by (cluster, rank) equals the oracle's slicing of the lists
+    act = torch.rand(1, K, generator=synth.gen(5))
+    for b in range(3):
+        lo, hi = host.offsets[b], host.offsets[b + 1]
+        want = O.select_indices(clusters[b], hi - lo, act[0].numpy(), 16)
+        starts, stops = O.select_windows([len(c) for c in clusters[b]], hi - lo, act[0].numpy(), 16)
+        pc, pr = host.patch_cluster[lo:hi].long(), host.patch_rank[lo:hi].long()
+        keep = (pr >= torch.as_tensor(starts)[pc]) & (pr < torch.as_tensor(stops)[pc])
+        assert torch.nonzero(keep).flatten().tolist()[:16] == [int(i) for i in want]
+    with pytest.raises(ValueError):
+        load_slide(ffiles[0], cfiles[1], K)                     # 7 labels for 50 patches
