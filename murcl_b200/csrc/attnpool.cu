@@ -511,13 +511,13 @@ int murcl_attnpool_fwd(const void* h, const void* wab, const float* bab, const f
       if (rc != MURCL_OK) return rc;
     }
     const bool bstat = nc == ap::PASS_N;                                 // one column pass: the weights stay in shared memory
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (const int slot = configured.pending(); slot >= 0) {
       MURCL_CUDA(cudaFuncSetAttribute(ap::attnpool_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ap::Cfg<true>::SMEM_BYTES));
       MURCL_CUDA(cudaFuncSetAttribute(ap::attnpool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ap::Cfg<false>::SMEM_BYTES));
-      configured = true;
+      configured.mark(slot);
     }
     ap::Params prm{};
     prm.n_rows = n_rows; prm.L = L; prm.NC = nc; prm.D = D; prm.gated = gated;

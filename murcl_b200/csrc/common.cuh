@@ -46,6 +46,20 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 int sm_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: one flag per device ordinal, so that a
+// process driving several GPUs (nn.DataParallel-style) configures the kernel on each of them.
+struct PerDeviceOnce {
+  std::atomic<bool> done[64];
+  PerDeviceOnce() { for (auto& d : done) d.store(false); }
+  // returns the device slot to configure (>= 0) when the current device has not been configured yet, else -1
+  int pending() const {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;   // unknown ordinal: always (re)configure
+    return done[dev].load(std::memory_order_acquire) ? -1 : dev;
+  }
+  void mark(int dev) { if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release); }
+};
+
 // ---- storage type helpers -----------------------------------------------------------------
 template <typename T>
 struct Store;

@@ -642,14 +642,14 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
                   cudaStream_t st) {
   using C = Cfg<BN, EPI, CG, (int)sizeof(TOUT), BSTAT>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, TOUT, CG, BSTAT>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (const int slot = configured.pending(); slot >= 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
       return MURCL_ECUDA;
     }
-    configured = true;
+    configured.mark(slot);
   }
   static int debug = -1;
   if (debug < 0) {

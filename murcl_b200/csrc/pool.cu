@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(256) attn_score_bwd_kernel(T* __restrict__ uv,
             const float gw = g * ww[j];
             const float ua = u[j] * iq, va = v[j] * iq;
             part[i][j] = fmaf(g, u[j] * v[j], part[i][j]);
-            oa[j] = (u[j] != 0.f) ? gw * v[j] * q * (1.f - ua * ua) : 0.f;
-            ob[j] = (v[j] != 0.f) ? gw * u[j] * q * va * (1.f - va) : 0.f;
+            oa[j] = (q == 1.f || u[j] != 0.f) ? gw * v[j] * q * (1.f - ua * ua) : 0.f;
+            ob[j] = (q == 1.f || v[j] != 0.f) ? gw * u[j] * q * va * (1.f - va) : 0.f;
             csb[i][j] += ob[j];
           }
           store4(r + D + d, make_float4(ob[0], ob[1], ob[2], ob[3]));
@@ -441,8 +441,8 @@ __global__ void __launch_bounds__(256) attn_score_bwd_generic_kernel(T* __restri
       const float v = Store<T>::load(r + D + d);
       const float ua = u * iq, va = v * iq;
       atomicAdd(&dwc[d], g * u * v);
-      Store<T>::store(r + d, u != 0.f ? gw * v * q * (1.f - ua * ua) : 0.f);
-      Store<T>::store(r + D + d, v != 0.f ? gw * u * q * va * (1.f - va) : 0.f);
+      Store<T>::store(r + d, (q == 1.f || u != 0.f) ? gw * v * q * (1.f - ua * ua) : 0.f);
+      Store<T>::store(r + D + d, (q == 1.f || v != 0.f) ? gw * u * q * va * (1.f - va) : 0.f);
     } else {
       const float ua = u * iq;
       atomicAdd(&dwc[d], g * u);

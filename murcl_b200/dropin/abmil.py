@@ -45,6 +45,7 @@ class ABMIL(nn.Module):
                                                self.attention[0].weight, self.attention[0].bias,
                                                self.attention[2].weight, self.attention[2].bias, None, None, enc)
         out = ops.linear(M, self.decoder[0].weight, self.decoder[0].bias, ops.ACT_RELU, self._meta(rows)["dtype"])
+        self.last_attention = p             # [n_rows] pooling weights incl. the 1/sqrt(N) post-scale (abmil.py:40-41)
         return out, p
 
     def bag_forward(self, bag):

@@ -154,6 +154,7 @@ class CLAM_SB(nn.Module):
             inst_b = torch.stack([m.bias for m in self.instance_classifiers], 0)
         M, p, s, inst_loss, preds = ops.mil_aggregate(rows.rows, rows.offsets, rows.row_seg, meta, wab, bab, wc, bc,
                                                       inst_w, inst_b, enc)
+        self.last_attention = p             # [n_rows] post-softmax attention of all bags of the call, CSR order
         results = [dict() for _ in range(rows.B)]
         if instance_eval:
             plan = meta["inst"]

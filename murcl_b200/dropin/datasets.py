@@ -1,6 +1,7 @@
 """``get_feats`` and ``mixup`` of utils/datasets.py:263-308 on the CSR packer kernels."""
 from __future__ import annotations
 
+import weakref
 from collections import OrderedDict
 from typing import List, Tuple, Union
 
@@ -9,22 +10,24 @@ import torch
 from ..csr import BagStore, gather_rows_padded
 
 _store_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
-_STORE_CACHE_SIZE = 4
+_STORE_CACHE_SIZE = 1      # the reference trainer builds fresh tensors every batch: only the current batch is ever hit
 
 
 def bag_store_for(feat_list: List[torch.Tensor], clusters_list: List[List[List[int]]], device) -> BagStore:
     """The CSR store of a batch, built once and reused by the 2 x T ``get_feats`` calls that
-    train_MuRCL.py:237,266 makes on the same ``feat_list`` / ``cluster_list`` objects."""
-    key = (tuple(id(f) for f in feat_list), tuple(id(c) for c in clusters_list), str(device))
+    train_MuRCL.py:237,266 makes on the same ``feat_list`` / ``cluster_list`` objects.
+
+    One entry.  The feature tensors are held by WEAK references (the cache never keeps a batch of features alive
+    on the GPU) and the key carries their autograd version counters, so an in-place edit or a recycled ``id()``
+    rebuilds the store instead of returning a stale one."""
+    key = (tuple((id(f), f._version, f.data_ptr()) for f in feat_list), tuple(id(c) for c in clusters_list), str(device))
     hit = _store_cache.get(key)
-    if hit is not None:
-        _store_cache.move_to_end(key)
+    if hit is not None and all(r() is f for r, f in zip(hit[1], feat_list)):
         return hit[0]
     store = BagStore.from_cluster_lists(feat_list, clusters_list, device)
-    # keep the source objects alive so their ids cannot be recycled while the entry exists
-    _store_cache[key] = (store, list(feat_list), list(clusters_list))
-    while len(_store_cache) > _STORE_CACHE_SIZE:
-        _store_cache.popitem(last=False)
+    _store_cache.clear()
+    # the cluster lists are small host objects: a strong reference keeps their ids from being recycled
+    _store_cache[key] = (store, [weakref.ref(f) for f in feat_list], list(clusters_list))
     return store
 
 

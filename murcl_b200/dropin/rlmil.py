@@ -85,9 +85,10 @@ class ActorCritic(nn.Module):
                 action = mean
         return action.detach()
 
-    def act_views(self, states, memories, restart_batch=False, training=True):
+    def act_views(self, states, memories, restart_batch=False, training=True, eps=None):
         """``act`` for several independent views in one batched pass (same math per view: rows do not interact).
-        Used by the fused pre-training step; halves the number of small launches."""
+        Used by the fused pre-training step; halves the number of small launches.  ``eps`` optionally supplies the
+        standard-normal draws, one ``[B, K]`` tensor per view (parity tests)."""
         n, b = len(states), states[0].size(0)
         with torch.no_grad():
             if restart_batch:
@@ -99,7 +100,10 @@ class ActorCritic(nn.Module):
             h_prev = torch.cat([m.hidden[-1][0] for m in memories], 0).contiguous()
             h = ops.gru_step(enc, h_prev, *_gru_params(self.gru), dtype=_dtype(self))
             logits = ops.linear(h, self.actor[0].weight, self.actor[0].bias)
-            eps = torch.randn(logits.shape, device=logits.device, dtype=torch.float32)
+            if eps is None:
+                eps = torch.randn(logits.shape, device=logits.device, dtype=torch.float32)
+            else:
+                eps = torch.cat([e.to(logits.device, torch.float32) for e in eps], 0)
             action, logprob, mean = ops.actor_head(logits, eps, self.action_std)
             outs = []
             for v, m in enumerate(memories):
@@ -153,9 +157,9 @@ class PPO:
     def select_action(self, state, memory, restart_batch=False, training=True):
         return self.policy_old.act(state, memory, restart_batch, training)
 
-    def select_action_views(self, states, memories, restart_batch=False, training=True):
+    def select_action_views(self, states, memories, restart_batch=False, training=True, eps=None):
         """``select_action`` for the two views of a patch-step (train_MuRCL.py:262-265) in one batched pass."""
-        return self.policy_old.act_views(states, memories, restart_batch, training)
+        return self.policy_old.act_views(states, memories, restart_batch, training, eps=eps)
 
     def update(self, memory):
         """PPO-clip update (rlmil.py:152-184): discounted returns normalised over the whole rollout, K epochs of the

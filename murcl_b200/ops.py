@@ -41,6 +41,10 @@ def _chk(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
         raise MurclError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise MurclError(f"{name}: expected a contiguous tensor")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's stream: a tensor of another GPU would be dereferenced there
+        raise MurclError(f"{name}: tensor lives on {t.device} but the current CUDA device is {torch.cuda.current_device()} "
+                         f"(wrap the call in `with torch.cuda.device(t.device)`)")
     return t
 
 
@@ -101,18 +105,32 @@ def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return dst
 
 
+_weight_epoch = 0
+
+
+def invalidate_weight_cache() -> None:
+    """Drop every cached storage-dtype weight copy.  Needed only after a mutation that autograd cannot see:
+    ``param.data.mul_(...)``-style edits do not bump ``param._version``.  Optimiser steps, ``load_state_dict``,
+    ``nn.init.*_`` and ``module.to(device)`` are detected without this call."""
+    global _weight_epoch
+    _weight_epoch += 1
+
+
 def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """Storage-dtype copy of a parameter.  The copy is cached ON the parameter object together with its
-    autograd version counter, so weights are cast once per optimiser update, not once per forward."""
+    """Storage-dtype copy of a parameter.  The copy is cached ON the parameter object and keyed by
+    ``(data_ptr, device, _version, dtype, shape, epoch)``: weights are cast once per optimiser update, not once per
+    forward; a device move / ``param.data = ...`` (new storage) or any versioned in-place update misses the cache.
+    Un-versioned ``.data`` edits need ``invalidate_weight_cache()``."""
     if w.dtype == dtype:
         d = w.detach()
         return d if d.is_contiguous() else d.contiguous()
+    key = (w.data_ptr(), w.device, w._version, dtype, tuple(w.shape), _weight_epoch)
     hit = getattr(w, "_murcl_cast", None)
-    if hit is not None and hit[0] == w._version and hit[1] == dtype and hit[2].shape == w.shape:
-        return hit[2]
+    if hit is not None and hit[0] == key:
+        return hit[1]
     out = cast(w.detach().contiguous(), dtype)
     try:
-        w._murcl_cast = (w._version, dtype, out)
+        w._murcl_cast = (key, out)
     except AttributeError:
         pass
     return out

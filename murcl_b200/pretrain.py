@@ -46,10 +46,10 @@ def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
     """``model(x_views)`` of train_MuRCL.py:242,271 -> ``(outputs, detached states)``.  Bags are independent, so
     when the model is the CL wrapper all views go through its encoder in ONE batched call (half the launches,
     twice the rows per GEMM) and are split afterwards; any other model is called with the list of views."""
+    from .dropin.cl import CL
     B = x_all.shape[0] // n_views
-    enc = getattr(model, "encoder", None)
-    if enc is not None:
-        out = enc(x_all)[0]
+    if isinstance(model, CL):            # not duck-typed on `.encoder`: the drop-in ABMIL has an attribute of that name too
+        out = model.encoder(x_all)[0]
         outs = [out[v * B:(v + 1) * B] for v in range(n_views)]
         return outs, [o.detach() for o in outs]
     return model([x_all[v * B:(v + 1) * B] for v in range(n_views)])
@@ -57,47 +57,62 @@ def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
 
 def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_size: int = 1024, alpha: float = 0.9,
                   stage: int = 1, ppo=None, memories=None, draws: Optional[Sequence[Draw]] = None,
-                  precision: Optional[str] = None, backward: bool = True):
-    """Returns ``(loss, per-step losses)``.  ``stage`` follows train_MuRCL.py: 1 = random actions, 3 = PPO actor
-    chooses the actions of patch-steps >= 1 (the actor is not updated); stage 2 (actor only) is not part of the
-    MIL fwd+bwd hot path.  ``draws`` injects the random numbers (parity tests)."""
-    if stage not in (1, 3):
-        raise NotImplementedError("pretrain_step implements train stages 1 and 3")
+                  precision: Optional[str] = None, backward: bool = True, eps=None, keep_memory: bool = False):
+    """Returns ``(loss, per-step losses)``.  ``stage`` follows train_MuRCL.py: 1 = random actions; 3 = the PPO actor
+    chooses the actions of patch-steps >= 1 (the actor is not updated, :292-295); 2 = the same rollout under ``no_grad``
+    with the MIL model frozen, then ``ppo.update(m)`` for each view's memory instead of the optimiser step (:244-247,
+    :296-298).  ``draws`` injects the random numbers (parity tests): ``draws[t] = (actions | None, lams, perms)`` -
+    ``None`` actions at ``t >= 1`` in stages 2/3 mean "ask the actor", with ``eps[t]`` (one ``[B, K]`` tensor per view) as
+    its Gaussian draws.  ``keep_memory`` leaves the rollout in ``memories`` (the reference clears it, :301-302)."""
+    if stage not in (1, 2, 3):
+        raise ValueError("train_stage must be 1, 2 or 3")
+    if stage != 1 and (ppo is None or memories is None):
+        raise ValueError("stages 2 and 3 need the PPO object and one Memory per view")
     B, K, dev = store.num_bags, store.K, store.device
     dt = ops.storage_dtype(precision or ops.default_precision())
     slot_bag = torch.arange(B, dtype=torch.int32, device=dev).repeat(2)
     losses = []
     states = None
     sim_last = None
-    for t in range(T):
-        if draws is not None:
-            draw = draws[t]
-        else:
-            actions = None
-            if stage == 3 and t >= 1:
+    grad_mode = torch.no_grad() if stage == 2 else torch.enable_grad()
+    with grad_mode:
+        for t in range(T):
+            actions = lams = perms = None
+            if draws is not None:
+                actions, lams, perms = draws[t]
+            if actions is None and stage != 1 and t >= 1:
+                e = None if eps is None else eps[t]
                 if hasattr(ppo, "select_action_views"):
-                    actions = ppo.select_action_views(states, memories, restart_batch=(t == 1))
+                    actions = ppo.select_action_views(states, memories, restart_batch=(t == 1), eps=e)
                 else:
                     actions = [ppo.select_action(s, m, restart_batch=(t == 1)) for s, m in zip(states, memories)]
-            draw = draw_patch_step(B, K, alpha, dev, actions)
-        x_all = pack_views(store, draw, feat_size, dt, slot_bag)
-        outputs, states = encode_views(model, x_all)
-        if hasattr(fc, "forward_views"):
-            outputs = fc.forward_views(outputs, restart=(t == 0))
-        else:
-            outputs = [fc(o, restart=(t == 0)) for o in outputs]
-        loss = criterion(outputs[0], outputs[1])
-        losses.append(loss)
-        sim = criterion.last_cosine.view(1, -1)          # by-product of the loss kernel (train_MuRCL.py:253,282)
-        if t >= 1 and memories is not None:
-            reward = sim_last - sim
-            for m in memories:
-                m.rewards.append(reward)
-        sim_last = sim
+            if lams is None:
+                draw = draw_patch_step(B, K, alpha, dev, actions)
+            else:
+                if actions is None:
+                    actions = [torch.rand((B, K), device=dev) for _ in range(2)]
+                draw = (actions, lams, perms)
+            x_all = pack_views(store, draw, feat_size, dt, slot_bag)
+            outputs, states = encode_views(model, x_all)
+            if hasattr(fc, "forward_views"):
+                outputs = fc.forward_views(outputs, restart=(t == 0))
+            else:
+                outputs = [fc(o, restart=(t == 0)) for o in outputs]
+            loss = criterion(outputs[0], outputs[1])
+            losses.append(loss)
+            sim = criterion.last_cosine.view(1, -1)          # by-product of the loss kernel (train_MuRCL.py:253,282)
+            if t >= 1 and memories is not None:
+                reward = sim_last - sim
+                for m in memories:
+                    m.rewards.append(reward)
+            sim_last = sim
     total = sum(losses) / T
-    if backward:
+    if stage == 2:
+        for m in memories:
+            ppo.update(m)
+    elif backward:
         total.backward()
-    if memories is not None:
+    if memories is not None and not keep_memory:
         for m in memories:
             m.clear_memory()
     return total.detach(), [l.detach() for l in losses]

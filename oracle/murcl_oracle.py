@@ -127,6 +127,17 @@ def abmil_bag(x: Tensor, sd: StateDict, masks: Optional[Dict[str, Tensor]] = Non
     return F.relu(F.linear(m.unsqueeze(0), sd["decoder.0.weight"], sd["decoder.0.bias"]))
 
 
+def abmil_attention(x: Tensor, sd: StateDict) -> Tensor:
+    """The attention weights ABMIL pools with (models/abmil.py:37-41): softmax over N of the tanh-attention scores,
+    then / sqrt(N).  x [N, D_in] -> [N]."""
+    h = x
+    for i in (0, 3, 6):
+        h = F.relu(F.linear(h, sd[f"encoder.{i}.weight"], sd[f"encoder.{i}.bias"]))
+    u = torch.tanh(F.linear(h, sd["attention.0.weight"], sd["attention.0.bias"]))
+    s = F.linear(u, sd["attention.2.weight"], sd["attention.2.bias"]).squeeze(-1)
+    return torch.softmax(s, dim=0) / math.sqrt(h.shape[0])
+
+
 def abmil_forward(bags: Sequence[Tensor], sd: StateDict) -> Tensor:
     """models/abmil.py:47-62: per-bag loop, concatenated -> [B, L]."""
     return torch.cat([abmil_bag(b.reshape(-1, b.shape[-1]), sd) for b in bags], 0)
@@ -180,11 +191,14 @@ def clam_instance_loss(p: Tensor, h: Tensor, sd: StateDict, label: int, n_classe
 def clam_sb_bag(x: Tensor, sd: StateDict, *, gate: bool = True, dropout_layers: bool = False,
                 label: Optional[int] = None, instance_eval: bool = False, n_classes: int = 2,
                 k_sample: int = 8, subtyping: bool = False, attention_only: bool = False,
-                masks: Optional[Dict[str, Tensor]] = None):
+                masks: Optional[Dict[str, Tensor]] = None, p_select: Optional[Tensor] = None):
     """One bag through CLAM_SB in eval mode (models/clam.py:134-181).  ``dropout_layers``
     only shifts the index of the attention sub-module in the Sequential (:69-77): it is
     ``attention_net.3`` when the model was built with dropout=True and ``.2`` otherwise.
-    Returns (M [1,512], results dict) or raw scores [1,N] when ``attention_only`` (:141-142)."""
+    Returns (M [1,512], results dict) or raw scores [1,N] when ``attention_only`` (:141-142).  ``p_select`` (tests of
+    the reduced-precision mode) replaces the attention weights the instance loss RANKS by - the top-k indices carry no
+    gradient (:107-110) - so that both sides evaluate the loss on the same instances; ``results["attention"]`` holds
+    this bag's own post-softmax weights."""
     att = "attention_net.3" if dropout_layers else "attention_net.2"
     h = F.relu(F.linear(x, sd["attention_net.0.weight"], sd["attention_net.0.bias"]))
     if masks is not None:                                   # train mode: Dropout(0.25) after the fc ReLU (clam.py:70-71)
@@ -193,10 +207,11 @@ def clam_sb_bag(x: Tensor, sd: StateDict, *, gate: bool = True, dropout_layers: 
     if attention_only:
         return s.unsqueeze(0)
     m, p = softmax_pool(s, h)
-    results = {}
+    results = {"attention": p.detach()}
     if instance_eval:
-        loss, preds, targets = clam_instance_loss(p.detach(), h, sd, int(label), n_classes, k_sample, subtyping)
-        results = {"instance_loss": loss, "inst_preds": preds, "inst_labels": targets}
+        rank_by = p.detach() if p_select is None else p_select
+        loss, preds, targets = clam_instance_loss(rank_by, h, sd, int(label), n_classes, k_sample, subtyping)
+        results.update({"instance_loss": loss, "inst_preds": preds, "inst_labels": targets})
     return m.unsqueeze(0), results
 
 
@@ -280,6 +295,74 @@ def actor_act(state: Tensor, h_prev: Optional[Tensor], sd: StateDict, action_std
     return action, logprob, h, mean
 
 
+def actor_evaluate(states: Tensor, actions: Tensor, sd: StateDict, action_std: float):
+    """ActorCritic.evaluate with policy_conv=False (models/rlmil.py:99-127): the stored states ``[T, B, ...]`` go
+    through the state MLP (:109), one ``nn.GRU`` pass over the T steps from a ZERO hidden state (:112), the sigmoid
+    actor head (:115) and the critic (:124); the action log-probability and the entropy are those of
+    ``MultivariateNormal(mean, scale_tril=diag(action_std))`` (:117-122).  Returns (logprob, value, entropy), each [T, B]."""
+    T, B = states.shape[0], states.shape[1]
+    s = states.flatten(2).reshape(T * B, -1)
+    s = F.relu(F.linear(s, sd["state_encoder.0.weight"], sd["state_encoder.0.bias"]))
+    s = F.relu(F.linear(s, sd["state_encoder.2.weight"], sd["state_encoder.2.bias"])).reshape(T, B, -1)
+    h = s.new_zeros(B, sd["gru.weight_hh_l0"].shape[1])
+    feats = []
+    for t in range(T):
+        h = gru_cell(s[t], h, sd["gru.weight_ih_l0"], sd["gru.weight_hh_l0"], sd["gru.bias_ih_l0"], sd["gru.bias_hh_l0"])
+        feats.append(h)
+    feat = torch.cat(feats, 0)
+    mean = torch.sigmoid(F.linear(feat, sd["actor.0.weight"], sd["actor.0.bias"]))
+    value = F.linear(feat, sd["critic.0.weight"], sd["critic.0.bias"])
+    k = mean.shape[1]
+    a = actions.reshape(T * B, -1)
+    logprob = (-0.5 * (((a - mean) / action_std) ** 2).sum(1)
+               - k * math.log(action_std) - 0.5 * k * math.log(2 * math.pi))
+    entropy = torch.full_like(logprob, 0.5 * k * (1.0 + math.log(2 * math.pi)) + k * math.log(action_std))
+    return logprob.view(T, B), value.view(T, B), entropy.view(T, B)
+
+
+def ppo_returns(rewards: Sequence[Tensor], gamma: float) -> Tensor:
+    """models/rlmil.py:153-162: discounted return per patch-step (each reward is ``[1, B]``, train_MuRCL.py:283-288),
+    concatenated to ``[T, B]`` and normalised with the mean / UNBIASED std over all T*B entries (+1e-5)."""
+    out, running = [], 0
+    for r in reversed(list(rewards)):
+        running = r + gamma * running
+        out.insert(0, running)
+    ret = torch.cat(out, 0)
+    return (ret - ret.mean()) / (ret.std() + 1e-5)
+
+
+def ppo_loss(sd: StateDict, states: Tensor, actions: Tensor, old_logprobs: Tensor, returns: Tensor, *,
+             action_std: float, eps_clip: float) -> Tensor:
+    """One epoch's scalar objective (models/rlmil.py:169-181): mean over [T, B] of
+    ``-min(ratio A, clip(ratio) A) + 0.5 * MSE(value, returns) - 0.01 * entropy`` with ``A = returns - value.detach()``;
+    the MSE is already a mean over all entries (a scalar broadcast into the sum)."""
+    logprob, value, entropy = actor_evaluate(states, actions, sd, action_std)
+    ratio = torch.exp(logprob - old_logprobs.detach())
+    adv = returns - value.detach()
+    surr = torch.min(ratio * adv, torch.clamp(ratio, 1 - eps_clip, 1 + eps_clip) * adv)
+    return (-surr + 0.5 * F.mse_loss(value, returns) - 0.01 * entropy).mean()
+
+
+def ppo_update(sd: StateDict, states: Tensor, actions: Tensor, old_logprobs: Tensor, rewards: Sequence[Tensor], *,
+               action_std: float, lr: float = 0.0003, betas=(0.9, 0.999), gamma: float = 0.7, K_epochs: int = 1,
+               eps_clip: float = 0.2):
+    """PPO.update (models/rlmil.py:152-184): K_epochs Adam steps (``torch.optim.Adam(lr, betas)``, :141) on ``ppo_loss``.
+    Returns (new state dict, gradients of the FIRST epoch, per-epoch losses)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=lr, betas=betas)
+    returns = ppo_returns(rewards, gamma)
+    first, losses = None, []
+    for _ in range(K_epochs):
+        loss = ppo_loss(params, states, actions, old_logprobs, returns, action_std=action_std, eps_clip=eps_clip)
+        opt.zero_grad()
+        loss.backward()
+        if first is None:
+            first = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+        losses.append(loss.detach())
+        opt.step()
+    return {k: p.detach() for k, p in params.items()}, first, losses
+
+
 # --------------------------------------------------------------------------------------
 # 5. The pre-training step (train_MuRCL.py:235-298), used as the CPU baseline workload
 # --------------------------------------------------------------------------------------
@@ -323,3 +406,57 @@ def pretrain_step(feat_list, clusters_list, sd_model: StateDict, sd_fc: StateDic
         loss.backward()
         grads = {n: p.grad for n, p in params.items()}
     return loss.detach(), grads
+
+
+def pretrain_step_stage3(feat_list, clusters_list, sd_model: StateDict, sd_fc: StateDict, sd_actor: StateDict, *,
+                         first_actions: Sequence[Tensor], lams, perms, eps, action_std: float, T: int,
+                         feat_size: int = 1024, temperature: float = 1.0, backward: bool = True):
+    """Stage-3 semantics of train_MuRCL.py:235-298 for ABMIL with every random draw injected: ``first_actions`` (2 x
+    [B, K]) are the uniform actions of patch-step 0 (:235); ``lams[t][v]`` / ``perms[t][v]`` the mixup draws (:239,268);
+    ``eps[t][v]`` (t >= 1) the actor's standard-normal draws.  From patch-step 1 on each view's actions come from
+    ``actor_act`` on the DETACHED bag embedding of the previous patch-step (:260-265; cl.py:15), the actor's GRU state
+    restarting from zeros at patch-step 1 (``restart_batch``) and carried per view afterwards.  Rewards are
+    ``similarity_last - similarity`` (:282-283).  Returns a dict: loss, losses, grads, actions, logprobs, rewards,
+    states (the rollout a stage-2 ``ppo_update`` would consume)."""
+    params = {n: p.detach().clone().requires_grad_(backward) for n, p in {**{"m." + a: v for a, v in sd_model.items()},
+                                                                              **{"f." + a: v for a, v in sd_fc.items()}}.items()}
+    sm = {n[2:]: p for n, p in params.items() if n.startswith("m.")}
+    sf = {n[2:]: p for n, p in params.items() if n.startswith("f.")}
+    hidden, actor_h = None, [None, None]
+    states = None
+    losses, rewards, actions_log = [], [], []
+    roll = [dict(states=[], actions=[], logprobs=[]) for _ in range(2)]
+    sim_last = None
+    for t in range(T):
+        if t == 0:
+            acts = [a.float() for a in first_actions]
+        else:
+            acts = []
+            for v in range(2):
+                a, lp, h, _mean = actor_act(states[v], None if t == 1 else actor_h[v], sd_actor, action_std, eps[t][v])
+                actor_h[v] = h
+                roll[v]["states"].append(states[v]); roll[v]["actions"].append(a); roll[v]["logprobs"].append(lp)
+                acts.append(a)
+        actions_log.append(acts)
+        outs, new_states = [], []
+        for v in range(2):
+            x, _ = get_feats(feat_list, clusters_list, acts[v], feat_size)
+            x = mixup_apply(x, lams[t][v], perms[t][v])
+            pooled = abmil_forward(list(x), sm)
+            new_states.append(pooled.detach())
+            z, hidden = full_layer_step(pooled, None if t == 0 else hidden, sf)
+            outs.append(z)
+        states = new_states
+        losses.append(nt_xent(outs[0], outs[1], temperature))
+        sim = pair_cosine(outs[0], outs[1]).view(1, -1)
+        if t >= 1:
+            rewards.append((sim_last - sim).detach())
+        sim_last = sim
+    loss = sum(losses) / T
+    grads = None
+    if backward:
+        loss.backward()
+        grads = {n: p.grad for n, p in params.items()}
+    return dict(loss=loss.detach(), losses=[l.detach() for l in losses], grads=grads, actions=actions_log,
+                logprobs=[torch.stack(r["logprobs"], 0) for r in roll], rewards=rewards,
+                states=[torch.stack(r["states"], 0) for r in roll], roll_actions=[torch.stack(r["actions"], 0) for r in roll])

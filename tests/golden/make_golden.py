@@ -265,6 +265,66 @@ def golden_actor():
     save("actor", **arrays)
 
 
+def golden_ppo_update():
+    """PPO.evaluate / PPO.update (models/rlmil.py:99-127,152-184) on a 4-step rollout produced by the reference's own
+    ``select_action`` with recorded Gaussian draws and fixed rewards: the evaluate outputs, the first epoch's
+    gradients and the weights after K_epochs=3 Adam steps."""
+    import torch.distributions.multivariate_normal as mvn
+    sdim, hid, k, b, std, T = 32, 24, 6, 7, 0.5, 4
+    sd = synth.actor_state(sdim, hid, k, seed=101)
+    ppo = rlmil.PPO(sdim, sdim, hid, False, action_std=std, lr=3e-4, gamma=0.1, K_epochs=3, action_size=k)
+    ppo.policy.load_state_dict(sd, strict=True)
+    ppo.policy_old.load_state_dict(sd, strict=True)
+    eps_log = []
+    orig = mvn._standard_normal
+
+    def recording(shape, dtype, device):
+        e = orig(shape, dtype, device)
+        eps_log.append(e.clone())
+        return e
+
+    mvn._standard_normal = recording
+    mem = rlmil.Memory()
+    g = synth.gen(102)
+    arrays = dict(dims=np.asarray([sdim, hid, k, b, T]), std=std, lr=3e-4, gamma=0.1, K_epochs=3, eps_clip=0.2, seed_actor=101)
+    torch.manual_seed(103)
+    for t in range(T):
+        state = torch.randn(b, sdim, generator=g)
+        ppo.select_action(state, mem, restart_batch=(t == 0))
+        arrays[f"state{t}"], arrays[f"eps{t}"] = npy(state), npy(eps_log[-1])
+        arrays[f"action{t}"], arrays[f"logprob{t}"] = npy(mem.actions[-1]), npy(mem.logprobs[-1])
+        reward = 0.3 * torch.randn(1, b, generator=g)           # shape of train_MuRCL.py:283 (sim_last - sim, [1, B])
+        mem.rewards.append(reward)
+        arrays[f"reward{t}"] = npy(reward)
+    mvn._standard_normal = orig
+    states, actions = torch.stack(mem.states, 0), torch.stack(mem.actions, 0)
+    lp, val, ent = ppo.policy.evaluate(states, actions)
+    arrays["eval_logprob"], arrays["eval_value"], arrays["eval_entropy"] = npy(lp), npy(val), npy(ent)
+    # first epoch's gradient = what update() computes before its first Adam step (same expressions, rlmil.py:153-181)
+    disc, run = [], 0
+    for r in reversed(mem.rewards):
+        run = r + ppo.gamma * run
+        disc.insert(0, run)
+    ret = torch.cat(disc, 0)
+    ret = (ret - ret.mean()) / (ret.std() + 1e-5)
+    arrays["returns"] = npy(ret)
+    ratios = torch.exp(lp - torch.stack(mem.logprobs, 0).detach())
+    adv = ret - val.detach()
+    loss = -torch.min(ratios * adv, torch.clamp(ratios, 0.8, 1.2) * adv) + 0.5 * ppo.MseLoss(val, ret) - 0.01 * ent
+    ppo.policy.zero_grad()
+    loss.mean().backward()
+    arrays["loss0"] = npy(loss.mean())
+    for n, p in ppo.policy.named_parameters():
+        arrays[f"grad.{n}"] = sample(npy(p.grad))
+    ppo.policy.zero_grad()
+    ppo.update(mem)
+    for n, p in ppo.policy.named_parameters():
+        arrays[f"new.{n}"] = sample(npy(p))
+        arrays[f"delta.{n}"] = sample(npy(p.detach() - sd[n]))
+    assert all(torch.equal(a, b_) for a, b_ in zip(ppo.policy.state_dict().values(), ppo.policy_old.state_dict().values()))
+    save("ppo_update", **arrays)
+
+
 def golden_pretrain_step():
     """A miniature stage-1 optimiser step assembled exactly as train_MuRCL.py:235-294 does."""
     from models import cl
@@ -299,16 +359,90 @@ def golden_pretrain_step():
     save("pretrain_step", **arrays)
 
 
+def golden_stage3_step():
+    """A miniature stage-3 optimiser step (train_MuRCL.py:235-298 with ``train_stage == 3``: the PPO actor chooses the
+    windows of patch-steps >= 1 from the detached bag embeddings; it is not updated), followed on the SAME rollout by
+    what stage 2 does instead of the optimiser step (``ppo.update(m)`` for both memories, :296-298).  All random draws
+    (first actions, mixup lambda / permutation, the actor's Gaussian noise) are recorded."""
+    import torch.distributions.multivariate_normal as mvn
+    from models import cl
+    b, k, d, fs, T, alpha, tau, std = 6, 4, 16, 32, 3, 0.9, 1.0, 0.5
+    L, D, hid, proj, phid = 32, 16, 24, 8, 20
+    sizes = [90, 20, 45, 33, 150, 64]
+    feats, clusters, _ = synth.make_bags(sizes, d, k, seed=111)
+    sd_m = synth.abmil_state(d, L, D, proj, seed=112)
+    sd_f = synth.full_layer_state(L, hid, proj, seed=113)
+    sd_a = synth.actor_state(L, phid, k, seed=114)
+    enc = abmil.ABMIL(d, L=L, D=D, dim_out=proj)
+    enc.load_state_dict(sd_m)
+    model = cl.CL(enc, projection_dim=proj, n_features=L)
+    fc = rlmil.Full_layer(L, hid, True, proj)
+    fc.load_state_dict(sd_f)
+    ppo = rlmil.PPO(d, L, phid, False, action_std=std, lr=1e-3, gamma=0.1, K_epochs=2, action_size=k)
+    ppo.policy.load_state_dict(sd_a)
+    ppo.policy_old.load_state_dict(sd_a)
+    crit = ref_losses.NT_Xent(b, tau)
+    feat_list = [f.unsqueeze(0) for f in feats]
+    memory_list = [rlmil.Memory(), rlmil.Memory()]
+    eps_log = []
+    orig = mvn._standard_normal
+
+    def recording(shape, dtype, device):
+        e = orig(shape, dtype, device)
+        eps_log.append(e.clone())
+        return e
+
+    mvn._standard_normal = recording
+    arrays = dict(cfg=np.asarray([b, k, d, fs, T, L, D, hid, proj, phid]), sizes=np.asarray(sizes), alpha=alpha, tau=tau,
+                  std=std, ppo_lr=1e-3, ppo_gamma=0.1, ppo_K_epochs=2)
+    torch.manual_seed(115)
+    loss_list, states = [], None
+    similarity_last = None
+    for t in range(T):
+        if t == 0:
+            acts = [torch.rand((b, k)) for _ in range(2)]
+        else:
+            acts = [ppo.select_action(s, m, restart_batch=(t == 1)) for s, m in zip(states, memory_list)]
+            arrays[f"eps{t}_0"], arrays[f"eps{t}_1"] = npy(eps_log[-2]), npy(eps_log[-1])
+        xv = [ref_datasets.get_feats(feat_list, clusters, action_sequence=a, feat_size=fs) for a in acts]
+        mixed = [ref_datasets.mixup(x, alpha) for x in xv]
+        for v in range(2):
+            arrays[f"act{t}_{v}"], arrays[f"lam{t}_{v}"], arrays[f"perm{t}_{v}"] = npy(acts[v]), npy(mixed[v][1]), npy(mixed[v][2])
+        outs, states = model([m_[0] for m_ in mixed])
+        outs = [fc(o, restart=(t == 0)) for o in outs]
+        loss = crit(outs[0], outs[1])
+        loss_list.append(loss)
+        arrays[f"loss{t}"] = npy(loss)
+        sim = torch.cosine_similarity(outs[0], outs[1]).view(1, -1)
+        if t >= 1:
+            reward = similarity_last - sim
+            arrays[f"reward{t}"] = npy(reward)
+            for m_ in memory_list:
+                m_.rewards.append(reward)
+        similarity_last = sim
+    mvn._standard_normal = orig
+    for v, m_ in enumerate(memory_list):
+        arrays[f"logprobs_{v}"] = npy(torch.stack(m_.logprobs, 0))
+    loss = sum(loss_list) / T
+    loss.backward()
+    arrays["loss"] = npy(loss)
+    arrays.update({f"grad.m.{n}": sample(npy(p.grad)) for n, p in enc.named_parameters() if p.grad is not None})
+    arrays.update({f"grad.f.{n}": sample(npy(p.grad)) for n, p in fc.named_parameters() if p.grad is not None})
+    # stage 2 on the same rollout: PPO update from both memories in turn (train_MuRCL.py:296-298)
+    for m_ in memory_list:
+        m_.rewards = [r.detach() for r in m_.rewards]
+        ppo.update(m_)
+    for n, p in ppo.policy.named_parameters():
+        arrays[f"ppo_delta.{n}"] = sample(npy(p.detach() - sd_a[n]))
+    save("stage3_step", **arrays)
+
+
 if __name__ == "__main__":
     assert REF.exists(), f"reference not found at {REF}"
     print("writing fixtures to", HERE)
-    golden_selection()
-    golden_get_feats()
-    golden_mixup()
-    golden_abmil()
-    golden_clam()
-    golden_dsmil()
-    golden_ntxent()
-    golden_full_layer()
-    golden_actor()
-    golden_pretrain_step()
+    makers = [golden_selection, golden_get_feats, golden_mixup, golden_abmil, golden_clam, golden_dsmil, golden_ntxent,
+              golden_full_layer, golden_actor, golden_ppo_update, golden_pretrain_step, golden_stage3_step]
+    only = set(sys.argv[1:])            # e.g. `make_golden.py golden_ppo_update` regenerates one fixture
+    for fn in makers:
+        if not only or fn.__name__ in only:
+            fn()

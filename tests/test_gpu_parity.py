@@ -13,12 +13,15 @@ import torch
 
 from murcl_b200 import synth
 from oracle import murcl_oracle as O
-from tests.helpers import assert_close, leaf_state, sample
+from tests.helpers import assert_close, assert_close_elementwise, leaf_state, sample
 
 pytestmark = pytest.mark.gpu
 
 FP32_OUT, FP32_GRAD = 1e-5, 1e-4
 BF16_OUT, BF16_GRAD = 2e-2, 6e-2
+# attention weights, EVERY element against its own reference value (floor = the mean weight): fp32 mode sees the
+# summation-order noise of |s| ~ 10 scores (1e-6 * |s| absolute on s = relative on p); bf16 mode the rounding of h / uv
+FP32_ATTN, BF16_ATTN = 2e-5, 5e-2
 DEV = "cuda"
 
 
@@ -232,6 +235,10 @@ def test_abmil_full_size(golden, precision, tol_out, tol_grad):
     (want * cot).sum().backward()
     out, _ = m([f.to(DEV) for f in feats])
     assert_close(out, want, tol_out, "out")
+    with torch.no_grad():
+        p_want = torch.cat([O.abmil_attention(f, sd) for f in feats])
+    assert_close(m.last_attention, p_want, tol_out, "attention weights (max-norm)")
+    assert_close_elementwise(m.last_attention, p_want, FP32_ATTN if precision == "fp32" else BF16_ATTN, "attention weights")
     (out * cot.to(DEV)).sum().backward()
     gr = _grads(m)
     for k, p in sdl.items():
@@ -241,19 +248,33 @@ def test_abmil_full_size(golden, precision, tol_out, tol_grad):
 
 
 def test_large_bag_stress_cfg5():
-    """BASELINE config 5 shape: one bag of N=100k patches x 1024-d, bf16 fused pooling (CLAM_SB small).  The
-    forward is compared with the fp32 oracle at the bf16 tolerance; a ragged second bag rides along."""
+    """BASELINE config 5 shape: one bag of N=100k patches x 1024-d, bf16 fused pooling (CLAM_SB small).  Forward,
+    attention weights and every parameter gradient are compared with the fp32 oracle at the bf16 tolerances; a ragged
+    second bag rides along."""
     from murcl_b200.dropin import clam
     sd = synth.clam_state(1024, "small", True, False, 2, seed=71, peak=3.0)
     m = _load(clam.CLAM_SB(gate=True, size_arg="small", in_dim=1024, precision="bf16"), sd).eval()
     feats, _, _ = synth.make_bags([100000, 2500], 1024, 3, seed=72)
-    with torch.no_grad():
-        want = torch.cat([O.clam_sb_bag(f, sd, gate=True)[0] for f in feats], 0)
+    sdl = leaf_state(sd)
+    torch.set_num_threads(os.cpu_count() or 1)
+    res = [O.clam_sb_bag(f, sdl, gate=True) for f in feats]
+    want = torch.cat([r[0] for r in res], 0)
+    cot = torch.randn(want.shape, generator=synth.gen(73))
+    (want * cot).sum().backward()
     out, _ = m([f.to(DEV) for f in feats])
     assert_close(out, want, BF16_OUT, "100k-patch bag")
-    out.sum().backward()
-    g = m.attention_net[0].weight.grad
-    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+    p_want = torch.cat([r[1]["attention"] for r in res])
+    assert_close(m.last_attention, p_want, BF16_OUT, "attention weights (max-norm)")
+    assert_close_elementwise(m.last_attention, p_want, BF16_ATTN, "attention weights")
+    (out * cot.to(DEV)).sum().backward()
+    gr = _grads(m)
+    n = 0
+    for k, p in sdl.items():
+        if p.grad is None or k.startswith("classifiers") or k.startswith("instance_classifiers"):
+            continue
+        assert_close(gr[k], p.grad, BF16_GRAD, k, floor=1e-1 if _zero_grad_key(k) else 1e-6)
+        n += 1
+    assert n >= 7
 
 
 @pytest.mark.parametrize("gate", [True, False])
@@ -396,7 +417,11 @@ def test_clam_big_and_errors(golden):
 
 @pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", FP32_OUT, FP32_GRAD), ("bf16", BF16_OUT, BF16_GRAD)])
 def test_clam_ragged_cfg2(precision, tol_out, tol_grad):
-    """BASELINE config 2 shape: CLAM_SB small + instance loss on ragged bags x 512-d."""
+    """BASELINE config 2 shape: CLAM_SB small + instance loss on ragged bags x 512-d.  Both modes check the bag vectors,
+    every attention weight, the instance loss and all gradients.  The instance loss ranks instances by attention weight
+    and the ranking carries no gradient (clam.py:107-110); in bf16 mode the bottom-k of near-zero weights legitimately
+    differs from the fp32 ranking, so there the oracle ranks by the weights the device produced (same instances on both
+    sides) - the loss values and gradients are then comparable at the bf16 tolerance."""
     from murcl_b200.dropin import clam
     sd = synth.clam_state(512, "small", True, False, 2, seed=45)
     m = _load(clam.CLAM_SB(gate=True, size_arg="small", k_sample=8, n_classes=2, subtyping=True, in_dim=512,
@@ -404,29 +429,39 @@ def test_clam_ragged_cfg2(precision, tol_out, tol_grad):
     sizes = [2000, 3111, 5000]
     feats, _, _ = synth.make_bags(sizes, 512, 3, seed=46)
     labels = [1, 0, 1]
+    cots = [torch.randn(1, 512, generator=synth.gen(50 + i)) for i in range(3)]
+    out, det, res = m([f.to(DEV) for f in feats], label=torch.tensor(labels), instance_eval=True)
+    p_dev = m.last_attention.detach().cpu()
+    off = np.concatenate([[0], np.cumsum(sizes)])
     sdl = leaf_state(sd)
     tot_ref, wants = 0.0, []
-    cots = [torch.randn(1, 512, generator=synth.gen(50 + i)) for i in range(3)]
     for i, f in enumerate(feats):
-        mm, res = O.clam_sb_bag(f, sdl, gate=True, label=labels[i], instance_eval=True, n_classes=2, k_sample=8, subtyping=True)
-        wants.append((mm, res))
-        tot_ref = tot_ref + (mm * cots[i]).sum() + 0.3 * res["instance_loss"]
+        rank_by = None if precision == "fp32" else p_dev[off[i]:off[i + 1]]
+        mm, r = O.clam_sb_bag(f, sdl, gate=True, label=labels[i], instance_eval=True, n_classes=2, k_sample=8, subtyping=True,
+                              p_select=rank_by)
+        wants.append((mm, r))
+        tot_ref = tot_ref + (mm * cots[i]).sum() + 0.3 * r["instance_loss"]
     tot_ref.backward()
-    out, det, res = m([f.to(DEV) for f in feats], label=torch.tensor(labels), instance_eval=True)
     tot = 0.0
     for i in range(3):
         assert_close(out[i:i + 1], wants[i][0], tol_out, f"M{i}")
+        assert_close(res[i]["instance_loss"], wants[i][1]["instance_loss"], tol_out, f"inst{i}")
+        assert np.array_equal(res[i]["inst_labels"], wants[i][1]["inst_labels"])
         if precision == "fp32":
-            assert_close(res[i]["instance_loss"], wants[i][1]["instance_loss"], tol_out, f"inst{i}")
             assert np.array_equal(res[i]["inst_preds"], wants[i][1]["inst_preds"])
+        p_i = p_dev[off[i]:off[i + 1]]
+        assert_close(p_i, wants[i][1]["attention"], tol_out, f"attention{i} (max-norm)")
+        assert_close_elementwise(p_i, wants[i][1]["attention"], FP32_ATTN if precision == "fp32" else BF16_ATTN, f"attention{i}")
         tot = tot + (out[i:i + 1] * cots[i].to(DEV)).sum() + 0.3 * res[i]["instance_loss"]
     tot.backward()
-    if precision == "fp32":
-        gr = _grads(m)
-        for k, p in sdl.items():
-            if k.startswith("classifiers") or p.grad is None:
-                continue
-            assert_close(gr[k], p.grad, tol_grad, k, floor=1e-1 if _zero_grad_key(k) else 1e-5)
+    gr = _grads(m)
+    n = 0
+    for k, p in sdl.items():
+        if k.startswith("classifiers") or p.grad is None:
+            continue
+        assert_close(gr[k], p.grad, tol_grad, k, floor=1e-1 if _zero_grad_key(k) else 1e-5)
+        n += 1
+    assert n >= 9
 
 
 # ------------------------------------------------------------------------------------------------
@@ -463,19 +498,37 @@ def test_dsmil_golden(golden):
         m(1.0)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", BF16_OUT)])
-def test_dsmil_tcga_shape(precision, tol):
-    """BASELINE config 4 shape: N=10k x 1024-d (V applied after pooling: 1e-6-level reassociation)."""
+@pytest.mark.parametrize("precision,tol,tol_grad", [("fp32", FP32_OUT, FP32_GRAD), ("bf16", BF16_OUT, BF16_GRAD)])
+def test_dsmil_tcga_shape(precision, tol, tol_grad):
+    """BASELINE config 4 shape: N=10k x 1024-d, values and gradients.  V is applied after pooling (a reassociation):
+    the fp32 comparison is made against the fp64 evaluation of the reference formula, which both the reference's fp32
+    result and ours must match to 1e-5."""
     from murcl_b200.dropin import dsmil
     sd = synth.dsmil_state(1024, 2, seed=55)
     m = dsmil.build_dsmil(1024, 2, precision=precision)
     m.load_state_dict(sd, strict=True)
     feats, _, _ = synth.make_bags([10000], 1024, 3, seed=56)
-    with torch.no_grad():
-        want_c, want_b = O.dsmil_bag(feats[0], sd)
-        classes, bag, _ = m(feats[0].unsqueeze(0).to(DEV))
-    assert_close(classes, want_c, tol, "classes")
-    assert_close(bag, want_b, tol, "bag")
+    torch.set_num_threads(os.cpu_count() or 1)
+    sdl = leaf_state(sd, torch.float64)
+    want_c, want_b = O.dsmil_bag(feats[0].double(), sdl)
+    g = synth.gen(57)
+    cot_b, cot_c = torch.randn(want_b.shape, generator=g), torch.randn(want_c.shape, generator=g)
+    ((want_b * cot_b.double()).sum() + (want_c * cot_c.double()).sum()).backward()
+    with torch.no_grad():                                   # the reference's own fp32 evaluation sits within the same bound
+        ref32_c, ref32_b = O.dsmil_bag(feats[0], sd)
+        assert_close(ref32_b, want_b.float(), FP32_OUT, "fp32 reference vs fp64")
+    classes, bag, _ = m(feats[0].unsqueeze(0).to(DEV))
+    assert_close(classes, want_c.float(), tol, "classes")
+    assert_close(bag, want_b.float(), tol, "bag")
+    ((bag * cot_b.to(DEV)).sum() + (classes * cot_c.to(DEV)).sum()).backward()
+    gr = _grads(m)
+    n = 0
+    for k, p in sdl.items():
+        if p.grad is None:
+            continue
+        assert_close(gr[k], p.grad.float(), tol_grad, k, floor=1e-6)
+        n += 1
+    assert n >= 6
 
 
 # ------------------------------------------------------------------------------------------------
@@ -566,6 +619,144 @@ def test_actor_golden(golden):
     ppo.update(mem)
     assert not torch.equal(before, ppo.policy.actor[0].weight.detach())
     assert torch.equal(ppo.policy.actor[0].weight, ppo.policy_old.actor[0].weight)
+
+
+def test_ppo_update_golden(golden):
+    """PPO.evaluate / PPO.update (models/rlmil.py:99-127,152-184) against the reference's own run: rollout, evaluate
+    outputs, the first epoch's gradients, and the weights after K_epochs Adam steps."""
+    from murcl_b200.dropin import rlmil
+    g = golden("ppo_update")
+    sdim, hid, k, b, T = g["dims"].tolist()
+    std = float(g["std"])
+    sd = synth.actor_state(sdim, hid, k, seed=int(g["seed_actor"]))
+    ppo = rlmil.PPO(sdim, sdim, hid, False, action_std=std, lr=float(g["lr"]), gamma=float(g["gamma"]),
+                    K_epochs=int(g["K_epochs"]), eps_clip=float(g["eps_clip"]), action_size=k)
+    ppo.policy.load_state_dict(sd, strict=True)
+    ppo.policy_old.load_state_dict(sd, strict=True)
+    mem = rlmil.Memory()
+    for t in range(T):
+        state = torch.from_numpy(g[f"state{t}"]).to(DEV)
+        action = ppo.policy_old.act(state, mem, restart_batch=(t == 0), training=True, eps=torch.from_numpy(g[f"eps{t}"]).to(DEV))
+        assert_close(action, g[f"action{t}"], FP32_OUT, f"action{t}")
+        assert_close(mem.logprobs[-1], g[f"logprob{t}"], FP32_OUT, f"logprob{t}")
+        mem.rewards.append(torch.from_numpy(g[f"reward{t}"]).to(DEV))
+    states, actions = torch.stack(mem.states, 0), torch.stack(mem.actions, 0)
+    lp, val, ent = ppo.policy.evaluate(states, actions)
+    assert_close(lp, g["eval_logprob"], FP32_OUT, "evaluate.logprob")
+    assert_close(val, g["eval_value"], FP32_OUT, "evaluate.value")
+    assert_close(ent, g["eval_entropy"], FP32_OUT, "evaluate.entropy")
+    # first epoch's objective and gradients (rlmil.py:169-181)
+    ret = torch.from_numpy(g["returns"]).to(DEV)
+    ratios = torch.exp(lp - torch.stack(mem.logprobs, 0).detach())
+    adv = ret - val.detach()
+    loss = -torch.min(ratios * adv, torch.clamp(ratios, 0.8, 1.2) * adv) + 0.5 * ppo.MseLoss(val, ret) - 0.01 * ent
+    ppo.policy.zero_grad()
+    loss.mean().backward()
+    assert_close(loss.mean(), g["loss0"], FP32_OUT, "loss0")
+    gr = _grads(ppo.policy)
+    for key, v in g.items():
+        if key.startswith("grad."):
+            assert_close(sample(gr[key[5:]].numpy()), v, FP32_GRAD, key, floor=1e-6)
+    ppo.policy.zero_grad()
+    ppo.update(mem)
+    n = 0
+    for name, p in ppo.policy.named_parameters():
+        # Adam's first steps move every weight by ~lr whatever the gradient's size: compare the DELTAS to 1 %
+        assert_close(sample((p.detach().cpu() - sd[name]).numpy()), g[f"delta.{name}"], 1e-2, f"delta.{name}", floor=1e-6)
+        n += 1
+    assert n == len(sd)
+    for a, b_ in zip(ppo.policy.state_dict().values(), ppo.policy_old.state_dict().values()):
+        assert torch.equal(a, b_)
+
+
+def _stage3_fixture(g):
+    b, k, d, fs, T, L, D, hid, proj, phid = g["cfg"].tolist()
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), d, k, seed=111)
+    draws, eps = [], [None]
+    for t in range(T):
+        acts = [torch.from_numpy(g[f"act0_{v}"]).to(DEV) for v in range(2)] if t == 0 else None
+        draws.append((acts, [torch.from_numpy(g[f"lam{t}_{v}"]).to(DEV) for v in range(2)],
+                      [torch.from_numpy(g[f"perm{t}_{v}"]).to(DEV) for v in range(2)]))
+        if t >= 1:
+            eps.append([torch.from_numpy(g[f"eps{t}_{v}"]).to(DEV) for v in range(2)])
+    return (b, k, d, fs, T, L, D, hid, proj, phid), feats, clusters, draws, eps
+
+
+def _stage3_objects(cfg, g, lr):
+    from murcl_b200.dropin import abmil, cl, losses, rlmil
+    b, k, d, fs, T, L, D, hid, proj, phid = cfg
+    enc = _load(abmil.ABMIL(d, L=L, D=D, dim_out=proj, precision="fp32"), synth.abmil_state(d, L, D, proj, seed=112))
+    model = cl.CL(enc, projection_dim=proj, n_features=L)
+    fc = _load(rlmil.Full_layer(L, hid, True, proj), synth.full_layer_state(L, hid, proj, seed=113))
+    sd_a = synth.actor_state(L, phid, k, seed=114)
+    ppo = rlmil.PPO(d, L, phid, False, action_std=float(g["std"]), lr=lr, gamma=float(g["ppo_gamma"]),
+                    K_epochs=int(g["ppo_K_epochs"]), action_size=k)
+    ppo.policy.load_state_dict(sd_a)
+    ppo.policy_old.load_state_dict(sd_a)
+    return enc, model, fc, ppo, sd_a, losses.NT_Xent(b, float(g["tau"]))
+
+
+def test_stage3_step_golden(golden):
+    """The benchmarked call sequence - actor-chosen windows (train_MuRCL.py:254-288, stage 3) through
+    ``pretrain.pretrain_step`` / ``act_views`` / ``forward_views`` - against the reference's own run of that loop:
+    chosen actions, log-probs, per-step losses, rewards, total loss and every gradient."""
+    from murcl_b200 import pretrain
+    from murcl_b200.csr import BagStore
+    from murcl_b200.dropin import rlmil
+    g = golden("stage3_step")
+    cfg, feats, clusters, draws, eps = _stage3_fixture(g)
+    b, k, d, fs, T, L, D, hid, proj, phid = cfg
+    enc, model, fc, ppo, sd_a, crit = _stage3_objects(cfg, g, float(g["ppo_lr"]))
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    mems = [rlmil.Memory(), rlmil.Memory()]
+    loss, per_step = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=float(g["alpha"]), stage=3,
+                                            ppo=ppo, memories=mems, draws=draws, eps=eps, precision="fp32", keep_memory=True)
+    for t in range(T):
+        assert_close(per_step[t], g[f"loss{t}"], FP32_OUT, f"loss{t}")
+    assert_close(loss, g["loss"], FP32_OUT, "loss")
+    for v, m in enumerate(mems):
+        assert len(m.actions) == T - 1 and len(m.rewards) == T - 1
+        for t in range(1, T):
+            assert_close(m.actions[t - 1], g[f"act{t}_{v}"], FP32_OUT, f"act{t}_{v}")
+            assert_close(m.rewards[t - 1], g[f"reward{t}"], 1e-4, f"reward{t}", floor=1e-3)
+        assert_close(torch.stack(m.logprobs, 0), g[f"logprobs_{v}"], FP32_OUT, f"logprobs_{v}")
+    gm, gf = _grads(enc), _grads(fc)
+    n = 0
+    for key, v in g.items():
+        if key.startswith("grad.m."):
+            assert_close(sample(gm[key[7:]].numpy()), v, 3e-4, key, floor=1e-5)
+            n += 1
+        elif key.startswith("grad.f."):
+            assert_close(sample(gf[key[7:]].numpy()), v, 3e-4, key, floor=1e-5)
+            n += 1
+    assert n >= 10
+    # the actor was not updated in stage 3
+    for name, p in ppo.policy.named_parameters():
+        assert torch.equal(p.detach().cpu(), sd_a[name])
+
+
+def test_stage2_step_golden(golden):
+    """Stage 2 (train_MuRCL.py:244-247,296-298): the same rollout under no_grad, then ``ppo.update`` from both views'
+    memories; the policy's weight deltas are compared with the reference's."""
+    from murcl_b200 import pretrain
+    from murcl_b200.csr import BagStore
+    from murcl_b200.dropin import rlmil
+    g = golden("stage3_step")
+    cfg, feats, clusters, draws, eps = _stage3_fixture(g)
+    b, k, d, fs, T, L, D, hid, proj, phid = cfg
+    enc, model, fc, ppo, sd_a, crit = _stage3_objects(cfg, g, float(g["ppo_lr"]))
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    mems = [rlmil.Memory(), rlmil.Memory()]
+    loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=float(g["alpha"]), stage=2,
+                                     ppo=ppo, memories=mems, draws=draws, eps=eps, precision="fp32")
+    assert_close(loss, g["loss"], FP32_OUT, "loss")
+    assert all(p.grad is None for p in enc.parameters()), "stage 2 must not touch the MIL model"
+    assert len(mems[0].actions) == 0, "the reference clears the memories after the update"
+    n = 0
+    for name, p in ppo.policy.named_parameters():
+        assert_close(sample((p.detach().cpu() - sd_a[name]).numpy()), g[f"ppo_delta.{name}"], 2e-2, f"ppo_delta.{name}", floor=1e-5)
+        n += 1
+    assert n == len(sd_a)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -211,3 +211,93 @@ def test_pretrain_step(golden):
             assert_close(sample(grads[key[5:]].numpy()), v, 2e-4, key, floor=1e-5)
             n += 1
     assert n >= 10
+
+
+def _ppo_rollout(g):
+    sdim, hid, k, b, T = g["dims"].tolist()
+    states = torch.stack([torch.from_numpy(g[f"state{t}"]) for t in range(T)], 0)
+    actions = torch.stack([torch.from_numpy(g[f"action{t}"]) for t in range(T)], 0)
+    logprobs = torch.stack([torch.from_numpy(g[f"logprob{t}"]) for t in range(T)], 0)
+    rewards = [torch.from_numpy(g[f"reward{t}"]) for t in range(T)]
+    return (sdim, hid, k, b, T), states, actions, logprobs, rewards
+
+
+def test_ppo_evaluate_and_update(golden):
+    """PPO.evaluate / PPO.update (models/rlmil.py:99-127,152-184) on the reference's own rollout."""
+    g = golden("ppo_update")
+    (sdim, hid, k, b, T), states, actions, logprobs, rewards = _ppo_rollout(g)
+    std = float(g["std"])
+    sd = synth.actor_state(sdim, hid, k, seed=int(g["seed_actor"]))
+    # the rollout itself: act() restated, chained over the T steps
+    h = None
+    for t in range(T):
+        a, lp, h, _ = O.actor_act(states[t], h, sd, std, torch.from_numpy(g[f"eps{t}"]))
+        assert_close(a, g[f"action{t}"], TOL, f"action{t}")
+        assert_close(lp, g[f"logprob{t}"], TOL, f"logprob{t}")
+    lp, val, ent = O.actor_evaluate(states, actions, sd, std)
+    assert_close(lp, g["eval_logprob"], TOL, "evaluate.logprob")
+    assert_close(val, g["eval_value"], TOL, "evaluate.value")
+    assert_close(ent, g["eval_entropy"], TOL, "evaluate.entropy")
+    assert_close(O.ppo_returns(rewards, float(g["gamma"])), g["returns"], TOL, "returns")
+    new, first, losses = O.ppo_update(sd, states, actions, logprobs, rewards, action_std=std, lr=float(g["lr"]),
+                                      gamma=float(g["gamma"]), K_epochs=int(g["K_epochs"]), eps_clip=float(g["eps_clip"]))
+    assert_close(losses[0], g["loss0"], TOL, "loss0")
+    n = 0
+    for key, v in g.items():
+        if key.startswith("grad."):
+            assert_close(sample(first[key[5:]].numpy()), v, 5e-5, key, floor=1e-6)
+        elif key.startswith("delta."):
+            # Adam's first steps move every weight by ~lr: compare the DELTAS (1e-3 of the weights) to 1 %
+            assert_close(sample((new[key[6:]] - sd[key[6:]]).numpy()), v, 1e-2, key, floor=1e-6)
+            n += 1
+    assert n == len(sd)
+
+
+def _stage3_inputs(g):
+    b, k, d, fs, T, L, D, hid, proj, phid = g["cfg"].tolist()
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), d, k, seed=111)
+    sd_m = synth.abmil_state(d, L, D, proj, seed=112)
+    sd_f = synth.full_layer_state(L, hid, proj, seed=113)
+    sd_a = synth.actor_state(L, phid, k, seed=114)
+    first = [torch.from_numpy(g[f"act0_{v}"]) for v in range(2)]
+    lams = [[torch.from_numpy(g[f"lam{t}_{v}"]) for v in range(2)] for t in range(T)]
+    perms = [[torch.from_numpy(g[f"perm{t}_{v}"]) for v in range(2)] for t in range(T)]
+    eps = [None] + [[torch.from_numpy(g[f"eps{t}_{v}"]) for v in range(2)] for t in range(1, T)]
+    return (b, k, d, fs, T, L, D, hid, proj, phid), feats, clusters, sd_m, sd_f, sd_a, first, lams, perms, eps
+
+
+def test_stage3_step(golden):
+    """Actor-driven pre-training step (train_MuRCL.py:235-298, stage 3) + the stage-2 PPO update on its rollout."""
+    g = golden("stage3_step")
+    (b, k, d, fs, T, L, D, hid, proj, phid), feats, clusters, sd_m, sd_f, sd_a, first, lams, perms, eps = _stage3_inputs(g)
+    r = O.pretrain_step_stage3(feats, clusters, sd_m, sd_f, sd_a, first_actions=first, lams=lams, perms=perms, eps=eps,
+                               action_std=float(g["std"]), T=T, feat_size=fs, temperature=float(g["tau"]))
+    for t in range(T):
+        for v in range(2):
+            assert_close(r["actions"][t][v], g[f"act{t}_{v}"], TOL, f"act{t}_{v}")
+        assert_close(r["losses"][t], g[f"loss{t}"], TOL, f"loss{t}")
+        if t >= 1:
+            assert_close(r["rewards"][t - 1], g[f"reward{t}"], 1e-4, f"reward{t}", floor=1e-3)
+    assert_close(r["loss"], g["loss"], TOL, "loss")
+    for v in range(2):
+        assert_close(r["logprobs"][v], g[f"logprobs_{v}"], TOL, f"logprobs_{v}")
+    n = 0
+    for key, val in g.items():
+        if key.startswith("grad.m.") or key.startswith("grad.f."):
+            assert_close(sample(r["grads"][key[5:]].numpy()), val, 5e-5, key, floor=1e-5)
+            n += 1
+    assert n >= 10
+    # stage 2: both memories update the same policy in turn, Adam state carried across the two updates
+    params = {kk: vv.detach().clone().requires_grad_(True) for kk, vv in sd_a.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=float(g["ppo_lr"]), betas=(0.9, 0.999))
+    for v in range(2):
+        ret = O.ppo_returns(r["rewards"], float(g["ppo_gamma"]))
+        for _ in range(int(g["ppo_K_epochs"])):
+            loss = O.ppo_loss(params, r["states"][v], r["roll_actions"][v], r["logprobs"][v], ret,
+                              action_std=float(g["std"]), eps_clip=0.2)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    for key, val in g.items():
+        if key.startswith("ppo_delta."):
+            assert_close(sample((params[key[10:]].detach() - sd_a[key[10:]]).numpy()), val, 2e-2, key, floor=1e-5)

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Launches every HBM- / latency-bound kernel of the MIL hot path once (after one warm launch) at the bench shapes, so
+that ONE ncu run captures them all (tools/prof_hbm.sh).  Also prints, as JSON, the ALGORITHMIC bytes of each launch
+(compulsory traffic: what the kernel must read and write once) - tools/ncu_summary.py divides them by the measured
+duration to get the achieved GB/s next to the dram__bytes counters.
+
+Shapes: cfg3 pre-train step (256 packed slots of 1024 x 512 bf16 = 262 144 instance rows), cfg2 ragged CLAM bags
+(64 bags, N ~ U[2000, 20000]) for the top-k, cfg4 (N = 10 000, C = 2) and a 64-bag batch for the arg-max, B = 128,
+d = 128 for NT-Xent.
+"""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from murcl_b200 import _lib, ops, synth                     # noqa: E402
+from murcl_b200.csr import BagStore, HostBags               # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    alg = {}
+    B, K, FS, D, L, DA = 128, 10, 1024, 512, 512, 128
+    g = synth.gen(7)
+
+    # ---- packer on a Camelyon16-shaped bf16 slide store ------------------------------------------------------
+    sizes = synth.camelyon_sizes(B, 500, 15500, seed=1000)
+    feats, _cl, labels = synth.make_bags(sizes, D, K, seed=1000)
+    host = HostBags(feats, labels, K, pin=False, dtype=torch.bfloat16)
+    store = BagStore.empty_like_host(host, dev)
+    store.copy_from_host(host)
+    act = torch.rand(2 * B, K, generator=g).to(dev)
+    lam = (0.9 + 0.1 * torch.rand(2 * B, generator=g)).to(dev)
+    perm = torch.cat([torch.randperm(B, generator=g), torch.randperm(B, generator=g) + B]).to(dev)
+    slot_bag = torch.arange(B, dtype=torch.int32, device=dev).repeat(2)
+    n_patches = sum(sizes)
+    for _ in range(2):
+        sel_idx, sel_cnt = store.select(act, FS, slot_bag)
+        x = store.gather(sel_idx, lam, perm, torch.bfloat16)
+    # select: every slot streams its bag's (cluster, rank) pairs once (8 B / patch) and writes FS indices
+    alg["pack_select_kernel"] = 2 * n_patches * 8 + 2 * B * FS * 4
+    # gather + mixup: two source rows read, one row written, per output row (bf16 store -> bf16 batch) + the index
+    alg["pack_gather_kernel"] = 2 * B * FS * (3 * D * 2 + 4)
+
+    rows = 2 * B * FS
+    offsets = torch.arange(0, rows + 1, FS, dtype=torch.int64, device=dev)
+    row_seg = ops.row_segments(offsets, rows)
+    H = x.reshape(rows, D)
+    # ---- fused attention pooling forward + the separate backward kernels ------------------------------------
+    sd = synth.abmil_state(D, L, DA, 128, seed=985, peak=2.0)
+    wab = sd["attention.0.weight"].to(dev).bfloat16().contiguous()
+    bab = sd["attention.0.bias"].to(dev).float().contiguous()
+    wc = sd["attention.2.weight"].to(dev).float().reshape(-1).contiguous()
+    bc = sd["attention.2.bias"].to(dev).float().reshape(-1).contiguous()
+    dM = torch.randn(2 * B, L, generator=g).to(dev)
+    for _ in range(2):
+        uv, s, p, M, stats = ops.attnpool_fwd(H, wab, bab, wc, bc, offsets, row_seg, 2 * B, DA, False, True)
+        if hasattr(ops, "attnpool_bwd"):
+            ops.attnpool_bwd(H, uv.clone(), p, M, dM, wc, offsets, row_seg, 2 * B, DA, False, True)
+        ds = ops.pool_bwd_scores(p, H, dM, M, offsets, row_seg, 2 * B, 1, True)
+        ops.attn_score_bwd_(uv.clone(), wc, ds, DA, False)
+    alg["attnpool_fwd_kernel"] = rows * (L * 2 + DA * 2 + 8)
+    alg["attnpool_bwd_kernel"] = rows * (L * 2 + DA * 2 * 2 + 4 + 4)        # h once, uv read + rewritten in place, p, ds
+    alg["pool_bwd_scores_c1_kernel"] = rows * (L * 2 + 4 + 4)               # h once, p in, ds out
+    alg["attn_score_bwd_kernel"] = rows * (DA * 2 * 2 + 4)                  # uv read + rewritten in place, ds in
+
+    # ---- segmented kernels ------------------------------------------------------------------------------------
+    sizes2 = torch.randint(2000, 20001, (64,), generator=g).tolist()
+    off2 = torch.tensor([0] + list(torch.tensor(sizes2).cumsum(0)), dtype=torch.int64, device=dev)
+    n2 = int(off2[-1])
+    p2 = torch.softmax(torch.randn(n2, generator=g), 0).to(dev)
+    c2 = torch.randn(n2, 2, generator=g).to(dev)
+    off4 = torch.tensor([0, 10000], dtype=torch.int64, device=dev)
+    for _ in range(2):
+        ops.seg_topk_ends(p2, off2, 64, 8)
+        ops.seg_argmax(c2, off2, 64, 2)
+        ops.seg_argmax(c2[:10000].contiguous(), off4, 1, 2)
+    alg["seg_topk_ends_kernel"] = n2 * 4 + 64 * 16 * 4                      # one pass over p, 2k indices per bag out
+    alg["seg_argmax_kernel"] = n2 * 2 * 4 + 64 * 2 * 4                      # first (64-bag) launch; the cfg4 one is 80 KB
+
+    # ---- NT-Xent ----------------------------------------------------------------------------------------------
+    z = torch.randn(2 * B, 128, generator=g).to(dev)
+    for _ in range(2):
+        ops.ntxent_raw(z, B, 1.0, True)
+    alg["ntxent"] = 2 * (2 * B * 128 * 4) + B * 4 + 4                       # z in, dz out, cosines, loss
+
+    torch.cuda.synchronize()
+    out = ROOT / "gpurun_out" / "prof_hbm_alg_bytes.json"
+    out.parent.mkdir(exist_ok=True)
+    out.write_text(json.dumps(alg, indent=1))
+    print(json.dumps(alg))
+
+
+if __name__ == "__main__":
+    main()
