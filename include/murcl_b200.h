@@ -166,6 +166,21 @@ int murcl_pool_bwd_direct(const float* p, const float* dM, const int32_t* row_se
 int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc, float* dbc, float* dpre_colsum,
                          int64_t N, int D, int gated, float drop_scale, int dtype, void* stream);
 
+/* Fused attention pooling, backward (abmil.py:36-45, clam.py:37-60,170 differentiated; the matching pass of
+ * murcl_attnpool_fwd): ONE pass over h [n_rows, L] computes ds[n] = p[n] * (dM[b].h[n] - (dM[b].M[b]) / post_scale_b),
+ * overwrites the saved activations uv [n_rows, D*(1+gated)] with the gradient w.r.t. the pre-activations (tanh' /
+ * sigmoid' and the gate applied) and accumulates dwc[D], dbc[1] and - when dpre_colsum != NULL - the column sums of
+ * the written gradient (bias gradient of the attention projection); all three fp32, zeroed by the caller.  ds itself is
+ * written only when the pointer is non-NULL.  Replaces murcl_pool_bwd_scores (C == 1) + murcl_attn_score_bwd: h is read
+ * once and ds never travels through memory.  The direct term dh[n] += p[n] dM[b] stays fused in murcl_linear_bwd_input.
+ * h, uv in dtype (fp32 or bf16); supported when murcl_attnpool_bwd_supported(...) != 0 (L <= 1024, L % 8 == 0,
+ * D <= 512, D % 4 == 0).  drop_scale as for murcl_attn_score_bwd. */
+int murcl_attnpool_bwd_supported(int L, int D, int gated, int dtype);
+int murcl_attnpool_bwd(const void* h, void* uv, const float* p, const float* M, const float* dM, const float* wc,
+                       const int64_t* offsets, const int32_t* row_seg, int64_t n_rows, int B, int L, int D, int gated,
+                       int inv_sqrt_n, float drop_scale, int dtype, float* ds, float* dwc, float* dbc, float* dpre_colsum,
+                       void* stream);
+
 /* ---- (3) segmented reductions: clam.py:103-132 (top-k instance loss), dsmil.py:71-78 ---- */
 
 /* Indices (global rows) of the k largest and k smallest p within each bag, ordered like

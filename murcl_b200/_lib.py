@@ -39,6 +39,8 @@ SIGNATURES = {
     "murcl_attnpool_supported": (_i, [_i, _i, _i, _i]),
     "murcl_attnpool_workspace": (_l, [_l, _i, _i]),
     "murcl_attnpool_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "murcl_attnpool_bwd_supported": (_i, [_i, _i, _i, _i]),
+    "murcl_attnpool_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p]),
     "murcl_seg_wsum_workspace": (_l, [_l, _i, _i, _i]),
     "murcl_seg_wsum": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _p, _p, _p]),
     "murcl_pool_bwd_scores": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p, _p, _p]),

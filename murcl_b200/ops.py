@@ -305,6 +305,30 @@ def attn_score_bwd_(uv, wc, ds, D, gated, drop_scale=1.0):
     return dwc, dbc, dpre
 
 
+def attnpool_bwd_supported(L, D, gated, dtype) -> bool:
+    if os.environ.get("MURCL_DISABLE_ATTNPOOL_BWD", "0") == "1" or dtype not in _DT:
+        return False
+    return bool(_lib.load().murcl_attnpool_bwd_supported(int(L), int(D), int(gated), _DT[dtype]))
+
+
+def attnpool_bwd_(h, uv, p, M, dM, wc, offsets, row_seg, B, D, gated, inv_sqrt_n, drop_scale=1.0, want_ds=False):
+    """Fused pooling backward (murcl_attnpool_bwd): one pass over ``h``; ``uv`` becomes the gradient w.r.t. the
+    pre-activations IN PLACE.  Returns (dwc [D], dbc [1], column sums of the new uv, ds or None)."""
+    _chk(h, "attnpool_bwd.h"); _chk(uv, "attnpool_bwd.uv", h.dtype)
+    _chk(p, "attnpool_bwd.p", torch.float32); _chk(M, "attnpool_bwd.M", torch.float32); _chk(dM, "attnpool_bwd.dM", torch.float32)
+    n_rows, L = h.shape
+    buf = torch.zeros((D + 4 + uv.shape[1],), device=uv.device, dtype=torch.float32)      # one memset for all three
+    dwc, dbc, dpre = buf[:D], buf[D:D + 1], buf[D + 4:]
+    ds = torch.empty((n_rows,), device=h.device, dtype=torch.float32) if want_ds else None
+    # profile record: "flops" slot carries the algorithmic HBM bytes (h once, uv read + rewritten, p)
+    es = h.element_size()
+    with _Timed("attnpool_bwd", float(n_rows) * (L * es + 2 * uv.shape[1] * es + 4)):
+        check(_lib.load().murcl_attnpool_bwd(_p(h), _p(uv), _p(p), _p(M), _p(dM), _p(wc), _p(offsets), _p(row_seg), n_rows, B, L,
+                                             D, int(gated), int(inv_sqrt_n), float(drop_scale), _dt(h), _p(ds), _p(dwc), _p(dbc),
+                                             _p(dpre), _s()), "murcl_attnpool_bwd")
+    return dwc, dbc, dpre, ds
+
+
 def seg_topk_ends(p, offsets, B, k):
     top = torch.empty((B, k), device=p.device, dtype=torch.int32)
     bot = torch.empty((B, k), device=p.device, dtype=torch.int32)
@@ -565,11 +589,16 @@ class _MILAggregate(torch.autograd.Function):
         H = hs[-1]
         L = H.shape[1]
         dM = dM.contiguous().float()
-        ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, meta["inv_sqrt_n"])
         drop = meta.get("drop")
         q_attn = 1.0 / (1.0 - drop["attn"]) if drop is not None and drop["attn"] > 0 else 1.0
         q_enc = [1.0 / (1.0 - pe) if drop is not None and pe > 0 else 1.0 for pe in (drop["enc"] if drop else [0.0] * n_enc)]
-        dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated, q_attn)    # uv now holds d(pre-activation)
+        if attnpool_bwd_supported(L, D, gated, H.dtype):
+            # one pass over H: t_n = dM.h_n, ds, d(pre-activation) over uv, dwc / bias column sums
+            dwc, dbc, dbab, _ = attnpool_bwd_(H, uv, p, M.reshape(B, L).contiguous(), dM, wc_f, offsets, row_seg, B, D, gated,
+                                              meta["inv_sqrt_n"], q_attn)
+        else:
+            ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, meta["inv_sqrt_n"])
+            dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated, q_attn)    # uv now holds d(pre-activation)
         dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
         hbits = ctx.hbits
         relu_src = H if (n_enc > 0 and hbits[n_enc] is None) else None

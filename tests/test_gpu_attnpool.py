@@ -141,3 +141,81 @@ def test_sharded_attention_pool_kernels_single_rank():
         assert_close(h.grad.cpu(), torch.cat([x.grad for x, n in zip(Hf, sizes) if n]), 1e-5, "dh")
         # ds = p (dM.h - dM.M): a difference of two O(sqrt(L)) dot products in fp32 (measured 1.8e-5)
         assert_close(s.grad.cpu(), torch.cat([x.grad for x, n in zip(Sf, sizes) if n]), 1e-4, "ds")
+
+
+BWD_CASES = [
+    # L, D, gated, inv_sqrt_n, sizes, dtype, drop_scale
+    (512, 128, False, True, RAGGED, torch.bfloat16, 1.0),          # ABMIL, the pre-training shape
+    (512, 128, False, True, [1024] * 24, torch.bfloat16, 1.0),     # tile-aligned bags, more chunks than one wave
+    (512, 256, True, False, RAGGED, torch.bfloat16, 1.0),          # CLAM_SB small, gated
+    (512, 384, True, False, [700, 3, 1500], torch.bfloat16, 1.0),  # CLAM_SB big
+    (512, 256, True, False, [300, 64], torch.bfloat16, 1.0 / 0.75),  # train-mode dropout after the activations
+    (512, 128, False, True, RAGGED, torch.float32, 1.0),           # exact mode
+    (512, 256, True, False, [130, 126, 1], torch.float32, 1.0),
+    (32, 16, False, True, [50, 77, 1], torch.float32, 1.0),        # the golden "small" shape: few active lanes
+    (1024, 128, False, False, [333, 2], torch.bfloat16, 1.0),      # widest supported rows
+]
+
+
+@pytest.mark.parametrize("L,D,gated,inv_sqrt_n,sizes,dtype,q", BWD_CASES)
+def test_attnpool_bwd_matches_separate_kernels_and_fp64(L, D, gated, inv_sqrt_n, sizes, dtype, q):
+    """murcl_attnpool_bwd (one pass over H: ds, d(pre-activation) over uv, dwc, dbc, bias column sums) against
+    (a) murcl_pool_bwd_scores + murcl_attn_score_bwd, which it replaces, and (b) an fp64 evaluation of SURVEY 7.3's
+    formulas on the same stored operands."""
+    from murcl_b200 import ops
+    assert ops.attnpool_bwd_supported(L, D, gated, dtype)
+    g = synth.gen(7 * L + D + len(sizes))
+    n, B = sum(sizes), len(sizes)
+    nc = D * (2 if gated else 1)
+    h = torch.clamp_min(0.5 * torch.randn(n, L, generator=g) + 0.2, 0).to(dtype)
+    u = torch.tanh(torch.randn(n, D, generator=g))
+    act = torch.cat([u, torch.sigmoid(torch.randn(n, D, generator=g))], 1) if gated else u
+    if q != 1.0:                                                 # inverted dropout: kept entries scaled by q, dropped = 0
+        act = act * q * (torch.rand(n, nc, generator=g) > 0.25)
+    act = act.to(dtype)
+    wc = torch.randn(D, generator=g) * (3.0 / math.sqrt(D))
+    s = 2.0 * torch.randn(n, generator=g)
+    dM = torch.randn(B, L, generator=g)
+    offsets = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64)
+    p = torch.empty(n)
+    M = torch.zeros(B, L)
+    for b in range(B):
+        lo, hi = int(offsets[b]), int(offsets[b + 1])
+        p[lo:hi] = torch.softmax(s[lo:hi], 0) / (math.sqrt(hi - lo) if inv_sqrt_n else 1.0)
+        M[b] = p[lo:hi] @ h[lo:hi].float()
+    hd, pd, Md, dMd, wcd, od = (t.to(DEV).contiguous() for t in (h, p, M, dM, wc, offsets))
+    row_seg = ops.row_segments(od, n)
+    uv1, uv2 = act.to(DEV).contiguous(), act.to(DEV).contiguous()
+    dwc, dbc, dpre, ds = ops.attnpool_bwd_(hd, uv1, pd, Md, dMd, wcd, od, row_seg, B, D, gated, inv_sqrt_n, q, want_ds=True)
+    # (a) the two kernels it replaces
+    ds2 = ops.pool_bwd_scores(pd, hd, dMd, Md.reshape(B, 1, L), od, row_seg, B, 1, inv_sqrt_n)
+    dwc2, dbc2, dpre2 = ops.attn_score_bwd_(uv2, wcd, ds2, D, gated, q)
+    assert_close(ds, ds2, 1e-5, "ds vs pool_bwd_scores", floor=1e-6)
+    assert_close(uv1.float(), uv2.float(), 1e-2 if dtype == torch.bfloat16 else 1e-5, "d(pre-activation) vs attn_score_bwd", floor=1e-6)
+    assert_close(dwc, dwc2, 1e-4, "dwc vs attn_score_bwd", floor=1e-5)
+    assert_close(dpre, dpre2, 1e-3 if dtype == torch.bfloat16 else 1e-4, "bias column sums vs attn_score_bwd", floor=1e-5)
+    # (b) fp64
+    hh, aa = h.double(), act.double()
+    seg = torch.repeat_interleave(torch.arange(B), torch.tensor(sizes))
+    alpha = torch.tensor([1.0 / math.sqrt(max(x, 1)) if inv_sqrt_n else 1.0 for x in sizes], dtype=torch.float64)
+    t = (dM.double()[seg] * hh).sum(1)
+    K = (dM.double() * M.double()).sum(1) / alpha
+    ds_ref = p.double() * (t - K[seg])
+    ua = aa[:, :D] / q
+    keep_u = (aa[:, :D] != 0) if q != 1.0 else torch.ones_like(ua, dtype=torch.bool)
+    if gated:
+        va = aa[:, D:] / q
+        keep_v = (aa[:, D:] != 0) if q != 1.0 else torch.ones_like(va, dtype=torch.bool)
+        du = ds_ref[:, None] * wc.double() * aa[:, D:] * q * (1 - ua * ua) * keep_u
+        dv = ds_ref[:, None] * wc.double() * aa[:, :D] * q * va * (1 - va) * keep_v
+        d_ref = torch.cat([du, dv], 1)
+        dwc_ref = (ds_ref[:, None] * aa[:, :D] * aa[:, D:]).sum(0)
+    else:
+        d_ref = ds_ref[:, None] * wc.double() * q * (1 - ua * ua) * keep_u
+        dwc_ref = (ds_ref[:, None] * aa).sum(0)
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-5
+    assert_close(ds.cpu(), ds_ref.float(), 2e-5, "ds vs fp64", floor=1e-6)
+    assert_close(uv1.float().cpu(), d_ref.float(), tol, "d(pre-activation) vs fp64", floor=1e-6)
+    assert_close(dwc.cpu(), dwc_ref.float(), 1e-4, "dwc vs fp64", floor=1e-5)
+    assert_close(dpre.cpu(), d_ref.sum(0).float(), 2e-3 if dtype == torch.bfloat16 else 1e-4, "bias column sums vs fp64", floor=1e-4)
+    assert_close(dbc.cpu(), ds_ref.sum().reshape(1).float(), 1.0, "dbc", floor=1e-3)   # analytically zero: noise only

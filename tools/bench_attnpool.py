@@ -57,6 +57,24 @@ def main():
         print(f"B={B} FS={FS} L={L} D={D} gated={gated}: fused {tf:.1f} us ({byts / tf / 1e3:.0f} GB/s algorithmic), "
               f"separate kernels {ts:.1f} us")
 
+        # backward: fused single pass vs pool_bwd_scores + attn_score_bwd
+        uv, s, p, M, _ = fused()
+        M = M.reshape(B, L).contiguous()
+        dM = torch.randn(B, L, generator=g).to(DEV)
+        uv_w = uv.clone()
+
+        def bwd_fused():
+            return ops.attnpool_bwd_(h, uv_w, p, M, dM, wc, off, seg, B, D, gated, True)
+
+        def bwd_separate():
+            ds = ops.pool_bwd_scores(p, h, dM, M.reshape(B, 1, L), off, seg, B, 1, True)
+            return ops.attn_score_bwd_(uv_w, wc, ds, D, gated)
+
+        tbf, tbs = timeit(bwd_fused, reps), timeit(bwd_separate, reps)
+        bytb = n * (L * 2 + 2 * nc * 2 + 4)
+        print(f"    backward: fused {tbf:.1f} us ({bytb / tbf / 1e3:.0f} GB/s algorithmic, {bytb / tbf / 1e3 / 6540.5:.2f} of the "
+              f"measured HBM peak), separate kernels {tbs:.1f} us")
+
 
 if __name__ == "__main__":
     main()

@@ -61,8 +61,7 @@ def main():
     dM = torch.randn(2 * B, L, generator=g).to(dev)
     for _ in range(2):
         uv, s, p, M, stats = ops.attnpool_fwd(H, wab, bab, wc, bc, offsets, row_seg, 2 * B, DA, False, True)
-        if hasattr(ops, "attnpool_bwd"):
-            ops.attnpool_bwd(H, uv.clone(), p, M, dM, wc, offsets, row_seg, 2 * B, DA, False, True)
+        ops.attnpool_bwd_(H, uv.clone(), p, M.reshape(2 * B, L).contiguous(), dM, wc, offsets, row_seg, 2 * B, DA, False, True)
         ds = ops.pool_bwd_scores(p, H, dM, M, offsets, row_seg, 2 * B, 1, True)
         ops.attn_score_bwd_(uv.clone(), wc, ds, DA, False)
     alg["attnpool_fwd_kernel"] = rows * (L * 2 + DA * 2 + 8)
