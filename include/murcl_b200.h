@@ -174,7 +174,7 @@ int murcl_attn_score_bwd(void* uv, const float* wc, const float* ds, float* dwc,
  * written only when the pointer is non-NULL.  Replaces murcl_pool_bwd_scores (C == 1) + murcl_attn_score_bwd: h is read
  * once and ds never travels through memory.  The direct term dh[n] += p[n] dM[b] stays fused in murcl_linear_bwd_input.
  * h, uv in dtype (fp32 or bf16); supported when murcl_attnpool_bwd_supported(...) != 0 (L <= 1024, L % 8 == 0,
- * D <= 512, D % 4 == 0).  drop_scale as for murcl_attn_score_bwd. */
+ * D <= 512, D % 8 == 0).  drop_scale as for murcl_attn_score_bwd. */
 int murcl_attnpool_bwd_supported(int L, int D, int gated, int dtype);
 int murcl_attnpool_bwd(const void* h, void* uv, const float* p, const float* M, const float* dM, const float* wc,
                        const int64_t* offsets, const int32_t* row_seg, int64_t n_rows, int B, int L, int D, int gated,
