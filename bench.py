@@ -10,8 +10,12 @@ NT-Xent over the global batch, backward, Adam.  Weak scaling: every rank owns 12
 all-gathered (NCCL) for the loss and gradients all-reduced once per step.
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with the slides already in HBM;
-`e2e` = the same step driven from PINNED HOST buffers (H2D of the step's slides inside the timed region,
-double-buffered on a copy stream, loss read back every step).
+`e2e` = the same step driven from the PINNED HOST staging of a finite dataset shard (`--dataset-slides` per rank) through
+the resident slide cache (csr.ResidentSlides): a slide crosses PCIe the first time a step touches it (prefetched on a copy
+stream one step ahead), afterwards a step uploads only its slide-id list; the timed region spans `--e2e-epochs` epochs
+INCLUDING the cold first one, and the loss is read back every step.  Secondary keys of the same line: `fp32_mode` (the
+reference-precision step), `strong_scaling` (BASELINE config 3 verbatim: 128 bags per step over all ranks) and `cfg5`
+(one 100k x 1024 bag, rows sharded over the ranks).
 """
 from __future__ import annotations
 
@@ -47,7 +51,10 @@ def parse():
     ap.add_argument("--clusters", type=int, default=10)
     ap.add_argument("--min-patches", type=int, default=500)
     ap.add_argument("--max-patches", type=int, default=15500)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--dataset-slides", type=int, default=256, help="slides in a rank's dataset shard (resident cache)")
+    ap.add_argument("--e2e-epochs", type=int, default=10, help="epochs of the dataset shard in the end-to-end region (first one cold)")
+    ap.add_argument("--fp32-steps", type=int, default=3, help="timed steps of the secondary fp32-mode measurement (0 = skip)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the fp32-mode / strong-scaling / cfg5 measurements")
     ap.add_argument("--cpu-bags", type=int, default=8, help="slides in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -62,7 +69,8 @@ def workload_config(a, world):
             "bags_per_gpu": a.bags, "global_bags": a.bags * world, "T": a.T, "views": 2, "feat_size": a.feat_size,
             "feat_dim": a.dim, "clusters": a.clusters, "patches_per_bag": f"U[{a.min_patches},{a.max_patches}]",
             "arch": "ABMIL(512,512,128)+Full_layer(512,1024,128)", "parallelism": f"dp{world} (bags sharded per rank)",
-            "l2_policy": "inputs larger than L2 (CSR store >= 1 GB/GPU, activations 268 MB each)",
+            "l2_policy": "inputs larger than L2 (resident slide arena ~2 GB/GPU, a different batch of slides every step, activations 268 MB each)",
+            "dataset_slides_per_gpu": a.dataset_slides,
             "slide_store_dtype": "bf16" if (a.precision == "bf16" and not a.fp32_store) else "f32",
             "bag_passes_per_step": a.bags * world * a.T * 2}
 
@@ -70,13 +78,15 @@ def workload_config(a, world):
 # ------------------------------------------------------------------------------------------------------
 # synthetic slides
 # ------------------------------------------------------------------------------------------------------
-def make_host_batch(a, seed, pin=True):
+def make_host_batch(a, seed, pin=True, n_slides=None, precision=None):
     from murcl_b200 import synth
     from murcl_b200.csr import HostBags
-    sizes = synth.camelyon_sizes(a.bags, a.min_patches, a.max_patches, seed=seed)
+    n_slides = n_slides or a.bags
+    precision = precision or a.precision
+    sizes = synth.camelyon_sizes(n_slides, a.min_patches, a.max_patches, seed=seed)
     feats, _clusters, labels = synth.make_bags(sizes, a.dim, a.clusters, seed=seed)
     # bf16 mode keeps the slide features as bf16 on the host too (what the first GEMM consumes): half the H2D bytes
-    store_dtype = torch.bfloat16 if (a.precision == "bf16" and not a.fp32_store) else torch.float32
+    store_dtype = torch.bfloat16 if (precision == "bf16" and not a.fp32_store) else torch.float32
     return HostBags(feats, labels, a.clusters, pin=pin, dtype=store_dtype)
 
 
@@ -128,13 +138,16 @@ class Clocks:
 # the job
 # ------------------------------------------------------------------------------------------------------
 class Job:
-    def __init__(self, a, rank, world, device):
+    def __init__(self, a, rank, world, device, bags=None, precision=None):
         from murcl_b200 import dist as mdist
         from murcl_b200 import synth
         from murcl_b200.dropin import abmil, cl, losses, rlmil
         self.a, self.rank, self.world, self.device = a, rank, world, device
+        self.bags = bags or a.bags
+        self.precision = precision or a.precision
+        os.environ["MURCL_PRECISION"] = self.precision      # heads (Full_layer, actor, decoder) follow the same mode
         torch.manual_seed(985 + rank)
-        enc = abmil.ABMIL(a.dim, L=512, D=128, dim_out=128, precision=a.precision)
+        enc = abmil.ABMIL(a.dim, L=512, D=128, dim_out=128, precision=self.precision)
         enc.load_state_dict(synth.abmil_state(a.dim, 512, 128, 128, seed=985, peak=2.0))
         self.model = cl.CL(enc.to(device), projection_dim=128, n_features=512)
         fc = rlmil.Full_layer(512, 1024, True, 128)
@@ -143,32 +156,30 @@ class Job:
         self.ppo = rlmil.PPO(a.dim, 512, 512, False, action_std=0.5, lr=1e-5, gamma=0.1, K_epochs=3, action_size=a.clusters)
         self.ppo.policy_old.load_state_dict(synth.actor_state(512, 512, a.clusters, seed=987))
         self.memories = [rlmil.Memory(), rlmil.Memory()]
+        for m in (self.fc, self.ppo.policy, self.ppo.policy_old):
+            m.precision = self.precision
         if world > 1:
-            self.crit = mdist.DistributedNTXent(a.bags, 1.0)
+            self.crit = mdist.DistributedNTXent(self.bags, 1.0)
         else:
-            self.crit = losses.NT_Xent(a.bags, 1.0)
+            self.crit = losses.NT_Xent(self.bags, 1.0)
         self.params = list(self.model.parameters()) + list(self.fc.parameters())
         self.opt = torch.optim.Adam(self.params, lr=1e-4, weight_decay=1e-5, capturable=True)
         self.mdist = mdist
         self.graphs = {}
         self.launches_per_step = None
 
-    def capture(self, stores):
-        """One CUDA graph per (double-buffered) store, sharing a memory pool.  Returns False (on every rank) if the
-        capture fails on any rank."""
+    def capture(self, store, slot_bag):
+        """The whole optimiser step as ONE CUDA graph over the resident arena; the step's slides are chosen by the
+        contents of the static ``slot_bag`` buffer.  Returns False (on every rank) if the capture fails on any rank."""
         import torch.distributed as dist
         from murcl_b200 import pretrain
         ok = True
         try:
-            pool = None
             # NCCL's watchdog thread polls events while we capture: keep the capture thread-local under torchrun
             mode = "thread_local" if self.world > 1 else "global"
-            for i, st in enumerate(stores):
-                g = pretrain.GraphedStep(lambda st=st: self.step(st), warmup=2 if i == 0 else 0, pool=pool,
-                                         capture_error_mode=mode)
-                pool = g.pool()
-                self.graphs[id(st)] = g
-                self.launches_per_step = g.launches
+            g = pretrain.GraphedStep(lambda: self.step(store, slot_bag), warmup=2, capture_error_mode=mode)
+            self.graphs[id(store)] = g
+            self.launches_per_step = g.launches
         except Exception as e:                                  # noqa: BLE001 - report and fall back to eager launches
             sys.stderr.write(f"[bench] rank {self.rank}: CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
             ok = False
@@ -181,16 +192,16 @@ class Job:
             self.graphs = {}
         return ok
 
-    def run(self, store):
+    def run(self, store, slot_bag):
         g = self.graphs.get(id(store))
-        return g() if g is not None else self.step(store)
+        return g() if g is not None else self.step(store, slot_bag)
 
-    def step(self, store):
+    def step(self, store, slot_bag):
         from murcl_b200 import pretrain
         self.opt.zero_grad(set_to_none=True)
         loss, _ = pretrain.pretrain_step(store, self.model, self.fc, self.crit, T=self.a.T, feat_size=self.a.feat_size,
                                          alpha=0.9, stage=3, ppo=self.ppo, memories=self.memories,
-                                         precision=self.a.precision)
+                                         precision=self.precision, slot_bag=slot_bag)
         if self.world > 1:
             self.mdist.allreduce_grads(self.params)
         self.opt.step()
@@ -218,7 +229,7 @@ def timed(fn, steps, world, device):
     return float(ms.item())
 
 
-def roofline_probe(job, store, peaks):
+def roofline_probe(job, store, slot_bag, peaks):
     """Times every dense-layer launch of one extra step with CUDA events on the launch stream and reports the
     dominant kernel family (the encoder/attention GEMMs) against the measured tensor peak."""
     from murcl_b200 import ops
@@ -226,7 +237,7 @@ def roofline_probe(job, store, peaks):
     ops.set_profile(log)
     torch.cuda.nvtx.range_push("murcl_probe_step")      # ncu --nvtx --nvtx-include "murcl_probe_step/" profiles exactly this step
     try:
-        job.step(store)
+        job.step(store, slot_bag)
         torch.cuda.synchronize()
     finally:
         torch.cuda.nvtx.range_pop()
@@ -254,14 +265,16 @@ def roofline_probe(job, store, peaks):
             traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
         except (ValueError, OSError):
             traffic = None
+    hbm_fams = ("attnpool_fwd", "attnpool_bwd")
     fam = {k: {"launches": v[2], "ms": round(v[1], 3), "tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1)} for k, v in by.items()
-           if k != "attnpool_fwd"}
+           if k not in hbm_fams}
     hbm = peaks.get("hbm_gbs") or 6500.0
-    if "attnpool_fwd" in by:     # the fused attention-pooling forward is HBM-bound: its record carries algorithmic bytes
-        v = by["attnpool_fwd"]
-        gbs = v[0] / (v[1] * 1e-3) / 1e9
-        fam["attnpool_fwd"] = {"launches": v[2], "ms": round(v[1], 3), "bound": "hbm", "algorithmic_gbs": round(gbs, 1),
-                               "frac_of_hbm_peak": round(gbs / hbm, 3)}
+    for name in hbm_fams:        # the fused attention-pooling kernels are HBM-bound: their records carry algorithmic bytes
+        if name in by:
+            v = by[name]
+            gbs = v[0] / (v[1] * 1e-3) / 1e9
+            fam[name] = {"launches": v[2], "ms": round(v[1], 3), "bound": "hbm", "algorithmic_gbs": round(gbs, 1),
+                         "frac_of_hbm_peak": round(gbs / hbm, 3)}
     return {"bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
             "traffic": traffic,
             "kernel": "gemm_tc_kernel (tcgen05) on the instance-level dense layers: murcl_linear_fwd / bwd_input / bwd_weight, "
@@ -313,10 +326,10 @@ def run_reference(a):
     sd_m = synth.abmil_state(a.dim, 512, 128, 128, seed=985, peak=2.0)
     sd_f = synth.full_layer_state(512, 1024, 128, seed=986)
     g = synth.gen(1)
-    for _ in range(min(a.warmup, 1)):
+    for _ in range(a.warmup):                     # warm-up steps are one patch-step each (thread pool, allocator, caches)
         O.pretrain_step(feats, clusters, sd_m, sd_f, T=1, feat_size=a.feat_size, generator=g)
     t0 = time.perf_counter()
-    steps = max(1, min(a.steps, 3))
+    steps = max(1, a.steps)
     for _ in range(steps):
         O.pretrain_step(feats, clusters, sd_m, sd_f, T=a.T, feat_size=a.feat_size, generator=g)
     dt = (time.perf_counter() - t0) / steps
@@ -324,7 +337,7 @@ def run_reference(a):
     sample = (f"{a.cpu_bags} slides per step (bounded sample of the {a.bags}-slide step), T={a.T} x 2 views, fwd+bwd, "
               f"{steps} timed steps, torch CPU fp32 oracle port, {threads} threads")
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-                      "warmup": min(a.warmup, 1), "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+                      "warmup": a.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": workload_config(a, world),
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -339,6 +352,102 @@ def vlog(msg):
     if os.environ.get("MURCL_BENCH_VERBOSE"):
         sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}\n")
         sys.stderr.flush()
+
+
+def epoch_batches(n_slides, bags, n_epochs, seed):
+    """Slide ids of every step of ``n_epochs`` epochs: a fresh shuffle per epoch, remainder dropped
+    (train_MuRCL.py:211,229-233)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_epochs):
+        perm = torch.randperm(n_slides, generator=g)
+        for i in range(n_slides // bags):
+            out.append(perm[i * bags:(i + 1) * bags].to(torch.int32))
+    return out
+
+
+def measure_fp32(a, rank, world, device):
+    """Secondary measurement: the same optimiser step in fp32 mode (the reference's precision: fp32 slide store, exact
+    FFMA GEMMs, 1e-5 parity budget), eager launches (a 0.3 s step is not launch-bound)."""
+    from murcl_b200.csr import BagStore
+    host = make_host_batch(a, seed=3000 + rank, pin=False, precision="fp32")
+    store = BagStore.empty_like_host(host, device)
+    store.copy_from_host(host)
+    job = Job(a, rank, world, device, precision="fp32")
+    slot_bag = torch.arange(a.bags, dtype=torch.int32, device=device).repeat(2)
+    for _ in range(2):
+        job.step(store, slot_bag)
+    ms = timed(lambda i: job.step(store, slot_bag), a.fp32_steps, world, device)
+    out = {"dtype": "f32", "value": round(a.bags * world * a.fp32_steps / (ms * 1e-3), 2), "unit": UNIT,
+           "ms_per_step": round(ms / a.fp32_steps, 3), "steps": a.fp32_steps, "warmup": 2, "cuda_graph": False,
+           "slide_store_dtype": "f32", "note": "same cfg3 step, fp32 storage and exact FFMA arithmetic (1e-5 parity mode)"}
+    del job, store, host
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_strong(a, rank, world, device, steps):
+    """Secondary measurement (world > 1): BASELINE config 3 verbatim - 128 bags per optimiser step over ALL ranks
+    (strong scaling: 128 / world slides per rank)."""
+    from murcl_b200.csr import BagStore
+    if a.bags % world:
+        return None
+    local = a.bags // world
+    host = make_host_batch(a, seed=5000 + rank, pin=False, n_slides=2 * local)
+    store = BagStore.empty_like_host(host, device)
+    store.copy_from_host(host)
+    job = Job(a, rank, world, device, bags=local)
+    slot_bag = torch.empty(2 * local, dtype=torch.int32, device=device)
+    table = [torch.arange(k * local, (k + 1) * local, dtype=torch.int32, device=device).repeat(2) for k in range(2)]
+    slot_bag.copy_(table[0])
+    graphed = (not a.no_graph) and job.capture(store, slot_bag)
+
+    def one(i):
+        slot_bag.copy_(table[i % 2])
+        job.run(store, slot_bag)
+
+    for i in range(3):
+        one(i)
+    ms = timed(one, steps, world, device)
+    return {"global_bags": a.bags, "bags_per_gpu": local, "value": round(a.bags * steps / (ms * 1e-3), 2), "unit": UNIT,
+            "ms_per_step": round(ms / steps, 3), "steps": steps, "scaling": "strong", "cuda_graph": bool(graphed)}
+
+
+def measure_cfg5(a, rank, world, device, iters=10):
+    """Secondary measurement: BASELINE config 5 - ONE bag of 100 000 patches x 1024-d through CLAM_SB (gated attention,
+    bf16 mode), its rows sharded over the ranks (`CLAM_SB.shard_bags`): local encoder + fused pooling, one all-gather
+    of the pooling partials, backward without a collective, then the gradient all-reduce."""
+    from murcl_b200 import dist as mdist
+    from murcl_b200 import synth
+    from murcl_b200.dropin import clam
+    n_total, dim = 100000, 1024
+    lo, hi = mdist.shard_range(n_total, rank, world)
+    g = torch.Generator().manual_seed(7000 + rank)
+    x = torch.clamp_min(0.5 * torch.randn(hi - lo, dim, generator=g) + 0.3, 0).to(device)
+    m = clam.CLAM_SB(gate=True, size_arg="small", in_dim=dim, precision="bf16")
+    m.load_state_dict(synth.clam_state(dim, "small", True, False, 2, seed=71, peak=3.0))
+    m = m.to(device).eval()
+    if world > 1:
+        m.shard_bags(True)
+    params = [p for p in m.parameters()]
+    cot = torch.randn(1, 512, generator=torch.Generator().manual_seed(7)).to(device)
+
+    def one(_i):
+        for p in params:
+            p.grad = None
+        out, _ = m([x])
+        (out * cot).sum().backward()
+        if world > 1:
+            mdist.allreduce_grads(params)
+
+    for i in range(3):
+        one(i)
+    ms = timed(one, iters, world, device)
+    per = ms / iters
+    return {"workload": "cfg5: one bag of 100000 x 1024 patches, CLAM_SB small (gated), bf16 mode, fwd+bwd", "n_gpus": world,
+            "rows_per_gpu": hi - lo, "ms_per_bag": round(per, 3), "bags_per_s": round(1e3 / per, 1),
+            "patches_per_s": round(n_total / (per * 1e-3), 0), "iters": iters,
+            "sharding": "rows of the bag split over the ranks; pooling partials merged by one all-gather" if world > 1 else "whole bag on one GPU"}
 
 
 def main():
@@ -360,75 +469,122 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     vlog("process group up")
     from murcl_b200 import _lib
-    from murcl_b200.csr import BagStore
+    from murcl_b200.csr import ResidentSlides
     _lib.load()
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
         peaks = json.loads(pk.read_text())
 
-    host = [make_host_batch(a, seed=1000 + 10 * rank + i) for i in range(2)]
-    stores = [BagStore.empty_like_host(h, device) for h in host]
-    for s, h in zip(stores, host):
-        s.copy_from_host(h)
+    if a.dataset_slides < 2 * a.bags:
+        raise SystemExit("--dataset-slides must hold at least two batches (different slides on consecutive steps)")
+    host = make_host_batch(a, seed=1000 + 10 * rank, n_slides=a.dataset_slides)       # the rank's dataset shard, pinned
+    slides = ResidentSlides(host, device)
+    slides.ensure(range(a.dataset_slides))
+    store = slides.store
     torch.cuda.synchronize()
-    vlog("host batches staged, stores on device")
+    vlog("dataset shard staged (pinned) and resident")
     job = Job(a, rank, world, device)
     vlog("job built")
+    steps_per_epoch = a.dataset_slides // a.bags
+    batches = epoch_batches(a.dataset_slides, a.bags, max(2, -(-(a.steps + a.warmup) // steps_per_epoch)), seed=77 + rank)
+    table = torch.stack([b.repeat(2) for b in batches]).to(device)              # [n_batches, 2B] slot -> slide
+    slot_bag = torch.empty(2 * a.bags, dtype=torch.int32, device=device)        # static buffer the graph reads
+    slot_bag.copy_(table[0])
 
     # ---- device-resident throughput --------------------------------------------------------------
-    graphed = (not a.no_graph) and job.capture(stores)
+    graphed = (not a.no_graph) and job.capture(store, slot_bag)
     vlog(f"graph capture: {graphed}")
+
+    def resident_step(i):
+        slot_bag.copy_(table[i % table.shape[0]])          # device-to-device: this step's slide ids
+        job.run(store, slot_bag)
+
     for i in range(a.warmup):
-        job.run(stores[i % 2])
+        resident_step(i)
     torch.cuda.synchronize()
     vlog("warm-up done")
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
     l0 = _lib.launch_count()
-    ms = timed(lambda i: job.run(stores[i % 2]), a.steps, world, device)
+    ms = timed(lambda i: resident_step(a.warmup + i), a.steps, world, device)
     launches = job.launches_per_step * a.steps if graphed else _lib.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     value = a.bags * world * a.steps / (ms * 1e-3)
     vlog(f"timed region done: {ms / a.steps:.2f} ms/step")
 
-    # ---- end to end from pinned host buffers -------------------------------------------------------
+    # ---- end to end: finite dataset shard on the host, resident slide cache ---------------------------
     e2e = None
     if not a.no_e2e:
         copy_stream = torch.cuda.Stream(device)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
-        h2d = host[0].nbytes
+        plan = epoch_batches(a.dataset_slides, a.bags, a.e2e_epochs, seed=991 + rank)
+        n_e2e = len(plan)
+        ids_pinned = torch.stack([b.repeat(2) for b in plan]).pin_memory()
+        ready = [torch.cuda.Event() for _ in range(n_e2e)]
+        h2d = [0] * n_e2e
         losses = []
+        marks = {}
 
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[i % 2])
-                stores[i % 2].copy_from_host(host[i % 2])
-                ready[i % 2].record(copy_stream)
+                h2d[i] += slides.ensure(plan[i].tolist())     # first touch: the slide's rows cross PCIe once
+                ready[i].record(copy_stream)
 
         def e2e_step(i):
             if i == 0:
                 prefetch(0)
-            if i + 1 < a.e2e_steps:
-                prefetch(i + 1)                      # next batch's H2D overlaps this step's compute
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            loss = job.run(stores[i % 2])
-            freed[i % 2].record()
-            losses.append(float(loss.item()))        # D2H read of the step's result
+            if i + 1 < n_e2e:
+                prefetch(i + 1)                                # next batch's missing slides overlap this step's compute
+            torch.cuda.current_stream().wait_event(ready[i])
+            slot_bag.copy_(ids_pinned[i], non_blocking=True)   # H2D: the step's slide ids
+            h2d[i] += ids_pinned[i].numel() * 4
+            loss = job.run(store, slot_bag)
+            losses.append(float(loss.item()))                  # D2H read of the step's result
+            if i + 1 == steps_per_epoch or i + 1 == n_e2e:
+                marks[i + 1] = time.perf_counter()
 
-        for f in freed:
-            f.record()
-        ms_e2e = timed(e2e_step, a.e2e_steps, world, device)
-        e2e = {"value": round(a.bags * world * a.e2e_steps / (ms_e2e * 1e-3), 2), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": a.e2e_steps,
-               "ms_per_step": round(ms_e2e / a.e2e_steps, 3),
-               "note": "per step: H2D of the step's slides (CSR features + cluster ids) from pinned memory on a copy stream, "
-                       "double-buffered against compute; loss.item() each step"}
+        slides.evict_all()                                     # cold start: nothing is resident
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        ms_e2e = timed(e2e_step, n_e2e, world, device)
+        cold_s = marks[steps_per_epoch] - t_start              # host clock: every step ends with loss.item()
+        warm_s = marks[n_e2e] - marks[steps_per_epoch]
+        warm_steps = n_e2e - steps_per_epoch
+        e2e = {"value": round(a.bags * world * n_e2e / (ms_e2e * 1e-3), 2), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(h2d) / n_e2e), "d2h_bytes_per_step": 4, "steps": n_e2e,
+               "ms_per_step": round(ms_e2e / n_e2e, 3), "epochs": a.e2e_epochs, "steps_per_epoch": steps_per_epoch,
+               "h2d_bytes_total": int(sum(h2d)),
+               "cold_epoch": {"steps": steps_per_epoch, "ms_per_step": round(cold_s * 1e3 / steps_per_epoch, 3),
+                              "value": round(a.bags * world * steps_per_epoch / cold_s, 2),
+                              "h2d_bytes_per_step": int(sum(h2d[:steps_per_epoch]) / steps_per_epoch)},
+               "steady_state": ({"steps": warm_steps, "ms_per_step": round(warm_s * 1e3 / warm_steps, 3),
+                                 "value": round(a.bags * world * warm_steps / warm_s, 2),
+                                 "h2d_bytes_per_step": int(sum(h2d[steps_per_epoch:]) / warm_steps)} if warm_steps else None),
+               "note": "finite dataset shard in pinned host memory; resident slide cache: a slide is uploaded (copy stream, one "
+                       "step ahead) the first time a step touches it, later steps upload only their slide-id list; the timed "
+                       "region covers all epochs including the cold first one; loss.item() every step; cold/steady splits are "
+                       "rank-0 host-clock marks inside the device-timed region"}
 
-    roof = roofline_probe(job, stores[0], peaks)      # every rank runs it: the step contains collectives
+    roof = roofline_probe(job, store, slot_bag, peaks)      # every rank runs it: the step contains collectives
     vlog("roofline probe done")
+
+    secondary = {}
+    if not a.no_secondary:
+        del job
+        torch.cuda.empty_cache()
+        if world > 1:
+            secondary["strong_scaling"] = measure_strong(a, rank, world, device, a.steps)
+        else:
+            secondary["strong_scaling"] = {"global_bags": a.bags, "bags_per_gpu": a.bags, "value": round(value, 2), "unit": UNIT,
+                                           "ms_per_step": round(ms / a.steps, 3), "scaling": "strong",
+                                           "note": "at 1 GPU the strong-scaling workload is the headline workload"}
+        vlog("strong scaling done")
+        secondary["cfg5"] = measure_cfg5(a, rank, world, device)
+        vlog("cfg5 done")
+        if a.fp32_steps > 0 and a.precision == "bf16":
+            secondary["fp32_mode"] = measure_fp32(a, rank, world, device)
+        vlog("fp32 mode done")
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu, _ = cpu_baseline(a)
@@ -440,6 +596,7 @@ def main():
                "config": dict(workload_config(a, world), cuda_graph=bool(graphed)), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roof, "cpu_baseline": cpu,
                "bag_passes_per_s": round(value * a.T * 2, 1)}
+        out.update(secondary)
         print(json.dumps(out), flush=True)
     if world > 1:
         # Tear down without ncclCommDestroy: destroying a communicator whose kernels live inside captured CUDA graphs

@@ -227,6 +227,59 @@ class HostBags:
         return sum(t.numel() * t.element_size() for t in (self.feats, self.patch_cluster, self.patch_rank, self.cluster_sizes))
 
 
+class ResidentSlides:
+    """A whole dataset (or a rank's shard of it) kept in HBM as ONE CSR arena, filled on first touch.
+
+    The reference copies every slide host -> device each time it is visited (train_MuRCL.py:224-227); Camelyon16's training
+    features are ~2.2 GB in bf16 (4.4 GB fp32) against 180 GB of HBM, so here a slide crosses PCIe once: ``ensure(ids)``
+    uploads the slides of a batch that are not resident yet (asynchronously, from the pinned ``HostBags`` staging, on the
+    current stream) and a step then addresses its bags through ``slot_bag`` - an index list into the arena - which is the
+    only per-step host -> device traffic in steady state.  The arena's row ranges are fixed by the dataset's patch counts,
+    so its addresses never change (CUDA-graph friendly)."""
+
+    def __init__(self, host: "HostBags", device=None):
+        self.host = host
+        self.store = BagStore.empty_like_host(host, device)
+        self.resident = np.zeros(len(host.offsets) - 1, dtype=bool)
+        self.bytes_uploaded = 0
+
+    @property
+    def num_slides(self) -> int:
+        return len(self.resident)
+
+    def ensure(self, slide_ids) -> int:
+        """Upload the not-yet-resident slides among ``slide_ids`` (features, cluster ids, ranks, cluster sizes) on the
+        current stream.  Returns the number of bytes queued (0 when everything was resident)."""
+        ids = np.unique(np.asarray(slide_ids, dtype=np.int64))
+        todo = ids[~self.resident[ids]]
+        if todo.size == 0:
+            return 0
+        h, st, off = self.host, self.store, self.host.offsets
+        moved = 0
+        # coalesce runs of consecutive slide ids into one copy per array
+        runs, start, prev = [], int(todo[0]), int(todo[0])
+        for b in todo[1:].tolist():
+            if b != prev + 1:
+                runs.append((start, prev))
+                start = b
+            prev = b
+        runs.append((start, prev))
+        for b0, b1 in runs:
+            lo, hi = off[b0], off[b1 + 1]
+            for dst, src in ((st.feats, h.feats), (st.patch_cluster, h.patch_cluster), (st.patch_rank, h.patch_rank)):
+                dst[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                moved += (hi - lo) * src.element_size() * (src.shape[1] if src.dim() == 2 else 1)
+            st.cluster_sizes[b0:b1 + 1].copy_(h.cluster_sizes[b0:b1 + 1], non_blocking=True)
+            moved += (b1 + 1 - b0) * h.cluster_sizes.shape[1] * 4
+        self.resident[todo] = True
+        self.bytes_uploaded += moved
+        return moved
+
+    def evict_all(self) -> None:
+        """Forget what is resident (the next touch uploads again): used to measure a cold epoch."""
+        self.resident[:] = False
+
+
 def load_slide(feature_file: str, cluster_file: str, num_clusters: int):
     """One slide from disk -> (features fp32 [N, D], labels int32 [N], ranks int32 [N] or None).  See
     ``HostBags.from_files`` for the formats.  Raises ``ValueError`` when the two files disagree."""

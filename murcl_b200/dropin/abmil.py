@@ -19,6 +19,7 @@ class ABMIL(nn.Module):
             raise NotImplementedError("ABMIL drop-in supports K=1 attention heads (the reference default)")
         self.dropout_p = float(dropout)
         self.precision = precision          # None -> MURCL_PRECISION env (fp32 | bf16)
+        self.shard_rows, self.shard_group = False, None      # see shard_bags()
 
         # parameter containers only: layout mirrors the reference so checkpoints load unchanged
         self.encoder = nn.Sequential(
@@ -30,12 +31,23 @@ class ABMIL(nn.Module):
         self.decoder = nn.Sequential(nn.Linear(L, L), nn.ReLU())
         self.fc = nn.Linear(L, dim_out)     # defined but never applied upstream (abmil.py:33)
 
+    def shard_bags(self, enabled=True, group=None):
+        """Intra-bag sharding (BASELINE config 5: one 100k-patch bag over 2/4/8 GPUs): every rank of ``group`` passes ITS
+        rows of each bag to ``forward`` (same number of bags, in the same order, on every rank; a rank may hold none of a
+        bag's rows only if another holds some).  Pooling partials are merged with one all-gather; the outputs are the
+        whole-bag results on every rank and the parameter gradients are per-rank partial sums (sum them with
+        ``dist.allreduce_grads``, as for data parallelism)."""
+        self.shard_rows, self.shard_group = bool(enabled), group
+        return self
+
     # ------------------------------------------------------------------------------------------
     def _meta(self, rows):
         prec = self.precision or ops.default_precision()
         meta = {"B": rows.B, "gated": False, "inv_sqrt_n": True, "dtype": ops.storage_dtype(prec)}
         if self.training and self.dropout_p > 0:
             meta["drop"] = {"enc": [self.dropout_p, self.dropout_p, 0.0], "attn": 0.0}     # abmil.py:15,18
+        if self.shard_rows:
+            meta.update(shard=True, shard_group=self.shard_group)
         return meta
 
     def _aggregate(self, x):

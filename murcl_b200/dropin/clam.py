@@ -85,7 +85,16 @@ class CLAM_SB(nn.Module):
         self.gate = gate
         self.has_dropout = bool(dropout)
         self.precision = precision
+        self.shard_rows, self.shard_group = False, None      # see shard_bags()
         initialize_weights(self)
+
+    def shard_bags(self, enabled=True, group=None):
+        """Intra-bag sharding (BASELINE config 5: one 100k-patch bag over 2/4/8 GPUs): every rank of ``group`` passes ITS
+        rows of each bag to ``forward``; pooling partials are merged with one all-gather, outputs are the whole-bag
+        results on every rank, parameter gradients are per-rank partial sums (``dist.allreduce_grads``).  The instance
+        loss needs whole bags and is refused in this mode."""
+        self.shard_rows, self.shard_group = bool(enabled), group
+        return self
 
     def relocate(self):
         """Move the sub-modules to the GPU when there is one (clam.py:86-90)."""
@@ -108,6 +117,8 @@ class CLAM_SB(nn.Module):
         if self.training and self.has_dropout:
             # Dropout(0.25) after the fc ReLU (clam.py:70-71) and after each attention branch (:26-27,46-48)
             meta["drop"] = {"enc": [0.25], "attn": 0.25}
+        if self.shard_rows:
+            meta.update(shard=True, shard_group=self.shard_group)
         return meta
 
     def _check_mode(self):

@@ -531,18 +531,28 @@ class _MILAggregate(torch.autograd.Function):
         if not attn_drop and attnpool_supported(H.shape[1], D, gated, H.dtype):
             # one pass over H: projection (tcgen05) + gating + score + online softmax + weighted sum
             uv, s, p, M, _ = attnpool_fwd(H, wab_s, bab.detach().contiguous().float(), wc_f, bc_f, offsets, row_seg, B, D,
-                                          gated, meta["inv_sqrt_n"])
+                                          gated, meta["inv_sqrt_n"] and not meta.get("shard"))
             M = M.reshape(B, -1)
         else:
             uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
             if attn_drop:
                 dropout_(uv, drop["attn"], seeds[-1:])
             s = attn_score_fwd(uv, wc_f, bc_f, D, gated)
-            p, _ = seg_softmax(s, offsets, B, 1, meta["inv_sqrt_n"])
+            p, _ = seg_softmax(s, offsets, B, 1, meta["inv_sqrt_n"] and not meta.get("shard"))
             M = seg_wsum(p, H, offsets, B, 1).reshape(B, -1)
+        shard = bool(meta.get("shard"))
+        inv_sqrt_bwd = meta["inv_sqrt_n"]
+        if shard:
+            # intra-bag sharding (BASELINE config 5): the rows of every bag are split across the ranks of
+            # meta["shard_group"]; p / M above are normalised over the LOCAL rows only.  One all-gather of (m, l, n, M_loc)
+            # per bag merges the partial softmax sums; afterwards p holds the GLOBAL weights of the local rows and M the
+            # global pooled vectors (identical on every rank).  The backward needs no collective.
+            M, p, inv_sqrt_bwd = _merge_shards(meta, offsets, row_seg, p, M, H, s)
         if _debug_save is not None:
             _debug_save.update(hs=[h.clone() for h in hs], uv=uv.clone())
         inst = meta.get("inst")
+        if inst is not None and shard:
+            raise MurclError("the instance-clustering loss ranks the instances of a whole bag: not available with row sharding")
         inst_loss = s.new_zeros((0,))
         preds = s.new_zeros((0,), dtype=torch.int32)
         saved_inst = ()
@@ -570,9 +580,13 @@ class _MILAggregate(torch.autograd.Function):
         ctx.consumed = False
         ctx.x_dtype = x.dtype
         ctx.hbits = hbits
+        ctx.inv_sqrt_bwd = inv_sqrt_bwd
+        M_out = M
+        if shard:
+            M, M_out = M          # (merged vectors without the post scale: what the backward's K_b uses, pooled output)
         ctx.save_for_backward(offsets, row_seg, wab_s, wc_f, uv, p, M, *hs, *enc_w, *saved_inst)
         ctx.mark_non_differentiable(p, s, preds)
-        return M, p, s, inst_loss, preds
+        return M_out, p, s, inst_loss, preds
 
     @staticmethod
     def backward(ctx, dM, _dp, _ds, dinst, _dpreds):
@@ -595,9 +609,9 @@ class _MILAggregate(torch.autograd.Function):
         if attnpool_bwd_supported(L, D, gated, H.dtype):
             # one pass over H: t_n = dM.h_n, ds, d(pre-activation) over uv, dwc / bias column sums
             dwc, dbc, dbab, _ = attnpool_bwd_(H, uv, p, M.reshape(B, L).contiguous(), dM, wc_f, offsets, row_seg, B, D, gated,
-                                              meta["inv_sqrt_n"], q_attn)
+                                              ctx.inv_sqrt_bwd, q_attn)
         else:
-            ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, meta["inv_sqrt_n"])
+            ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, ctx.inv_sqrt_bwd)
             dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated, q_attn)    # uv now holds d(pre-activation)
         dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
         hbits = ctx.hbits
@@ -640,6 +654,23 @@ class _MILAggregate(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = dz.to(ctx.x_dtype)
         return (dx, None, None, None, dwab, dbab, dwc.reshape(1, -1), dbc, d_inst_w, d_inst_b, *grads_enc)
+
+
+def _merge_shards(meta, offsets, row_seg, p_loc, M_loc, H, s):
+    """Local pooling partials -> global attention weights and pooled vectors (``dist.merge_pool_partials``).  Returns
+    ``((M_merged, M_out), p_global, False)``: ``M_out = post * M_merged`` is the module output, ``M_merged`` what the
+    backward's ``K_b = dM . M / post`` needs (with the post scale folded into ``p`` the kernel runs with inv_sqrt_n off)."""
+    from . import dist as mdist
+    B = meta["B"]
+    # (m, l) of the local softmax: recomputed from s and p would cost a pass; both pooling paths return the local
+    # normalisation, so m_b = max s, l_b = sum exp(s - m_b) are taken from one segmented softmax over the raw scores
+    _, stats = seg_softmax(s, offsets, B, 1, False)
+    m, l = stats[:, 0, 0].contiguous(), stats[:, 0, 1].contiguous()
+    n_loc = (offsets[1:] - offsets[:-1]).to(torch.float32)
+    M_merged, scale, n_tot = mdist.merge_pool_partials(m, l, M_loc.reshape(B, -1).float(), n_loc, meta.get("shard_group"))
+    post = torch.rsqrt(n_tot.clamp_min(1.0)) if meta["inv_sqrt_n"] else torch.ones_like(n_tot)
+    p = (p_loc * (scale * post)[row_seg.long()]).contiguous()
+    return (M_merged.contiguous(), (M_merged * post.unsqueeze(1)).contiguous()), p, False
 
 
 @torch.no_grad()

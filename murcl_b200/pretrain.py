@@ -33,9 +33,9 @@ def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dty
     """Both views of a patch-step through one packer pass: ``2B`` output slots over ``B`` bags.  Returns the
     ``[2B, feat_size, D]`` tensor; rows ``[0,B)`` are view 0, ``[B,2B)`` view 1."""
     actions, lams, perms = draw
-    B = store.num_bags
     if slot_bag is None:
-        slot_bag = torch.arange(B, dtype=torch.int32, device=store.device).repeat(2)
+        slot_bag = torch.arange(store.num_bags, dtype=torch.int32, device=store.device).repeat(2)
+    B = slot_bag.numel() // 2
     act = torch.cat([a.to(torch.float32) for a in actions], 0)
     lam = torch.cat([l.reshape(-1) for l in lams], 0)
     perm = torch.cat([perms[0].reshape(-1), perms[1].reshape(-1) + B], 0)     # each view mixes within itself
@@ -57,20 +57,29 @@ def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
 
 def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_size: int = 1024, alpha: float = 0.9,
                   stage: int = 1, ppo=None, memories=None, draws: Optional[Sequence[Draw]] = None,
-                  precision: Optional[str] = None, backward: bool = True, eps=None, keep_memory: bool = False):
+                  precision: Optional[str] = None, backward: bool = True, eps=None, keep_memory: bool = False,
+                  slot_bag: Optional[torch.Tensor] = None):
     """Returns ``(loss, per-step losses)``.  ``stage`` follows train_MuRCL.py: 1 = random actions; 3 = the PPO actor
     chooses the actions of patch-steps >= 1 (the actor is not updated, :292-295); 2 = the same rollout under ``no_grad``
     with the MIL model frozen, then ``ppo.update(m)`` for each view's memory instead of the optimiser step (:244-247,
     :296-298).  ``draws`` injects the random numbers (parity tests): ``draws[t] = (actions | None, lams, perms)`` -
     ``None`` actions at ``t >= 1`` in stages 2/3 mean "ask the actor", with ``eps[t]`` (one ``[B, K]`` tensor per view) as
-    its Gaussian draws.  ``keep_memory`` leaves the rollout in ``memories`` (the reference clears it, :301-302)."""
+    its Gaussian draws.  ``keep_memory`` leaves the rollout in ``memories`` (the reference clears it, :301-302).
+    ``slot_bag`` (int32 ``[2B]`` on the device: the store's bag index of every packed slot, view 0 then view 1) selects
+    the step's B slides out of a larger resident store (``csr.ResidentSlides``); default: all bags of ``store``."""
     if stage not in (1, 2, 3):
         raise ValueError("train_stage must be 1, 2 or 3")
     if stage != 1 and (ppo is None or memories is None):
         raise ValueError("stages 2 and 3 need the PPO object and one Memory per view")
-    B, K, dev = store.num_bags, store.K, store.device
+    K, dev = store.K, store.device
     dt = ops.storage_dtype(precision or ops.default_precision())
-    slot_bag = torch.arange(B, dtype=torch.int32, device=dev).repeat(2)
+    if slot_bag is None:
+        B = store.num_bags
+        slot_bag = torch.arange(B, dtype=torch.int32, device=dev).repeat(2)
+    else:
+        if slot_bag.dtype != torch.int32 or slot_bag.dim() != 1 or slot_bag.numel() % 2:
+            raise ValueError("slot_bag must be an int32 vector of 2 * B store indices")
+        B = slot_bag.numel() // 2
     losses = []
     states = None
     sim_last = None

@@ -804,3 +804,64 @@ def test_pretrain_step_golden(golden):
             assert_close(sample(gf[key[7:]].numpy()), v, 3e-4, key, floor=1e-5)
             n += 1
     assert n >= 10
+
+
+# ------------------------------------------------------------------------------------------------
+# resident slide cache, slot_bag addressing, row-sharded bags
+# ------------------------------------------------------------------------------------------------
+def test_resident_slides_slot_bag_matches_per_batch_store():
+    """csr.ResidentSlides: slides uploaded on first touch into one arena; a step addresses its slides through slot_bag.
+    The packed batch must be bit-identical to packing a store built from just those slides (get_feats, datasets.py:274-308)."""
+    from murcl_b200.csr import BagStore, HostBags, ResidentSlides
+    sizes = [300, 40, 1000, 65, 7, 512]
+    k, d, fs = 5, 16, 64
+    feats, clusters, labels = synth.make_bags(sizes, d, k, seed=201)
+    res = ResidentSlides(HostBags(feats, labels, k, pin=True), DEV)
+    pick = [4, 1, 2]
+    moved = res.ensure(pick)
+    assert moved == sum(sizes[i] for i in pick) * (d * 4 + 8) + len(pick) * k * 4
+    assert res.ensure(pick) == 0 and res.ensure([2, 5]) == sizes[5] * (d * 4 + 8) + k * 4
+    g = synth.gen(202)
+    act = torch.rand(2 * len(pick), k, generator=g).to(DEV)
+    lam = (0.9 + 0.1 * torch.rand(2 * len(pick), generator=g)).to(DEV)
+    perm = torch.cat([torch.randperm(3, generator=g), torch.randperm(3, generator=g) + 3]).to(DEV)
+    slot_bag = torch.tensor(pick, dtype=torch.int32, device=DEV).repeat(2)
+    got = res.store.pack(act, fs, lam, perm, torch.float32, slot_bag)
+    small = BagStore.from_cluster_lists([feats[i] for i in pick], [clusters[i] for i in pick], DEV)
+    want = small.pack(act, fs, lam, perm, torch.float32, torch.arange(3, dtype=torch.int32, device=DEV).repeat(2))
+    assert torch.equal(got, want)
+    for v in range(2):        # and against the oracle's list slicing + mixup of each view
+        x, _ = O.get_feats([feats[i] for i in pick], [clusters[i] for i in pick], act[3 * v:3 * v + 3].cpu(), fs)
+        x = O.mixup_apply(x, lam[3 * v:3 * v + 3].cpu().reshape(-1, 1), (perm[3 * v:3 * v + 3] - 3 * v).cpu())
+        assert torch.equal(got[3 * v:3 * v + 3].cpu(), x)
+
+
+@pytest.mark.parametrize("kind", ["clam", "abmil"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_row_sharded_mode_single_rank_is_identity(kind, precision):
+    """shard_bags() without a process group: the merge of pooling partials is the identity, so values and gradients must
+    equal the un-sharded model's (the 2-rank merge is covered on CPU by tests/test_dist_gloo.py and on GPUs by
+    tools/check_sharded_model.py)."""
+    from murcl_b200.dropin import abmil, clam
+
+    def build():
+        if kind == "clam":
+            return _load(clam.CLAM_SB(gate=True, size_arg="small", in_dim=64, precision=precision),
+                         synth.clam_state(64, "small", True, False, 2, seed=301, peak=3.0)).eval()
+        return _load(abmil.ABMIL(64, precision=precision), synth.abmil_state(64, 512, 128, 2, seed=302, peak=2.0)).eval()
+
+    feats, _, _ = synth.make_bags([700, 33, 1500], 64, 3, seed=303)
+    cot = torch.randn(3, 512, generator=synth.gen(304)).to(DEV)
+    a, b = build(), build().shard_bags(True)
+    outs = []
+    for m in (a, b):
+        out, _ = m([f.to(DEV) for f in feats])
+        (out * cot).sum().backward()
+        outs.append(out)
+    tol = 1e-6 if precision == "fp32" else 1e-3
+    assert_close(outs[1], outs[0], tol, "sharded vs whole")
+    assert_close(b.last_attention, a.last_attention, tol, "attention")
+    ga, gb = _grads(a), _grads(b)
+    for n in ga:
+        if not n.startswith(("fc.", "classifiers", "instance_classifiers")):
+            assert_close(gb[n], ga[n], 50 * tol, n, floor=1e-1 if _zero_grad_key(n) else 1e-6)   # atomics: summation order

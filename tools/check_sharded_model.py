@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""BASELINE config 5 through the drop-in model classes: ONE bag of N x 1024 patches, rows split over the ranks
+(`CLAM_SB.shard_bags` / `ABMIL.shard_bags`).  Every rank runs the encoder and the fused pooling on its rows, one all-gather
+merges the pooling partials, the backward needs no collective, gradients are all-reduced.  Rank 0 compares the bag vector
+and the summed parameter gradients with the SAME model run un-sharded on the whole bag on its own GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded_model.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from murcl_b200 import dist as mdist, synth  # noqa: E402
+from murcl_b200.dropin import abmil, clam  # noqa: E402
+
+
+def build(kind, dim, precision, dev):
+    if kind == "clam":
+        m = clam.CLAM_SB(gate=True, size_arg="small", in_dim=dim, precision=precision)
+        m.load_state_dict(synth.clam_state(dim, "small", True, False, 2, seed=71, peak=3.0))
+    else:
+        m = abmil.ABMIL(dim, precision=precision)
+        m.load_state_dict(synth.abmil_state(dim, 512, 128, 2, seed=31, peak=2.0))
+    return m.to(dev).eval()
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    if world > 1:
+        dist.init_process_group("nccl")
+    dev = "cuda"
+    N, dim = int(os.environ.get("ROWS", 100000)), 1024
+    sizes = [N, 2500]                                             # the big bag plus a small one riding along
+    feats, _, _ = synth.make_bags(sizes, dim, 3, seed=72)
+    cot = torch.randn(len(sizes), 512, generator=synth.gen(73)).to(dev)
+    ok = True
+    for kind in ("clam", "abmil"):
+        for precision, tol, gtol in (("bf16", 2e-2, 6e-2), ("fp32", 1e-5, 2e-4)):
+            m = build(kind, dim, precision, dev).shard_bags(world > 1)
+            local = []
+            for f in feats:
+                lo, hi = mdist.shard_range(f.shape[0], rank, world)
+                local.append(f[lo:hi].to(dev))
+            out, _ = m(local)
+            (out * cot).sum().backward()
+            params = [p for p in m.parameters() if p.grad is not None]
+            mdist.allreduce_grads(params)
+            torch.cuda.synchronize()
+            if rank == 0:
+                ref = build(kind, dim, precision, dev)
+                want, _ = ref([f.to(dev) for f in feats])
+                (want * cot).sum().backward()
+                err = float((out - want).abs().max() / want.abs().max())
+                gerr = 0.0
+                for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+                    if p.grad is None or q.grad is None or n.endswith(("attention.2.bias", "attention_c.bias")):
+                        continue
+                    gerr = max(gerr, float((p.grad - q.grad).abs().max() / q.grad.abs().max().clamp_min(1e-6)))
+                good = err <= tol and gerr <= gtol
+                ok = ok and good
+                print(f"{kind:5s} {precision}: one {N} x {dim} bag over {world} GPU(s): rel err bag vector {err:.1e}, "
+                      f"gradients {gerr:.1e}: {'OK' if good else 'MISMATCH'}")
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.broadcast(flag, 0)
+        ok = bool(flag.item())
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
