@@ -163,7 +163,11 @@ class Job:
         else:
             self.crit = losses.NT_Xent(self.bags, 1.0)
         self.params = list(self.model.parameters()) + list(self.fc.parameters())
-        self.opt = torch.optim.Adam(self.params, lr=1e-4, weight_decay=1e-5, capturable=True)
+        # one flat fp32 parameter / gradient / bf16-shadow arena: gradients are summed inside the kernels, one memset
+        # clears them, one cast refreshes the bf16 weights, one all-reduce exchanges them, Adam updates one tensor
+        from murcl_b200.arena import ParamArena
+        self.arena = ParamArena(self.params, shadow_dtype=torch.bfloat16 if self.precision == "bf16" else None)
+        self.opt = torch.optim.Adam(self.arena.optimizer_params(), lr=1e-4, weight_decay=1e-5, capturable=True)
         self.mdist = mdist
         self.graphs = {}
         self.launches_per_step = None
@@ -181,7 +185,9 @@ class Job:
             self.graphs[id(store)] = g
             self.launches_per_step = g.launches
         except Exception as e:                                  # noqa: BLE001 - report and fall back to eager launches
-            sys.stderr.write(f"[bench] rank {self.rank}: CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
+            import traceback
+            sys.stderr.write(f"[bench] rank {self.rank}: CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n"
+                             + "".join(traceback.format_exc().splitlines(keepends=True)[-14:]))
             ok = False
         torch.cuda.synchronize()
         if self.world > 1:
@@ -198,13 +204,14 @@ class Job:
 
     def step(self, store, slot_bag):
         from murcl_b200 import pretrain
-        self.opt.zero_grad(set_to_none=True)
+        self.arena.zero_grad()
         loss, _ = pretrain.pretrain_step(store, self.model, self.fc, self.crit, T=self.a.T, feat_size=self.a.feat_size,
                                          alpha=0.9, stage=3, ppo=self.ppo, memories=self.memories,
                                          precision=self.precision, slot_bag=slot_bag)
         if self.world > 1:
-            self.mdist.allreduce_grads(self.params)
+            self.arena.allreduce()
         self.opt.step()
+        self.arena.refresh()
         return loss
 
 

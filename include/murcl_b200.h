@@ -105,10 +105,13 @@ int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, i
                            int dtype, int backend, void* stream);
 
 /* dw[N,K] (fp32) = dy[M,N]^T . x[M,K], db[N] (fp32, may be NULL) = column sums of dy.
- * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats. */
+ * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats.  accumulate != 0 ADDS to the existing
+ * contents of dw / db instead of overwriting them: the T x 2 bag passes of one optimiser step (train_MuRCL.py:291-295:
+ * one backward over all patch-steps) sum their weight gradients inside the split-K reduction / column-sum kernels, in a
+ * persistent gradient buffer (murcl_b200/arena.py), with no separate accumulation kernel. */
 int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K);
 int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K,
-                            int dtype, int backend, float* workspace, void* stream);
+                            int dtype, int backend, float* workspace, int accumulate, void* stream);
 
 /* ---- (2) attention pooling: abmil.py:38-42, clam.py:37-60,139-170 --------------------- */
 
@@ -222,10 +225,18 @@ int murcl_clam_inst_ce_bwd(const float* rows, const float* dlogits, const float*
 
 /* z fp32 [2B,d]: rows [0,B) view i, [B,2B) view j.  loss[1] = mean_a(LSE_{b!=a} s_ab - s_a,pos(a)),
  * s = cos/tau; dz[2B,d] = d loss / d z (NULL to skip); cos_pair[B] = cos(z_i[b], z_j[b]) (NULL to
- * skip).  workspace: murcl_ntxent_workspace(B, d) floats (normalised rows, the [2B,2B] Gram matrix, scratch). */
+ * skip).  workspace: murcl_ntxent_workspace(B, d) floats.  For d % 4 == 0, d <= 256 two kernels do everything (row
+ * log-sum-exp + loss, then coefficient tiles x rows with the normalisation backward) and no [2B,2B] matrix is stored. */
 int64_t murcl_ntxent_workspace(int B, int d);
 int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
                          float* workspace, void* stream);
+/* The same loss with the gradient restricted to a SLAB of samples: dz rows [b0, b0+nb) and [B+b0, B+b0+nb) are written,
+ * all other rows of dz are left untouched.  loss and cos_pair cover the whole batch.  Data parallelism: every
+ * rank evaluates the loss over the all-gathered global batch but needs only the gradient rows of its own samples, so the
+ * O((2B)^2 d) gradient contraction shrinks by the number of ranks and no second collective is needed.  Needs d % 4 == 0,
+ * d <= 256 and a 16-byte aligned z unless the slab is the whole batch. */
+int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, int b0, int nb, float* loss, float* dz,
+                              float* cos_pair, float* workspace, void* stream);
 
 /* ---- (5) recurrent heads: rlmil.py:66-97 (actor), :187-220 (Full_layer) --------------- */
 

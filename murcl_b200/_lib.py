@@ -33,7 +33,7 @@ SIGNATURES = {
     "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p, _p]),
     "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _p, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),
-    "murcl_linear_bwd_weight": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _p, _p]),
+    "murcl_linear_bwd_weight": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _p, _i, _p]),
     "murcl_attn_score_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p]),
     "murcl_seg_softmax": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "murcl_attnpool_supported": (_i, [_i, _i, _i, _i]),
@@ -56,6 +56,7 @@ SIGNATURES = {
     "murcl_clam_inst_ce_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "murcl_ntxent_workspace": (_l, [_i, _i]),
     "murcl_ntxent_fwd_bwd": (_i, [_p, _i, _i, _f, _p, _p, _p, _p, _p]),
+    "murcl_ntxent_fwd_bwd_slab": (_i, [_p, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p]),
     "murcl_gru_cell_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_gru_cell_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_actor_head": (_i, [_p, _p, _f, _p, _p, _p, _i, _i, _p]),

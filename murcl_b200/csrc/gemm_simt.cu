@@ -166,14 +166,26 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(GemmParams p) {
   }
 }
 
-// Sum split-K partials: out[i] = sum_z ws[z*stride + i].
+// Sum split-K partials: out[i] (+)= sum_z ws[z*stride + i].  `accumulate` adds to the existing contents: weight gradients
+// of the T patch-steps of an optimiser step land in ONE persistent gradient buffer without a separate add kernel.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t stride,
-                                                            float* __restrict__ out, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                            float* __restrict__ out, int64_t n, int accumulate, int vec_ok) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += ws[z * stride + i];
-  out[i] = s;
+  if (i + 4 <= n && vec_ok) {
+    float4 s = accumulate ? *reinterpret_cast<const float4*>(out + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + z * stride + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
+  } else {
+    for (int64_t j = i; j < n && j < i + 4; ++j) {
+      float s = accumulate ? out[j] : 0.f;
+      for (int z = 0; z < splits; ++z) s += ws[z * stride + j];
+      out[j] = s;
+    }
+  }
 }
 
 // Split-K tail for the small-M dense layers: sum the partials, then the same fused epilogue as the main kernel.
@@ -217,8 +229,9 @@ int launch_relu_bits(const void* y, int64_t M, int N, int dtype, unsigned long l
   return check_launch("relu_bits_kernel");
 }
 
-int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st) {
-  splitk_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws, splits, stride, out, n);
+int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st, int accumulate) {
+  const int vec_ok = (((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && (stride & 3) == 0) ? 1 : 0;
+  splitk_reduce_kernel<<<ceil_div(n, 1024), 256, 0, st>>>(ws, splits, stride, out, n, accumulate, vec_ok);
   return check_launch("splitk_reduce_kernel");
 }
 
@@ -409,12 +422,13 @@ static int bwd_weight_splits(int64_t M, int N, int K) {
 
 int64_t simt_linear_bwd_weight_workspace(int64_t M, int N, int K) {
   const int s = bwd_weight_splits(M, N, K);
-  return s > 1 ? (int64_t)s * N * K : 0;
+  return (int64_t)(s > 1 ? s : 1) * N * K;          // one slab even without a split: the accumulate mode goes through it
 }
 
 int simt_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, int N, int K, int dtype,
-                           float* workspace, cudaStream_t st) {
+                           float* workspace, cudaStream_t st, int accumulate) {
   const int splits = bwd_weight_splits(M, N, K);
+  const bool via_ws = splits > 1 || accumulate;
   GemmParams p{};
   // C = dw [N, K]; reduction over rows M; A(m'=n, k'=m) = dy[m, n]; B(n'=k_in, k'=m) = x[m, k_in].
   p.A = dy; p.B = x; p.M = N; p.N = K; p.K = M; p.lda = N; p.ldb = K; p.ldc = K;
@@ -422,16 +436,16 @@ int simt_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, 
   chunk = (chunk + BK - 1) / BK * BK;
   p.k_chunk = chunk;
   p.split_stride = (int64_t)N * K;
-  p.C = splits > 1 ? (void*)workspace : (void*)dw;
-  if (splits > 1 && workspace == nullptr) {
-    set_error("linear_bwd_weight: workspace required (%d splits)", splits);
+  p.C = via_ws ? (void*)workspace : (void*)dw;
+  if (via_ws && workspace == nullptr) {
+    set_error("linear_bwd_weight: workspace required (%d splits, accumulate=%d)", splits, accumulate);
     return MURCL_EINVAL;
   }
   int rc = (dtype == MURCL_F32) ? launch<float, float, float, false, false>(p, splits, st)
                                 : launch<__nv_bfloat16, __nv_bfloat16, float, false, false>(p, splits, st);
-  if (rc != MURCL_OK || splits == 1) return rc;
+  if (rc != MURCL_OK || !via_ws) return rc;
   const int64_t n = (int64_t)N * K;
-  return launch_splitk_reduce(workspace, splits, n, dw, n, st);
+  return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);
 }
 
 }  // namespace murcl

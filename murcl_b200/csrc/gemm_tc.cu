@@ -28,7 +28,7 @@
 namespace murcl {
 
 // defined in gemm_simt.cu
-int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st);
+int launch_splitk_reduce(const float* ws, int splits, int64_t stride, float* out, int64_t n, cudaStream_t st, int accumulate);
 
 namespace tc {
 
@@ -855,7 +855,8 @@ int64_t tc_linear_bwd_weight_workspace(int64_t M, int N, int K) {
   return (int64_t)splits * N * K;
 }
 
-int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, int N, int K, float* workspace, cudaStream_t st) {
+int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, int N, int K, float* workspace, cudaStream_t st,
+                         int accumulate) {
   if (!aligned16(dy) || !aligned16(x) || !aligned16(dw) || !aligned16(workspace)) {
     set_error("linear_bwd_weight(tcgen05): operands must be 16-byte aligned");
     return MURCL_EINVAL;
@@ -881,7 +882,7 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
                  : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
   if (rc != MURCL_OK) return rc;
   const int64_t n = (int64_t)N * K;
-  return launch_splitk_reduce(workspace, splits, n, dw, n, st);
+  return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);
 }
 
 }  // namespace murcl

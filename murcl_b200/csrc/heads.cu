@@ -183,11 +183,13 @@ __global__ void __launch_bounds__(256) dropout_kernel(T* __restrict__ x, int64_t
   }
 }
 
-int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st);
-  if (e != cudaSuccess) {
-    set_error("colsum: memset failed: %s", cudaGetErrorString(e));
-    return MURCL_ECUDA;
+int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st, int accumulate) {
+  if (!accumulate) {                       // the kernel adds its slices' partial sums with atomics
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st);
+    if (e != cudaSuccess) {
+      set_error("colsum: memset failed: %s", cudaGetErrorString(e));
+      return MURCL_ECUDA;
+    }
   }
   const int col_tiles = ceil_div(N, 128);
   int slices = (8 * sm_count() + col_tiles - 1) / col_tiles;
@@ -267,7 +269,7 @@ int murcl_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* s
     MURCL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, as_stream(stream)));
     return MURCL_OK;
   }
-  return colsum_impl(a, M, N, dtype, out, as_stream(stream));
+  return colsum_impl(a, M, N, dtype, out, as_stream(stream), 0);
 }
 
 int murcl_dropout(void* x, int64_t n, float p, const int64_t* seed_dev, int dtype, void* stream) {

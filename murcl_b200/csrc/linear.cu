@@ -10,7 +10,7 @@ int simt_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, co
                           const unsigned long long* relu_bits = nullptr);
 int launch_relu_bits(const void* y, int64_t M, int N, int dtype, unsigned long long* bits, cudaStream_t st);
 int64_t simt_linear_bwd_weight_workspace(int64_t, int, int);
-int simt_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, float*, cudaStream_t);
+int simt_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, float*, cudaStream_t, int accumulate);
 
 bool tc_fwd_supported(int64_t M, int N, int K, int dtype, int out_dtype);
 bool tc_bwd_input_supported(int64_t M, int N, int K, int dtype);
@@ -19,9 +19,9 @@ int tc_linear_fwd(const void*, const void*, const float*, void*, int64_t, int, i
 int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, const void*, const float*, const float*,
                         const int32_t*, float*, float, const unsigned long long*, cudaStream_t);
 int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
-int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t);
+int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t, int accumulate);
 
-int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st);
+int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st, int accumulate = 0);
 }  // namespace murcl
 
 using namespace murcl;
@@ -76,7 +76,7 @@ int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, i
   int rc = simt_linear_bwd_input(dy, w, dx, M, N, K, relu_src, row_scale, row_vec, row_seg, out_scale, dtype, as_stream(stream),
                                  nullptr, 0, bits);
   if (rc != MURCL_OK || col_sum == nullptr) return rc;
-  return colsum_impl(dx, M, K, dtype, col_sum, as_stream(stream));       // same sums, separate pass
+  return colsum_impl(dx, M, K, dtype, col_sum, as_stream(stream), 1);    // same sums, separate pass; ADDS like the fused epilogue
 }
 
 int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K) {
@@ -85,18 +85,19 @@ int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K) {
 }
 
 int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K, int dtype,
-                            int backend, float* workspace, void* stream) {
+                            int backend, float* workspace, int accumulate, void* stream) {
   MURCL_REQUIRE(dy && x && dw, "linear_bwd_weight: null pointer");
   MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_weight: bad shape");
   MURCL_REQUIRE(valid_dtype(dtype), "linear_bwd_weight: bad dtype");
   cudaStream_t st = as_stream(stream);
   if (M == 0) {
+    if (accumulate) return MURCL_OK;
     MURCL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
     if (db) MURCL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
     return MURCL_OK;
   }
   if (db) {
-    int rc = colsum_impl(dy, M, N, dtype, db, st);
+    int rc = colsum_impl(dy, M, N, dtype, db, st, accumulate);
     if (rc != MURCL_OK) return rc;
   }
   const bool tc_ok = tc_bwd_weight_supported(M, N, K, dtype);
@@ -104,8 +105,8 @@ int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db,
     set_error("linear_bwd_weight: tcgen05 path does not take M=%lld N=%d K=%d dtype=%d", (long long)M, N, K, dtype);
     return MURCL_EUNSUPPORTED;
   }
-  if (backend != MURCL_GEMM_SIMT && tc_ok) return tc_linear_bwd_weight(dy, x, dw, M, N, K, workspace, st);
-  return simt_linear_bwd_weight(dy, x, dw, M, N, K, dtype, workspace, st);
+  if (backend != MURCL_GEMM_SIMT && tc_ok) return tc_linear_bwd_weight(dy, x, dw, M, N, K, workspace, st, accumulate);
+  return simt_linear_bwd_weight(dy, x, dw, M, N, K, dtype, workspace, st, accumulate);
 }
 
 }  // extern "C"

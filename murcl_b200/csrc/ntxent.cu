@@ -168,6 +168,262 @@ __global__ void __launch_bounds__(256) ntx_finish_kernel(const float* __restrict
   }
 }
 
+
+// ================================================================================================================
+// Two-kernel form (d <= 256, d % 4 == 0: the projection widths in use).  Nothing of size [2B, 2B] touches memory.
+//
+//   ntx_lse_kernel   every CTA owns 8 rows a: streams all rows b in tiles of 64 through shared memory, normalises them
+//                    on the fly, keeps per-thread online (max, sum-exp) of s_ab over b != a, records the positive logit;
+//                    writes 1/|z_a|, lse_a, the row's loss term and cos(z_i, z_j); the last CTA to finish sums the loss
+//                    terms in a fixed order (deterministic).
+//   ntx_grad_kernel  grid (row blocks of 16 rows of the caller's SLAB, splits of the b range): recomputes the 16 x 64
+//                    score tile, turns it into the coefficients e^{s-lse_a} + e^{s-lse_b} - 2[b = pos(a)], multiplies
+//                    them with the normalised rows of the tile, adds the partial dzn rows to a scratch accumulator; the
+//                    last split of a row block takes the rows through the normalisation backward and writes dz.
+//
+// The slab (samples [b0, b0 + nb) of both views) is what data parallelism needs: every rank evaluates the loss over the
+// global batch (lse of all rows: ntx_lse_kernel, 2B x 2B x d FMAs) but only the gradient rows of its own samples
+// (2 nb x 2B x 2d FMAs) - no second collective, no redundant gradient work (utils/losses.py:24-41 differentiated).
+constexpr int NTX_RA1 = 8, NTX_RA2 = 16, NTX_TB = 64, NTX_MAXD = 256;
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ z, int B, int d, float inv_tau,
+                                                      float* __restrict__ inv_norm, float* __restrict__ lse,
+                                                      float* __restrict__ row_loss, float* __restrict__ cos_pair,
+                                                      float* __restrict__ loss, unsigned int* __restrict__ ticket) {
+  extern __shared__ __align__(16) float sm[];
+  const int R = 2 * B, ldb = d + 4;
+  float* za = sm;                               // [8][d]   normalised rows a
+  float* zb = za + NTX_RA1 * d;                 // [64][d+4] raw rows b of the tile
+  float* invb = zb + NTX_TB * ldb;              // [64]
+  float* red_m = invb + NTX_TB;                 // [8][64]
+  float* red_l = red_m + NTX_RA1 * NTX_TB;      // [8][64]
+  float* s_pos = red_l + NTX_RA1 * NTX_TB;      // [8]
+  float* inva = s_pos + NTX_RA1;                // [8]
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int a0 = blockIdx.x * NTX_RA1;
+  // rows a: warp w normalises row a0 + w
+  {
+    const int a = a0 + w;
+    float ss = 0.f;
+    if (a < R)
+      for (int j = lane; j < d; j += 32) { const float v = z[(int64_t)a * d + j]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), COS_EPS);
+    for (int j = lane; j < d; j += 32) za[w * d + j] = (a < R) ? z[(int64_t)a * d + j] * inv : 0.f;
+    if (lane == 0) { inva[w] = inv; s_pos[w] = 0.f; }
+  }
+  const int bl = t & 63, ag = t >> 6;                       // thread: column bl of the tile, rows 2ag, 2ag + 1
+  float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
+  const int ar0 = a0 + 2 * ag, ar1 = ar0 + 1;
+  const int pos0 = ar0 < B ? ar0 + B : ar0 - B, pos1 = ar1 < B ? ar1 + B : ar1 - B;
+  for (int b0 = 0; b0 < R; b0 += NTX_TB) {
+    __syncthreads();
+    for (int i = t; i < NTX_TB * (d >> 2); i += 256) {
+      const int r = i / (d >> 2), c = i % (d >> 2);
+      const float4 v = (b0 + r < R) ? *reinterpret_cast<const float4*>(z + (int64_t)(b0 + r) * d + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(zb + r * ldb + 4 * c) = v;
+    }
+    __syncthreads();
+    for (int r = w; r < NTX_TB; r += 8) {                   // norms of the tile's rows
+      float ss = 0.f;
+      for (int j = lane; j < d; j += 32) { const float v = zb[r * ldb + j]; ss = fmaf(v, v, ss); }
+      ss = warp_sum(ss);
+      if (lane == 0) invb[r] = 1.f / fmaxf(sqrtf(ss), COS_EPS);
+    }
+    __syncthreads();
+    float acc0 = 0.f, acc1 = 0.f;
+    const float* rb = zb + bl * ldb;
+    const float* ra0 = za + (2 * ag) * d;
+    const float* ra1 = ra0 + d;
+    for (int k = 0; k < d; k += 4) {
+      const float4 vb = *reinterpret_cast<const float4*>(rb + k);
+      acc0 = dot4(*reinterpret_cast<const float4*>(ra0 + k), vb, acc0);
+      acc1 = dot4(*reinterpret_cast<const float4*>(ra1 + k), vb, acc1);
+    }
+    const int b = b0 + bl;
+    if (b < R) {
+      const float sc = invb[bl] * inv_tau;
+      const float s0 = acc0 * sc, s1 = acc1 * sc;
+      if (b != ar0) { const float mn = fmaxf(m0, s0); l0 = l0 * expf(m0 - mn) + expf(s0 - mn); m0 = mn; }
+      if (b != ar1) { const float mn = fmaxf(m1, s1); l1 = l1 * expf(m1 - mn) + expf(s1 - mn); m1 = mn; }
+      if (b == pos0) s_pos[2 * ag] = s0;
+      if (b == pos1) s_pos[2 * ag + 1] = s1;
+    }
+  }
+  red_m[(2 * ag) * NTX_TB + bl] = m0; red_l[(2 * ag) * NTX_TB + bl] = l0;
+  red_m[(2 * ag + 1) * NTX_TB + bl] = m1; red_l[(2 * ag + 1) * NTX_TB + bl] = l1;
+  __syncthreads();
+  {                                                           // warp w merges the 64 partial (m, l) of row a0 + w
+    const int a = a0 + w;
+    const float ma = red_m[w * NTX_TB + lane], mb = red_m[w * NTX_TB + 32 + lane];
+    const float la = red_l[w * NTX_TB + lane], lb = red_l[w * NTX_TB + 32 + lane];
+    float m = fmaxf(ma, mb);
+    m = warp_max(m);
+    float l = (la > 0.f ? la * expf(ma - m) : 0.f) + (lb > 0.f ? lb * expf(mb - m) : 0.f);
+    l = warp_sum(l);
+    if (lane == 0 && a < R) {
+      const float e = m + logf(l);
+      lse[a] = e;
+      inv_norm[a] = inva[w];
+      row_loss[a] = e - s_pos[w];
+      if (cos_pair && a < B) cos_pair[a] = s_pos[w] / inv_tau;
+    }
+  }
+  // the last CTA sums the rows' loss terms in index order
+  __threadfence();
+  __syncthreads();
+  if (t == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float sacc = 0.f;
+    for (int i = t; i < R; i += 256) sacc += __ldcg(row_loss + i);
+    sacc = block_sum(sacc, red);
+    if (t == 0) loss[0] = sacc / (float)R;
+  }
+}
+
+// NC = d / 128 rounded up: float4 column chunks per thread in the accumulation phase.
+template <int NC>
+__global__ void __launch_bounds__(256) ntx_grad_kernel(const float* __restrict__ z, int B, int d, float inv_tau, int sb0, int nb,
+                                                       int tiles_per_split, const float* __restrict__ inv_norm,
+                                                       const float* __restrict__ lse, float* __restrict__ acc_ws,
+                                                       unsigned int* __restrict__ tickets, float* __restrict__ dz) {
+  extern __shared__ __align__(16) float sm[];
+  const int R = 2 * B, ldb = d + 4, ldg = NTX_TB + 1;
+  float* za = sm;                               // [16][d] normalised rows a
+  float* zb = za + NTX_RA2 * d;                 // [64][d+4] normalised rows b
+  float* G = zb + NTX_TB * ldb;                 // [16][65]
+  float* lse_b = G + NTX_RA2 * ldg;             // [64]
+  float* lse_a = lse_b + NTX_TB;                // [16]
+  __shared__ int a_of[NTX_RA2];
+  __shared__ bool is_last;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int r0 = blockIdx.x * NTX_RA2;                       // first local row of this block (slab rows: 2 * nb)
+  if (t < NTX_RA2) {
+    const int r = r0 + t;
+    a_of[t] = r < nb ? sb0 + r : (r < 2 * nb ? B + sb0 + (r - nb) : -1);
+  }
+  __syncthreads();
+  for (int i = t; i < NTX_RA2 * (d >> 2); i += 256) {
+    const int r = i / (d >> 2), c = i % (d >> 2);
+    const int a = a_of[r];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a >= 0) {
+      v = *reinterpret_cast<const float4*>(z + (int64_t)a * d + 4 * c);
+      const float inv = inv_norm[a];
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    }
+    *reinterpret_cast<float4*>(za + r * d + 4 * c) = v;
+  }
+  if (t < NTX_RA2) lse_a[t] = a_of[t] >= 0 ? lse[a_of[t]] : 0.f;
+  const int bl = t & 63, ag = t >> 6;                        // phase 1: column bl, rows 4ag .. 4ag + 3
+  const int j4 = t & 31, g2 = t >> 5;                        // phase 2: columns 4 j4 (+128 c), rows 2 g2, 2 g2 + 1
+  float acc[2][NC][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][c][e] = 0.f;
+  const int tile0 = blockIdx.y * tiles_per_split;
+  const int n_tiles = (R + NTX_TB - 1) / NTX_TB;
+  for (int tile = tile0; tile < tile0 + tiles_per_split && tile < n_tiles; ++tile) {
+    const int b0 = tile * NTX_TB;
+    __syncthreads();
+    for (int i = t; i < NTX_TB * (d >> 2); i += 256) {
+      const int r = i / (d >> 2), c = i % (d >> 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + r < R) {
+        v = *reinterpret_cast<const float4*>(z + (int64_t)(b0 + r) * d + 4 * c);
+        const float inv = inv_norm[b0 + r];
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      }
+      *reinterpret_cast<float4*>(zb + r * ldb + 4 * c) = v;
+    }
+    if (t < NTX_TB) lse_b[t] = (b0 + t < R) ? lse[b0 + t] : 0.f;
+    __syncthreads();
+    {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* rb = zb + bl * ldb;
+      const float* ra = za + (4 * ag) * d;
+      for (int k = 0; k < d; k += 4) {
+        const float4 vb = *reinterpret_cast<const float4*>(rb + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s4[i] = dot4(*reinterpret_cast<const float4*>(ra + i * d + k), vb, s4[i]);
+      }
+      const int b = b0 + bl;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = a_of[4 * ag + i];
+        float c = 0.f;
+        if (a >= 0 && b < R && b != a) {
+          const float s = s4[i] * inv_tau;
+          const int pos = a < B ? a + B : a - B;
+          c = expf(s - lse_a[4 * ag + i]) + expf(s - lse_b[bl]) - (b == pos ? 2.f : 0.f);
+        }
+        G[(4 * ag + i) * ldg + bl] = c;
+      }
+    }
+    __syncthreads();
+    for (int b = 0; b < NTX_TB; ++b) {
+      const float c0 = G[(2 * g2) * ldg + b], c1 = G[(2 * g2 + 1) * ldg + b];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (4 * j4 + 128 * c < d) {
+          const float4 v = *reinterpret_cast<const float4*>(zb + b * ldb + 4 * j4 + 128 * c);
+          acc[0][c][0] = fmaf(c0, v.x, acc[0][c][0]); acc[0][c][1] = fmaf(c0, v.y, acc[0][c][1]);
+          acc[0][c][2] = fmaf(c0, v.z, acc[0][c][2]); acc[0][c][3] = fmaf(c0, v.w, acc[0][c][3]);
+          acc[1][c][0] = fmaf(c1, v.x, acc[1][c][0]); acc[1][c][1] = fmaf(c1, v.y, acc[1][c][1]);
+          acc[1][c][2] = fmaf(c1, v.z, acc[1][c][2]); acc[1][c][3] = fmaf(c1, v.w, acc[1][c][3]);
+        }
+      }
+    }
+  }
+  // partial dzn rows -> scratch accumulator (rows of the slab), then the last split of the row block finishes them
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = r0 + 2 * g2 + i;
+    if (r < 2 * nb) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (4 * j4 + 128 * c < d)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) atomicAdd(acc_ws + (int64_t)r * d + 4 * j4 + 128 * c + e, acc[i][c][e]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) is_last = atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float scale = inv_tau / (float)R;
+  for (int rr = w; rr < NTX_RA2; rr += 8) {                  // one warp per row: projection through the normalisation
+    const int a = a_of[rr];
+    if (a < 0) continue;
+    const int r = r0 + rr;
+    float proj = 0.f;
+    for (int j = lane; j < d; j += 32) proj = fmaf(__ldcg(acc_ws + (int64_t)r * d + j) * scale, za[rr * d + j], proj);
+    proj = warp_sum(proj);
+    const float inv = inv_norm[a];
+    const bool clamped = inv >= 1.f / COS_EPS;               // |z| <= eps: zn = z / eps is linear in z, no projection term
+    for (int j = lane; j < d; j += 32) {
+      const float g = __ldcg(acc_ws + (int64_t)r * d + j) * scale;
+      dz[(int64_t)a * d + j] = clamped ? g * inv : (g - proj * za[rr * d + j]) * inv;
+    }
+  }
+}
+
+static bool ntx_fused_ok(int d) { return d % 4 == 0 && d <= NTX_MAXD; }
+
 }  // namespace murcl
 
 using namespace murcl;
@@ -176,17 +432,15 @@ extern "C" {
 
 int64_t murcl_ntxent_workspace(int B, int d) {
   const int64_t R = 2 * (int64_t)B;
-  return R * d /*zn*/ + 4 * R /*inv_norm, lse, row_loss, pad*/ + R * R /*gram / coefficients*/ + R * d /*C zn*/ +
-         32 * R * d /*split-K scratch of the C zn product*/;
+  const int64_t legacy = R * d /*zn*/ + 4 * R /*inv_norm, lse, row_loss, pad*/ + R * R /*gram / coefficients*/ + R * d /*C zn*/ +
+                         32 * R * d /*split-K scratch of the C zn product*/;
+  const int64_t fused = 4 * R /*inv_norm, lse, row_loss, pad*/ + R * d /*dzn accumulator*/ + R / 16 + 64 /*tickets*/;
+  return ntx_fused_ok(d) ? fused : legacy;
 }
 
-int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
-                         float* workspace, void* stream) {
-  MURCL_REQUIRE(z && loss && workspace, "ntxent: null pointer");
-  MURCL_REQUIRE(B > 0 && d > 0 && temperature > 0.f, "ntxent: bad B=%d d=%d tau=%g", B, d, (double)temperature);
-  MURCL_REQUIRE(B <= 16384, "ntxent: 2B=%d rows exceed the Gram-matrix scratch design", 2 * B);
+static int ntxent_legacy(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
+                         float* workspace, cudaStream_t st) {
   const int R = 2 * B;
-  cudaStream_t st = as_stream(stream);
   float* zn = workspace;
   float* inv_norm = zn + (int64_t)R * d;
   float* lse = inv_norm + R;
@@ -227,6 +481,61 @@ int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float*
   if (rc != MURCL_OK) return rc;
   ntx_finish_kernel<<<ceil_div(R, 8), 256, 0, st>>>(cz, zn, inv_norm, R, d, inv_tau / (float)R, dz);
   return check_launch("ntx_finish_kernel");
+}
+
+int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, int b0, int nb, float* loss, float* dz,
+                              float* cos_pair, float* workspace, void* stream) {
+  MURCL_REQUIRE(z && loss && workspace, "ntxent: null pointer");
+  MURCL_REQUIRE(B > 0 && d > 0 && temperature > 0.f, "ntxent: bad B=%d d=%d tau=%g", B, d, (double)temperature);
+  MURCL_REQUIRE(B <= 16384, "ntxent: 2B=%d rows exceed the design", 2 * B);
+  MURCL_REQUIRE(b0 >= 0 && nb >= 0 && b0 + nb <= B, "ntxent: gradient slab [%d, %d) outside the batch of %d", b0, b0 + nb, B);
+  cudaStream_t st = as_stream(stream);
+  if (!ntx_fused_ok(d) || (reinterpret_cast<uintptr_t>(z) & 15)) {
+    MURCL_REQUIRE(b0 == 0 && nb == B, "ntxent: the gradient slab needs d %% 4 == 0, d <= %d and a 16-byte aligned z", NTX_MAXD);
+    return ntxent_legacy(z, B, d, temperature, loss, dz, cos_pair, workspace, st);
+  }
+  const int R = 2 * B;
+  const float inv_tau = 1.f / temperature;
+  float* inv_norm = workspace;
+  float* lse = inv_norm + R;
+  float* row_loss = lse + R;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(row_loss + 2 * R);    // [1 + row blocks] in a slot of R/16 + 64 words
+  float* acc_ws = row_loss + 2 * R + (R / 16 + 64);                              // [2 nb, d]
+  const int row_blocks = ceil_div(2 * nb, NTX_RA2);
+  const bool want_grad = dz != nullptr && nb > 0;
+  // one memset node clears the tickets and, right behind them, the gradient accumulator
+  MURCL_CUDA(cudaMemsetAsync(tickets, 0, sizeof(float) * ((size_t)(R / 16 + 64) + (want_grad ? (size_t)2 * nb * d : 0)), st));
+  {
+    const size_t smem = sizeof(float) * (size_t)(NTX_RA1 * d + NTX_TB * (d + 4) + NTX_TB + 2 * NTX_RA1 * NTX_TB + 2 * NTX_RA1);
+    static PerDeviceOnce configured;
+    if (const int slot = configured.pending(); slot >= 0) {
+      MURCL_CUDA(cudaFuncSetAttribute(ntx_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      configured.mark(slot);
+    }
+    ntx_lse_kernel<<<ceil_div(R, NTX_RA1), 256, smem, st>>>(z, B, d, inv_tau, inv_norm, lse, row_loss, cos_pair, loss, tickets);
+    int rc = check_launch("ntx_lse_kernel");
+    if (rc != MURCL_OK || !want_grad) return rc;
+  }
+  const int n_tiles = ceil_div(R, NTX_TB);
+  int splits = ceil_div(128, row_blocks);
+  if (splits > n_tiles) splits = n_tiles;
+  if (splits < 1) splits = 1;
+  const int tiles_per_split = ceil_div(n_tiles, splits);
+  splits = ceil_div(n_tiles, tiles_per_split);
+  const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_RA2 * (NTX_TB + 1) + NTX_TB + NTX_RA2);
+  const dim3 grid(row_blocks, splits);
+  if (d <= 128)
+    ntx_grad_kernel<1><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tiles_per_split, inv_norm, lse, acc_ws, tickets + 1, dz);
+  else
+    ntx_grad_kernel<2><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tiles_per_split, inv_norm, lse, acc_ws, tickets + 1, dz);
+  return check_launch("ntx_grad_kernel");
+}
+
+int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,
+                         float* workspace, void* stream) {
+  return murcl_ntxent_fwd_bwd_slab(z, B, d, temperature, 0, B, loss, dz, cos_pair, workspace, stream);
 }
 
 }  // extern "C"

@@ -61,9 +61,7 @@ class DistributedNTXent(torch.nn.Module):
         if z_i.shape[0] != self.local_batch_size or z_j.shape[0] != self.local_batch_size:
             raise RuntimeError(f"DistributedNTXent was built for local batch {self.local_batch_size}")
         fn = self.loss_fn
-        if fn is None:
-            from . import ops
-            fn = ops.ntxent
+        b = self.local_batch_size
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             both = _GatherViews.apply(torch.stack([z_i, z_j], 0), self.group)      # [W, 2, B_local, d]
             gi = both[:, 0].reshape(-1, z_i.shape[1])
@@ -71,8 +69,13 @@ class DistributedNTXent(torch.nn.Module):
             rank = dist.get_rank(self.group)
         else:
             gi, gj, rank = z_i, z_j, 0
-        loss, cos = fn(gi, gj, float(self.temperature))
-        b = self.local_batch_size
+        if fn is None:
+            # the loss covers the global batch; only this rank's samples need gradient rows (_GatherViews.backward keeps
+            # exactly those), so the gradient contraction runs on the rank's slab of rows
+            from . import ops
+            loss, cos = ops.ntxent(gi, gj, float(self.temperature), slab=(rank * b, b))
+        else:
+            loss, cos = fn(gi, gj, float(self.temperature))
         self.last_cosine = cos[rank * b:(rank + 1) * b] if cos is not None else None
         return loss
 

@@ -105,6 +105,15 @@ def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return dst
 
 
+def cast_into(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[:] = src converted to dst's storage type (one launch; same element count)."""
+    _chk(src, "cast_into.src"); _chk(dst, "cast_into.dst")
+    if src.numel() != dst.numel():
+        raise MurclError("cast_into: element counts differ")
+    check(_lib.load().murcl_cast(_p(src), _dt(src), _p(dst), _dt(dst), src.numel(), _s()), "murcl_cast")
+    return dst
+
+
 _weight_epoch = 0
 
 
@@ -124,6 +133,9 @@ def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if w.dtype == dtype:
         d = w.detach()
         return d if d.is_contiguous() else d.contiguous()
+    sh = getattr(w, "_murcl_shadow", None)          # ParamArena: one multi-tensor cast per optimiser step keeps it fresh
+    if sh is not None and sh.dtype == dtype and sh.device == w.device:
+        return sh
     key = (w.data_ptr(), w.device, w._version, dtype, tuple(w.shape), _weight_epoch)
     hit = getattr(w, "_murcl_cast", None)
     if hit is not None and hit[0] == key:
@@ -177,19 +189,38 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
     return dx
 
 
-def linear_bwd_weight(dy, x, want_bias=True):
+def linear_bwd_weight(dy, x, want_bias=True, dw_into=None, db_into=None):
+    """(dw [N, K], db [N] | None) fp32.  ``dw_into`` / ``db_into`` (fp32, contiguous, e.g. the ``.grad`` views of a
+    ``ParamArena``) make the kernels ADD their result to those buffers (no separate accumulation launch); the returned
+    entry is then the buffer itself."""
     _chk(dy, "linear_bwd_weight.dy"); _chk(x, "linear_bwd_weight.x", dy.dtype)
     M, N = dy.shape
     K = x.shape[1]
     lib = _lib.load()
-    dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
-    db = torch.empty((N,), device=dy.device, dtype=torch.float32) if want_bias else None
+    acc = dw_into is not None
+    if acc:
+        _chk(dw_into, "linear_bwd_weight.dw_into", torch.float32)
+        if dw_into.numel() != N * K:
+            raise MurclError(f"linear_bwd_weight: dw_into has {dw_into.numel()} elements, expected {N * K}")
+        if want_bias and db_into is None:
+            raise MurclError("linear_bwd_weight: accumulating dw needs db_into as well when a bias gradient is wanted")
+    dw = dw_into if acc else torch.empty((N, K), device=dy.device, dtype=torch.float32)
+    db = None
+    if want_bias:
+        db = db_into if acc else torch.empty((N,), device=dy.device, dtype=torch.float32)
     nws = int(lib.murcl_linear_bwd_weight_workspace(M, N, K))
     ws = torch.empty((max(nws, 1),), device=dy.device, dtype=torch.float32)
     with _Timed("linear_bwd_weight" if M >= 4096 else "head_bwd_weight", 2.0 * M * N * K):
-        check(lib.murcl_linear_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), M, N, K, _dt(dy), _backend(), _p(ws), _s()),
+        check(lib.murcl_linear_bwd_weight(_p(dy), _p(x), _p(dw), _p(db), M, N, K, _dt(dy), _backend(), _p(ws), int(acc), _s()),
               "murcl_linear_bwd_weight")
     return dw, db
+
+
+def grad_target(param):
+    """The persistent fp32 gradient view the kernels accumulate into when ``param`` belongs to a ``ParamArena``
+    (murcl_b200/arena.py), else None (the gradient is returned to autograd as usual)."""
+    t = getattr(param, "_murcl_accum", None) if param is not None else None
+    return t if (t is not None and t.is_cuda) else None
 
 
 def relu_bwd(dy, y):
@@ -311,14 +342,19 @@ def attnpool_bwd_supported(L, D, gated, dtype) -> bool:
     return bool(_lib.load().murcl_attnpool_bwd_supported(int(L), int(D), int(gated), _DT[dtype]))
 
 
-def attnpool_bwd_(h, uv, p, M, dM, wc, offsets, row_seg, B, D, gated, inv_sqrt_n, drop_scale=1.0, want_ds=False):
+def attnpool_bwd_(h, uv, p, M, dM, wc, offsets, row_seg, B, D, gated, inv_sqrt_n, drop_scale=1.0, want_ds=False,
+                  into=None):
     """Fused pooling backward (murcl_attnpool_bwd): one pass over ``h``; ``uv`` becomes the gradient w.r.t. the
-    pre-activations IN PLACE.  Returns (dwc [D], dbc [1], column sums of the new uv, ds or None)."""
+    pre-activations IN PLACE.  Returns (dwc [D], dbc [1], column sums of the new uv, ds or None).  ``into`` =
+    (dwc, dbc, dpre) fp32 buffers the kernel's atomics ADD to (persistent gradient views); default: fresh zeros."""
     _chk(h, "attnpool_bwd.h"); _chk(uv, "attnpool_bwd.uv", h.dtype)
     _chk(p, "attnpool_bwd.p", torch.float32); _chk(M, "attnpool_bwd.M", torch.float32); _chk(dM, "attnpool_bwd.dM", torch.float32)
     n_rows, L = h.shape
-    buf = torch.zeros((D + 4 + uv.shape[1],), device=uv.device, dtype=torch.float32)      # one memset for all three
-    dwc, dbc, dpre = buf[:D], buf[D:D + 1], buf[D + 4:]
+    if into is not None:
+        dwc, dbc, dpre = into
+    else:
+        buf = torch.zeros((D + 4 + uv.shape[1],), device=uv.device, dtype=torch.float32)      # one memset for all three
+        dwc, dbc, dpre = buf[:D], buf[D:D + 1], buf[D + 4:]
     ds = torch.empty((n_rows,), device=h.device, dtype=torch.float32) if want_ds else None
     # profile record: "flops" slot carries the algorithmic HBM bytes (h once, uv read + rewritten, p)
     es = h.element_size()
@@ -372,6 +408,7 @@ class _Linear(torch.autograd.Function):
         ctx.has_bias = b is not None
         ctx.dtype = dtype
         ctx.x_dtype = x.dtype
+        ctx.gw, ctx.gb = grad_target(w), grad_target(b)
         ctx.save_for_backward(xs, ws, y)
         return y
 
@@ -391,7 +428,10 @@ class _Linear(torch.autograd.Function):
         dx = linear_bwd_input(dz, ws).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = linear_bwd_weight(dz, xs, want_bias=ctx.has_bias)
+            if ctx.gw is not None and (not ctx.has_bias or ctx.gb is not None):
+                linear_bwd_weight(dz, xs, want_bias=ctx.has_bias, dw_into=ctx.gw, db_into=ctx.gb)     # summed in place
+            else:
+                dw, db = linear_bwd_weight(dz, xs, want_bias=ctx.has_bias)
         return dx, dw, db, None, None
 
 
@@ -451,24 +491,32 @@ def actor_head(logits, eps, std):
 # ------------------------------------------------------------------------------------------------
 # autograd: NT-Xent
 # ------------------------------------------------------------------------------------------------
-def ntxent_raw(z: torch.Tensor, B: int, temperature: float, want_grad=True):
+def ntxent_raw(z: torch.Tensor, B: int, temperature: float, want_grad=True, slab=None):
+    """(loss [1], dz [2B, d] | None, cos [B]).  ``slab = (b0, nb)`` restricts the gradient to the samples
+    [b0, b0 + nb) of both views (murcl_ntxent_fwd_bwd_slab); the other rows of dz are zero."""
     _chk(z, "ntxent.z", torch.float32)
     R, d = z.shape
     loss = torch.empty((1,), device=z.device, dtype=torch.float32)
-    dz = torch.empty_like(z) if want_grad else None
     cos = torch.empty((B,), device=z.device, dtype=torch.float32)
     ws = torch.empty((int(_lib.load().murcl_ntxent_workspace(B, d)),), device=z.device, dtype=torch.float32)
-    check(_lib.load().murcl_ntxent_fwd_bwd(_p(z), B, d, float(temperature), _p(loss), _p(dz), _p(cos), _p(ws), _s()),
-          "murcl_ntxent_fwd_bwd")
+    if slab is None or tuple(slab) == (0, B):
+        dz = torch.empty_like(z) if want_grad else None
+        check(_lib.load().murcl_ntxent_fwd_bwd(_p(z), B, d, float(temperature), _p(loss), _p(dz), _p(cos), _p(ws), _s()),
+              "murcl_ntxent_fwd_bwd")
+    else:
+        b0, nb = int(slab[0]), int(slab[1])
+        dz = torch.zeros_like(z) if want_grad else None
+        check(_lib.load().murcl_ntxent_fwd_bwd_slab(_p(z), B, d, float(temperature), b0, nb, _p(loss), _p(dz), _p(cos), _p(ws),
+                                                    _s()), "murcl_ntxent_fwd_bwd_slab")
     return loss, dz, cos
 
 
 class _NTXent(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z_i, z_j, temperature):
+    def forward(ctx, z_i, z_j, temperature, slab):
         B = z_i.shape[0]
         z = torch.cat([z_i.detach(), z_j.detach()], 0).float().contiguous()
-        loss, dz, cos = ntxent_raw(z, B, temperature, True)
+        loss, dz, cos = ntxent_raw(z, B, temperature, True, slab)
         ctx.save_for_backward(dz)
         ctx.B = B
         ctx.mark_non_differentiable(cos)
@@ -478,14 +526,16 @@ class _NTXent(torch.autograd.Function):
     def backward(ctx, g, _gcos):
         (dz,) = ctx.saved_tensors
         dz = dz * g
-        return dz[: ctx.B], dz[ctx.B:], None
+        return dz[: ctx.B], dz[ctx.B:], None, None
 
 
-def ntxent(z_i, z_j, temperature):
-    """(loss, cos_pair): fused NT-Xent forward+gradient; cos_pair[b] = cos(z_i[b], z_j[b]) (the reward signal)."""
+def ntxent(z_i, z_j, temperature, slab=None):
+    """(loss, cos_pair): fused NT-Xent forward+gradient; cos_pair[b] = cos(z_i[b], z_j[b]) (the reward signal).
+    ``slab = (b0, nb)``: only the samples [b0, b0 + nb) receive a gradient (what a data-parallel rank needs for the rows it
+    contributed to an all-gathered batch; the other rows' gradients are returned as zeros)."""
     if not z_i.is_cuda:
         raise MurclError("ntxent: expected CUDA tensors (libmurcl_b200 has no CPU path)")
-    return _NTXent.apply(z_i, z_j, temperature)
+    return _NTXent.apply(z_i, z_j, temperature, slab)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -581,6 +631,9 @@ class _MILAggregate(torch.autograd.Function):
         ctx.x_dtype = x.dtype
         ctx.hbits = hbits
         ctx.inv_sqrt_bwd = inv_sqrt_bwd
+        # persistent gradient views (ParamArena): the backward kernels add into them and autograd gets None
+        ctx.g_attn = tuple(grad_target(t) for t in (wab, bab, wc, bc))
+        ctx.g_enc = tuple(grad_target(t) for t in enc)
         M_out = M
         if shard:
             M, M_out = M          # (merged vectors without the post scale: what the backward's K_b uses, pooled output)
@@ -606,21 +659,36 @@ class _MILAggregate(torch.autograd.Function):
         drop = meta.get("drop")
         q_attn = 1.0 / (1.0 - drop["attn"]) if drop is not None and drop["attn"] > 0 else 1.0
         q_enc = [1.0 / (1.0 - pe) if drop is not None and pe > 0 else 1.0 for pe in (drop["enc"] if drop else [0.0] * n_enc)]
+        g_wab, g_bab, g_wc, g_bc = ctx.g_attn
+        g_enc = ctx.g_enc
+        inst = meta.get("inst")
+        attn_in_place = all(t is not None for t in (g_wab, g_bab, g_wc, g_bc))
+        # every encoder parameter has a persistent gradient view and no instance-loss scatter touches dZ afterwards
+        enc_in_place = n_enc > 0 and inst is None and all(t is not None for t in g_enc)
         if attnpool_bwd_supported(L, D, gated, H.dtype):
             # one pass over H: t_n = dM.h_n, ds, d(pre-activation) over uv, dwc / bias column sums
+            into = (g_wc.reshape(-1), g_bc.reshape(-1), g_bab.reshape(-1)) if attn_in_place else None
             dwc, dbc, dbab, _ = attnpool_bwd_(H, uv, p, M.reshape(B, L).contiguous(), dM, wc_f, offsets, row_seg, B, D, gated,
-                                              ctx.inv_sqrt_bwd, q_attn)
+                                              ctx.inv_sqrt_bwd, q_attn, into=into)
         else:
             ds = pool_bwd_scores(p, H, dM, M.reshape(B, 1, L), offsets, row_seg, B, 1, ctx.inv_sqrt_bwd)
             dwc, dbc, dbab = attn_score_bwd_(uv, wc_f, ds, D, gated, q_attn)    # uv now holds d(pre-activation)
-        dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
+            if attn_in_place:
+                g_wc.reshape(-1).add_(dwc); g_bc.reshape(-1).add_(dbc); g_bab.add_(dbab)
+        if attn_in_place:
+            linear_bwd_weight(uv, H, want_bias=False, dw_into=g_wab)
+            dwab = dbab = dwc = dbc = None
+        else:
+            dwab, _ = linear_bwd_weight(uv, H, want_bias=False)
         hbits = ctx.hbits
         relu_src = H if (n_enc > 0 and hbits[n_enc] is None) else None
-        inst = meta.get("inst")
         # bias gradients ride along as fused column sums of each dZ (the instance-loss scatter below changes dZ
         # after the fact, so that case takes the separate column-sum pass)
         fuse_db = n_enc > 0 and inst is None
-        db_next = torch.zeros((n_enc, L), device=uv.device, dtype=torch.float32) if fuse_db else None
+        if enc_in_place:
+            db_next = [g_enc[2 * l + 1] for l in range(n_enc)]            # atomics add straight into the bias gradients
+        else:
+            db_next = torch.zeros((n_enc, L), device=uv.device, dtype=torch.float32) if fuse_db else None
         dz = linear_bwd_input(uv, wab_s, relu_src, p, dM, row_seg, col_sum=db_next[n_enc - 1] if fuse_db else None,
                               out_scale=q_enc[n_enc - 1] if n_enc > 0 else 1.0,
                               relu_bits=hbits[n_enc] if n_enc > 0 else None)       # + p_n dM[b] direct term, ReLU mask
@@ -640,9 +708,13 @@ class _MILAggregate(torch.autograd.Function):
             scatter_add_rows_(dz, idx, drows.contiguous())
         grads_enc = []
         for l in range(n_enc, 0, -1):
-            dw, db = linear_bwd_weight(dz, hs[l - 1], want_bias=not fuse_db)
-            if fuse_db:
-                db = db_next[l - 1]
+            if enc_in_place:
+                linear_bwd_weight(dz, hs[l - 1], want_bias=False, dw_into=g_enc[2 * (l - 1)])
+                dw = db = None
+            else:
+                dw, db = linear_bwd_weight(dz, hs[l - 1], want_bias=not fuse_db)
+                if fuse_db:
+                    db = db_next[l - 1]
             grads_enc = [dw, db] + grads_enc
             if l > 1:
                 dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1] if hbits[l - 1] is None else None,
@@ -653,7 +725,8 @@ class _MILAggregate(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = dz.to(ctx.x_dtype)
-        return (dx, None, None, None, dwab, dbab, dwc.reshape(1, -1), dbc, d_inst_w, d_inst_b, *grads_enc)
+        return (dx, None, None, None, dwab, dbab, None if dwc is None else dwc.reshape(1, -1), dbc, d_inst_w, d_inst_b,
+                *grads_enc)
 
 
 def _merge_shards(meta, offsets, row_seg, p_loc, M_loc, H, s):

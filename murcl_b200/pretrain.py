@@ -124,6 +124,12 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
     if memories is not None and not keep_memory:
         for m in memories:
             m.clear_memory()
+    # Full_layer.hidden carries its autograd graph across the T patch-steps (rlmil.py:216-219); the next optimiser step
+    # restarts it (restart=True at t == 0), so once the backward has run the graph is dead weight: dropping it releases the
+    # step's activations now and lets autograd rebuild its leaf nodes on whatever stream the next step runs on
+    hid = getattr(fc, "hidden", None)
+    if isinstance(hid, torch.Tensor) and hid.requires_grad:
+        fc.hidden = hid.detach()
     return total.detach(), [l.detach() for l in losses]
 
 
@@ -146,7 +152,9 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph, pool=pool, capture_error_mode=capture_error_mode):
+        # capture on the warm-up stream: autograd remembers the stream a leaf's gradient node was created on, and a
+        # node that survived the warm-up would otherwise make the captured backward wait on an uncaptured stream
+        with torch.cuda.graph(self.graph, pool=pool, stream=side, capture_error_mode=capture_error_mode):
             self.loss = step_fn()
         self.launches = _lib.launch_count() - n0          # libmurcl_b200 kernels per replay
 

@@ -865,3 +865,79 @@ def test_row_sharded_mode_single_rank_is_identity(kind, precision):
     for n in ga:
         if not n.startswith(("fc.", "classifiers", "instance_classifiers")):
             assert_close(gb[n], ga[n], 50 * tol, n, floor=1e-1 if _zero_grad_key(n) else 1e-6)   # atomics: summation order
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pretrain_step_golden_with_param_arena(golden, precision):
+    """The same reference-generated miniature step with the parameters laid out in a ParamArena: gradients are summed
+    inside the kernels into the flat buffer (no autograd accumulation), bf16 weights come from the shadow copy; a second
+    step after ``zero_grad`` must reproduce the first (nothing leaks between steps), and ``refresh`` must track an update."""
+    from murcl_b200 import pretrain
+    from murcl_b200.arena import ParamArena
+    from murcl_b200.csr import BagStore
+    from murcl_b200.dropin import abmil, cl, losses, rlmil
+    g = golden("pretrain_step")
+    cfg = g["cfg"].tolist()
+    b, k, d, fs, T, L, D, hid, proj = cfg
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), d, k, seed=91)
+    enc = _load(abmil.ABMIL(d, L=L, D=D, dim_out=proj, precision=precision), synth.abmil_state(d, L, D, proj, seed=92))
+    model = cl.CL(enc, projection_dim=proj, n_features=L)
+    fc = _load(rlmil.Full_layer(L, hid, True, proj), synth.full_layer_state(L, hid, proj, seed=93))
+    fc.precision = precision
+    arena = ParamArena(list(enc.parameters()) + list(fc.parameters()),
+                       shadow_dtype=torch.bfloat16 if precision == "bf16" else None)
+    assert all(p.grad is not None and p._murcl_accum is p.grad for p in enc.parameters())
+    crit = losses.NT_Xent(b, float(g["tau"]))
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    draws = [([a.to(DEV) for a in acts], [l.to(DEV) for l in lams], [p.to(DEV) for p in perms])
+             for acts, lams, perms in _mini_step_draws(cfg, 94)]
+    tol_l, tol_g = (FP32_OUT, 3e-4) if precision == "fp32" else (BF16_OUT, 1e-1)
+    snaps = []
+    for rep in range(2):
+        arena.zero_grad()
+        loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=float(g["alpha"]), draws=draws,
+                                         precision=precision)
+        assert_close(loss, g["loss"], tol_l, "loss")
+        gm, gf = _grads(enc), _grads(fc)
+        n = 0
+        for key, v in g.items():
+            if key.startswith("grad.m.") and not key.endswith("fc.weight") and not key.endswith("fc.bias"):
+                assert_close(sample(gm[key[7:]].numpy()), v, tol_g, key, floor=1e-5 if precision == "fp32" else 1e-3)
+                n += 1
+            elif key.startswith("grad.f."):
+                assert_close(sample(gf[key[7:]].numpy()), v, tol_g, key, floor=1e-5 if precision == "fp32" else 1e-3)
+                n += 1
+        assert n >= 10
+        snaps.append(arena.grad.clone())
+    assert_close(snaps[1], snaps[0], 1e-5 if precision == "fp32" else 1e-3, "second step after zero_grad", floor=1e-6)
+    # the optimiser sees one flat leaf; the bf16 shadow follows after refresh()
+    opt = torch.optim.SGD(arena.optimizer_params(), lr=0.1)
+    before = enc.encoder[0].weight.detach().clone()
+    opt.step()
+    arena.refresh()
+    assert not torch.equal(before, enc.encoder[0].weight.detach())
+    if precision == "bf16":
+        assert torch.equal(enc.encoder[0].weight._murcl_shadow, enc.encoder[0].weight.detach().bfloat16())
+
+
+@pytest.mark.parametrize("B,d,b0,nb", [(128, 128, 0, 128), (128, 128, 32, 16), (1024, 128, 896, 128), (24, 32, 5, 7), (8, 256, 0, 3)])
+def test_ntxent_gradient_slab(B, d, b0, nb):
+    """murcl_ntxent_fwd_bwd_slab: the loss covers the whole batch, the gradient only the samples [b0, b0+nb) of both views
+    (what a data-parallel rank keeps); compared with the fp64 evaluation of utils/losses.py:24-41."""
+    from murcl_b200 import ops
+    g = synth.gen(B + d + b0)
+    zi = torch.randn(B, d, generator=g, dtype=torch.float64)
+    zj = 0.7 * zi + torch.randn(B, d, generator=g, dtype=torch.float64)
+    zi.requires_grad_(True); zj.requires_grad_(True)
+    want = O.nt_xent(zi, zj, 0.5)
+    want.backward()
+    z = torch.cat([zi.detach(), zj.detach()], 0).float().to(DEV)
+    loss, dz, cos = ops.ntxent_raw(z, B, 0.5, True, slab=(b0, nb))
+    assert_close(loss, want.float().reshape(1), FP32_OUT, "loss")
+    assert_close(cos, torch.cosine_similarity(zi.detach(), zj.detach()).float(), FP32_OUT, "cos")
+    full = torch.cat([zi.grad, zj.grad], 0).float()
+    rows = torch.cat([torch.arange(b0, b0 + nb), torch.arange(B + b0, B + b0 + nb)])
+    assert_close(dz.cpu()[rows], full[rows], FP32_GRAD, "slab rows", floor=float(full.abs().max()) * 1e-3)
+    mask = torch.ones(2 * B, dtype=torch.bool)
+    mask[rows] = False
+    assert float(dz.cpu()[mask].abs().max() if mask.any() else 0.0) == 0.0, "rows outside the slab must stay zero"
