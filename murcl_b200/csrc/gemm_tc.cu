@@ -329,20 +329,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc_nb = -1;
     const int etid = threadIdx.x;                           // 0..511: the epilogue threads come first
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); };
-    auto flush_colacc = [&](int nb_flush) {
-      epi_sync();                                           // all epilogue warps have added their units
-      for (int i = etid; i < BN; i += EPI_THREADS) {
-        const int col = nb_flush * BN + i;
-        const float sum = colacc[i];
-        if (col < p.N && sum != 0.f) atomicAdd(p.col_sum + col, sum);
-        colacc[i] = 0.f;
+    // Column sums (bias gradient of the layer below) live in REGISTERS across the tiles of a column tile: the persistent
+    // schedule hands a CTA the same column tile again and again, so a warp meets the same (at most NU) 32-column units
+    // every tile; lane l accumulates columns 2 (l & 15), +1 of every second row.  They go to global memory (atomics) only
+    // when the column tile changes and at the end of the kernel - no shared-memory atomics, no CTA barrier per tile.
+    constexpr int NU = (BN + 127) / 128;                    // units of a tile per epilogue warp
+    float cs[NU][2];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) cs[u][0] = cs[u][1] = 0.f;
+    auto flush_colsum = [&](int nb_flush) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const float s0 = cs[u][0] + __shfl_xor_sync(0xffffffffu, cs[u][0], 16);
+        const float s1 = cs[u][1] + __shfl_xor_sync(0xffffffffu, cs[u][1], 16);
+        const int col = nb_flush * BN + part * 32 + 128 * u + 2 * (lane & 15);
+        if (lane < 16 && part * 32 + 128 * u < BN) {
+          if (col < p.N && s0 != 0.f) atomicAdd(p.col_sum + col, s0);
+          if (col + 1 < p.N && s1 != 0.f) atomicAdd(p.col_sum + col + 1, s1);
+        }
+        cs[u][0] = cs[u][1] = 0.f;
       }
-      epi_sync();
     };
-    if (want_colsum) {
-      for (int i = etid; i < BN; i += EPI_THREADS) colacc[i] = 0.f;
-      epi_sync();
-    }
     for (int t = tile_first; t < total_tiles; t += tile_step) {
       int mb, nb, sp;
       tile_coords(t, mb, nb, sp);
@@ -353,9 +360,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // latency is hidden behind it (the wait is a compiler barrier: loads placed after it would start after it)
       float rs = 0.f;
       const float* rv = nullptr;
-      if (EPI == EPI_DGRAD && p.row_scale != nullptr && row < p.M) {
-        rs = __ldg(p.row_scale + row);
-        rv = p.row_vec + (int64_t)__ldg(p.row_seg + row) * p.N;
+      bool same_bag = false;                                // warp-uniform: all 32 rows of this warp belong to one bag
+      float gl[NU];                                         // same_bag: lane l holds row_vec[bag][n0 + c0(u) + l]
+      unsigned int wb[NU];                                  // ReLU bit word of (row, unit u)
+#pragma unroll
+      for (int u = 0; u < NU; ++u) { gl[u] = 0.f; wb[u] = 0u; }
+      if (EPI == EPI_DGRAD) {
+        if (p.row_scale != nullptr) {
+          int seg = -1;
+          if (row < p.M) {
+            rs = __ldg(p.row_scale + row);
+            seg = __ldg(p.row_seg + row);
+            rv = p.row_vec + (int64_t)seg * p.N;
+          }
+          const int seg0 = __shfl_sync(0xffffffffu, seg, 0);
+          same_bag = seg0 >= 0 && __all_sync(0xffffffffu, seg == seg0 || seg < 0);
+          if (same_bag) {
+            // ONE coalesced 128-byte read of the bag's row vector per unit (instead of 8 broadcast float4 reads per
+            // lane after the TMEM wait); the values are handed round with shuffles in the FMA loop
+            const float* rv0 = p.row_vec + (int64_t)seg0 * p.N;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+              const int col = n0 + part * 32 + 128 * u + lane;
+              if (part * 32 + 128 * u < BN && col < p.N) gl[u] = __ldg(rv0 + col);
+            }
+          }
+        }
+        if (p.bits_in != nullptr && row < p.M) {
+          // the ReLU bit words of the tile's units are requested here as well: their L2 latency used to be exposed after
+          // every TMEM load (the top stall of the kernel: R2P waiting for the word)
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int col0 = n0 + part * 32 + 128 * u;
+            if (part * 32 + 128 * u < BN && col0 < p.N)
+              wb[u] = __ldg(reinterpret_cast<const unsigned int*>(p.bits_in) + ((((int64_t)(col0 >> 6) * p.M + row) << 1) + ((col0 >> 5) & 1)));
+          }
+        }
       }
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
@@ -383,12 +423,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       } else {
-        if (want_colsum && nb != acc_nb) {                 // new column tile: flush the CTA's partial sums
-          if (acc_nb >= 0) flush_colacc(acc_nb);
+        if (want_colsum && nb != acc_nb) {                 // new column tile: flush this warp's partial sums
+          if (acc_nb >= 0) flush_colsum(acc_nb);
           acc_nb = nb;
         }
-#pragma unroll 1
-        for (int c0 = part * 32; c0 < BN; c0 += 128) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int c0 = part * 32 + 128 * u;
+          if (c0 >= BN) break;
           const int col0 = n0 + c0;
           if (col0 >= p.N || row0 >= p.M) break;            // warp-uniform: nothing of this unit is in range
           MURCL_STAMP(0)
@@ -400,10 +442,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool whole = col0 + 32 <= p.N;               // warp-uniform
           // the unit's 128-byte line of the bias / pooling row vector: pulled into L1 now, read after the TMEM wait
           if (EPI == EPI_FWD && p.bias != nullptr) prefetch_l1(p.bias + col0);
-          if (EPI == EPI_DGRAD && rv != nullptr) prefetch_l1(rv + col0);
-          unsigned int wbits = 0u;
-          if (EPI == EPI_DGRAD && p.bits_in != nullptr && row < p.M)
-            wbits = __ldg(reinterpret_cast<const unsigned int*>(p.bits_in) + bit_word);
+          if (EPI == EPI_DGRAD && rv != nullptr && !same_bag) prefetch_l1(rv + col0);
+          const unsigned int wbits = wb[u];
           float v[32];
           {
             uint32_t r[32];
@@ -445,7 +485,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               reinterpret_cast<unsigned int*>(p.bits_out)[bit_word] = q0 | (q1 << 16);
             }
           } else if (EPI == EPI_DGRAD) {
-            if (rv != nullptr) {
+            if (same_bag) {
+              const float gu = gl[u];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaf(rs, __shfl_sync(0xffffffffu, gu, i), v[i]);
+            } else if (rv != nullptr) {
               if (whole) {
                 float4 g4[8];
 #pragma unroll
@@ -534,12 +578,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               s0 += f.x;
               s1 += f.y;
             }
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            if (lane < 16) {
-              atomicAdd(&colacc[c0 + 2 * lane], s0);
-              atomicAdd(&colacc[c0 + 2 * lane + 1], s1);
-            }
+            cs[u][0] += s0;
+            cs[u][1] += s1;
           }
         }
       }
@@ -556,7 +596,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
-    if (want_colsum && acc_nb >= 0) flush_colacc(acc_nb);
+    if (want_colsum && acc_nb >= 0) flush_colsum(acc_nb);
     if (EPI != EPI_SPLIT && lane == 0) bulk_wait_all();     // all bulk stores of this warp have completed
   }
 

@@ -172,9 +172,10 @@ __global__ void __launch_bounds__(256) ntx_finish_kernel(const float* __restrict
 // ================================================================================================================
 // Two-kernel form (d <= 256, d % 4 == 0: the projection widths in use).  Nothing of size [2B, 2B] touches memory.
 //
-//   ntx_lse_kernel   every CTA owns 8 rows a: streams all rows b in tiles of 64 through shared memory, normalises them
-//                    on the fly, keeps per-thread online (max, sum-exp) of s_ab over b != a, records the positive logit;
-//                    writes 1/|z_a|, lse_a, the row's loss term and cos(z_i, z_j); the last CTA to finish sums the loss
+//   ntx_lse_kernel   grid (row blocks of 16 rows a, splits of the b range): streams its rows b in tiles of 64 through
+//                    shared memory, normalises them on the fly, keeps per-thread online (max, sum-exp) of s_ab over
+//                    b != a, records the positive logit; the last split of a row block merges the partials and writes
+//                    1/|z_a|, lse_a, the row's loss term and cos(z_i, z_j); the last row block to finish sums the loss
 //                    terms in a fixed order (deterministic).
 //   ntx_grad_kernel  grid (row blocks of 16 rows of the caller's SLAB, splits of the b range): recomputes the 16 x 64
 //                    score tile, turns it into the coefficients e^{s-lse_a} + e^{s-lse_b} - 2[b = pos(a)], multiplies
@@ -184,46 +185,51 @@ __global__ void __launch_bounds__(256) ntx_finish_kernel(const float* __restrict
 // The slab (samples [b0, b0 + nb) of both views) is what data parallelism needs: every rank evaluates the loss over the
 // global batch (lse of all rows: ntx_lse_kernel, 2B x 2B x d FMAs) but only the gradient rows of its own samples
 // (2 nb x 2B x 2d FMAs) - no second collective, no redundant gradient work (utils/losses.py:24-41 differentiated).
-constexpr int NTX_RA1 = 8, NTX_RA2 = 16, NTX_TB = 64, NTX_MAXD = 256;
+constexpr int NTX_RA2 = 16, NTX_TB = 64, NTX_MAXD = 256;
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
   return acc;
 }
 
-__global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ z, int B, int d, float inv_tau,
+// grid (row blocks of 16 rows, splits of the b range).  Every CTA merges its tiles into one partial (max, sum-exp) per
+// row; the last split of a row block (ticket) merges the partials into lse / loss term / cosine; the last row block
+// to finish sums the loss terms in index order (deterministic).
+__global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ z, int B, int d, float inv_tau, int tiles_per_split,
                                                       float* __restrict__ inv_norm, float* __restrict__ lse,
                                                       float* __restrict__ row_loss, float* __restrict__ cos_pair,
-                                                      float* __restrict__ loss, unsigned int* __restrict__ ticket) {
+                                                      float* __restrict__ part /* [row blocks*16][splits][2] */,
+                                                      float* __restrict__ pos_s /* [R] */, float* __restrict__ loss,
+                                                      unsigned int* __restrict__ tickets /* [0]: global, [1 + rb]: per row block */) {
   extern __shared__ __align__(16) float sm[];
   const int R = 2 * B, ldb = d + 4;
-  float* za = sm;                               // [8][d]   normalised rows a
-  float* zb = za + NTX_RA1 * d;                 // [64][d+4] raw rows b of the tile
+  float* za = sm;                               // [16][d]   normalised rows a
+  float* zb = za + NTX_RA2 * d;                 // [64][d+4] raw rows b of the tile
   float* invb = zb + NTX_TB * ldb;              // [64]
-  float* red_m = invb + NTX_TB;                 // [8][64]
-  float* red_l = red_m + NTX_RA1 * NTX_TB;      // [8][64]
-  float* s_pos = red_l + NTX_RA1 * NTX_TB;      // [8]
-  float* inva = s_pos + NTX_RA1;                // [8]
+  float* red_m = invb + NTX_TB;                 // [16][64]
+  float* red_l = red_m + NTX_RA2 * NTX_TB;      // [16][64]
+  float* inva = red_l + NTX_RA2 * NTX_TB;       // [16]
   __shared__ float red[32];
   __shared__ bool is_last;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int a0 = blockIdx.x * NTX_RA1;
-  // rows a: warp w normalises row a0 + w
-  {
-    const int a = a0 + w;
+  const int a0 = blockIdx.x * NTX_RA2;
+  const int n_splits = gridDim.y;
+  for (int rr = w; rr < NTX_RA2; rr += 8) {                  // rows a: a warp normalises rows w, w + 8
+    const int a = a0 + rr;
     float ss = 0.f;
     if (a < R)
       for (int j = lane; j < d; j += 32) { const float v = z[(int64_t)a * d + j]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
     const float inv = 1.f / fmaxf(sqrtf(ss), COS_EPS);
-    for (int j = lane; j < d; j += 32) za[w * d + j] = (a < R) ? z[(int64_t)a * d + j] * inv : 0.f;
-    if (lane == 0) { inva[w] = inv; s_pos[w] = 0.f; }
+    for (int j = lane; j < d; j += 32) za[rr * d + j] = (a < R) ? z[(int64_t)a * d + j] * inv : 0.f;
+    if (lane == 0) inva[rr] = inv;
   }
-  const int bl = t & 63, ag = t >> 6;                       // thread: column bl of the tile, rows 2ag, 2ag + 1
-  float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
-  const int ar0 = a0 + 2 * ag, ar1 = ar0 + 1;
-  const int pos0 = ar0 < B ? ar0 + B : ar0 - B, pos1 = ar1 < B ? ar1 + B : ar1 - B;
-  for (int b0 = 0; b0 < R; b0 += NTX_TB) {
+  const int bl = t & 63, ag = t >> 6;                       // thread: column bl of the tile, rows 4ag .. 4ag + 3
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, l4[4] = {0.f, 0.f, 0.f, 0.f};
+  const int n_tiles = (R + NTX_TB - 1) / NTX_TB;
+  const int tile0 = blockIdx.y * tiles_per_split;
+  for (int tile = tile0; tile < tile0 + tiles_per_split && tile < n_tiles; ++tile) {
+    const int b0 = tile * NTX_TB;
     __syncthreads();
     for (int i = t; i < NTX_TB * (d >> 2); i += 256) {
       const int r = i / (d >> 2), c = i % (d >> 2);
@@ -238,50 +244,75 @@ __global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ 
       if (lane == 0) invb[r] = 1.f / fmaxf(sqrtf(ss), COS_EPS);
     }
     __syncthreads();
-    float acc0 = 0.f, acc1 = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const float* rb = zb + bl * ldb;
-    const float* ra0 = za + (2 * ag) * d;
-    const float* ra1 = ra0 + d;
+    const float* ra = za + (4 * ag) * d;
     for (int k = 0; k < d; k += 4) {
       const float4 vb = *reinterpret_cast<const float4*>(rb + k);
-      acc0 = dot4(*reinterpret_cast<const float4*>(ra0 + k), vb, acc0);
-      acc1 = dot4(*reinterpret_cast<const float4*>(ra1 + k), vb, acc1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = dot4(*reinterpret_cast<const float4*>(ra + i * d + k), vb, acc[i]);
     }
     const int b = b0 + bl;
     if (b < R) {
       const float sc = invb[bl] * inv_tau;
-      const float s0 = acc0 * sc, s1 = acc1 * sc;
-      if (b != ar0) { const float mn = fmaxf(m0, s0); l0 = l0 * expf(m0 - mn) + expf(s0 - mn); m0 = mn; }
-      if (b != ar1) { const float mn = fmaxf(m1, s1); l1 = l1 * expf(m1 - mn) + expf(s1 - mn); m1 = mn; }
-      if (b == pos0) s_pos[2 * ag] = s0;
-      if (b == pos1) s_pos[2 * ag + 1] = s1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = a0 + 4 * ag + i;
+        const float sv = acc[i] * sc;
+        if (b != a) { const float mn = fmaxf(m4[i], sv); l4[i] = l4[i] * expf(m4[i] - mn) + expf(sv - mn); m4[i] = mn; }
+        if (a < R && b == (a < B ? a + B : a - B)) pos_s[a] = sv;
+      }
     }
   }
-  red_m[(2 * ag) * NTX_TB + bl] = m0; red_l[(2 * ag) * NTX_TB + bl] = l0;
-  red_m[(2 * ag + 1) * NTX_TB + bl] = m1; red_l[(2 * ag + 1) * NTX_TB + bl] = l1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red_m[(4 * ag + i) * NTX_TB + bl] = m4[i];
+    red_l[(4 * ag + i) * NTX_TB + bl] = l4[i];
+  }
   __syncthreads();
-  {                                                           // warp w merges the 64 partial (m, l) of row a0 + w
-    const int a = a0 + w;
-    const float ma = red_m[w * NTX_TB + lane], mb = red_m[w * NTX_TB + 32 + lane];
-    const float la = red_l[w * NTX_TB + lane], lb = red_l[w * NTX_TB + 32 + lane];
-    float m = fmaxf(ma, mb);
-    m = warp_max(m);
+  for (int rr = w; rr < NTX_RA2; rr += 8) {                  // a warp merges the 64 per-thread partials of a row
+    const float ma = red_m[rr * NTX_TB + lane], mb = red_m[rr * NTX_TB + 32 + lane];
+    const float la = red_l[rr * NTX_TB + lane], lb = red_l[rr * NTX_TB + 32 + lane];
+    float m = warp_max(fmaxf(ma, mb));
     float l = (la > 0.f ? la * expf(ma - m) : 0.f) + (lb > 0.f ? lb * expf(mb - m) : 0.f);
     l = warp_sum(l);
-    if (lane == 0 && a < R) {
-      const float e = m + logf(l);
-      lse[a] = e;
-      inv_norm[a] = inva[w];
-      row_loss[a] = e - s_pos[w];
-      if (cos_pair && a < B) cos_pair[a] = s_pos[w] / inv_tau;
+    if (lane == 0) {
+      float* pp = part + ((int64_t)(a0 + rr) * n_splits + blockIdx.y) * 2;
+      pp[0] = m;
+      pp[1] = l;
     }
   }
-  // the last CTA sums the rows' loss terms in index order
   __threadfence();
   __syncthreads();
-  if (t == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  if (t == 0) is_last = atomicAdd(tickets + 1 + blockIdx.x, 1u) == (unsigned)n_splits - 1;
   __syncthreads();
-  if (is_last) {
+  if (!is_last) return;
+  __threadfence();
+  for (int rr = w; rr < NTX_RA2; rr += 8) {                  // last split of the row block: merge the splits' partials
+    const int a = a0 + rr;
+    if (a >= R) continue;
+    float m = -INFINITY;
+    for (int sidx = lane; sidx < n_splits; sidx += 32) m = fmaxf(m, __ldcg(part + ((int64_t)a * n_splits + sidx) * 2));
+    m = warp_max(m);
+    float l = 0.f;
+    for (int sidx = lane; sidx < n_splits; sidx += 32) {
+      const float pm = __ldcg(part + ((int64_t)a * n_splits + sidx) * 2), pl = __ldcg(part + ((int64_t)a * n_splits + sidx) * 2 + 1);
+      if (pl > 0.f) l += pl * expf(pm - m);
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      const float e = m + logf(l), sp = __ldcg(pos_s + a);
+      lse[a] = e;
+      inv_norm[a] = inva[rr];
+      row_loss[a] = e - sp;
+      if (cos_pair && a < B) cos_pair[a] = sp / inv_tau;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) is_last = atomicAdd(tickets, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {                                             // the last row block sums the loss terms in index order
     __threadfence();
     float sacc = 0.f;
     for (int i = t; i < R; i += 256) sacc += __ldcg(row_loss + i);
@@ -434,7 +465,8 @@ int64_t murcl_ntxent_workspace(int B, int d) {
   const int64_t R = 2 * (int64_t)B;
   const int64_t legacy = R * d /*zn*/ + 4 * R /*inv_norm, lse, row_loss, pad*/ + R * R /*gram / coefficients*/ + R * d /*C zn*/ +
                          32 * R * d /*split-K scratch of the C zn product*/;
-  const int64_t fused = 4 * R /*inv_norm, lse, row_loss, pad*/ + R * d /*dzn accumulator*/ + R / 16 + 64 /*tickets*/;
+  const int64_t fused = 4 * R /*inv_norm, lse, row_loss, pos_s*/ + (R + 16) * ((R + 63) / 64) * 2 /*(max, sum-exp) partials*/ +
+                        2 * (R / 16 + 2) + 16 /*tickets*/ + R * d /*dzn accumulator*/;
   return ntx_fused_ok(d) ? fused : legacy;
 }
 
@@ -496,17 +528,33 @@ int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, i
   }
   const int R = 2 * B;
   const float inv_tau = 1.f / temperature;
+  const int n_tiles = ceil_div(R, NTX_TB);
+  const int rb_all = ceil_div(R, NTX_RA2);                              // row blocks of the log-sum-exp pass (all rows)
+  const int row_blocks = ceil_div(2 * nb, NTX_RA2);                      // row blocks of the gradient pass (the slab)
+  auto plan = [&](int blocks, int& splits, int& tps) {                   // ~2 CTAs per SM, every split >= 1 tile
+    splits = ceil_div(2 * sm_count(), blocks > 0 ? blocks : 1);
+    if (splits > n_tiles) splits = n_tiles;
+    if (splits < 1) splits = 1;
+    tps = ceil_div(n_tiles, splits);
+    splits = ceil_div(n_tiles, tps);
+  };
+  int splits1, tps1, splits2, tps2;
+  plan(rb_all, splits1, tps1);
+  plan(row_blocks, splits2, tps2);
+  // workspace: inv_norm [R] | lse [R] | row_loss [R] | pos_s [R] | part [rb_all*16][n_tiles][2] | tickets | accumulator
   float* inv_norm = workspace;
   float* lse = inv_norm + R;
   float* row_loss = lse + R;
-  unsigned int* tickets = reinterpret_cast<unsigned int*>(row_loss + 2 * R);    // [1 + row blocks] in a slot of R/16 + 64 words
-  float* acc_ws = row_loss + 2 * R + (R / 16 + 64);                              // [2 nb, d]
-  const int row_blocks = ceil_div(2 * nb, NTX_RA2);
+  float* pos_s = row_loss + R;
+  float* part = pos_s + R;
+  const int64_t n_tickets = 2 + (int64_t)rb_all + row_blocks;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(part + (int64_t)rb_all * NTX_RA2 * n_tiles * 2);
+  float* acc_ws = reinterpret_cast<float*>(tickets) + ((n_tickets + 3) / 4) * 4;   // [2 nb, d], 16-byte aligned
   const bool want_grad = dz != nullptr && nb > 0;
   // one memset node clears the tickets and, right behind them, the gradient accumulator
-  MURCL_CUDA(cudaMemsetAsync(tickets, 0, sizeof(float) * ((size_t)(R / 16 + 64) + (want_grad ? (size_t)2 * nb * d : 0)), st));
+  MURCL_CUDA(cudaMemsetAsync(tickets, 0, sizeof(float) * ((size_t)((n_tickets + 3) / 4) * 4 + (want_grad ? (size_t)2 * nb * d : 0)), st));
   {
-    const size_t smem = sizeof(float) * (size_t)(NTX_RA1 * d + NTX_TB * (d + 4) + NTX_TB + 2 * NTX_RA1 * NTX_TB + 2 * NTX_RA1);
+    const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_TB + 2 * NTX_RA2 * NTX_TB + NTX_RA2);
     static PerDeviceOnce configured;
     if (const int slot = configured.pending(); slot >= 0) {
       MURCL_CUDA(cudaFuncSetAttribute(ntx_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -514,22 +562,18 @@ int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, i
       MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured.mark(slot);
     }
-    ntx_lse_kernel<<<ceil_div(R, NTX_RA1), 256, smem, st>>>(z, B, d, inv_tau, inv_norm, lse, row_loss, cos_pair, loss, tickets);
+    ntx_lse_kernel<<<dim3(rb_all, splits1), 256, smem, st>>>(z, B, d, inv_tau, tps1, inv_norm, lse, row_loss, cos_pair, part, pos_s,
+                                                            loss, tickets);
     int rc = check_launch("ntx_lse_kernel");
     if (rc != MURCL_OK || !want_grad) return rc;
   }
-  const int n_tiles = ceil_div(R, NTX_TB);
-  int splits = ceil_div(128, row_blocks);
-  if (splits > n_tiles) splits = n_tiles;
-  if (splits < 1) splits = 1;
-  const int tiles_per_split = ceil_div(n_tiles, splits);
-  splits = ceil_div(n_tiles, tiles_per_split);
   const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_RA2 * (NTX_TB + 1) + NTX_TB + NTX_RA2);
-  const dim3 grid(row_blocks, splits);
+  const dim3 grid(row_blocks, splits2);
+  unsigned int* tickets2 = tickets + 1 + rb_all;
   if (d <= 128)
-    ntx_grad_kernel<1><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tiles_per_split, inv_norm, lse, acc_ws, tickets + 1, dz);
+    ntx_grad_kernel<1><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps2, inv_norm, lse, acc_ws, tickets2, dz);
   else
-    ntx_grad_kernel<2><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tiles_per_split, inv_norm, lse, acc_ws, tickets + 1, dz);
+    ntx_grad_kernel<2><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps2, inv_norm, lse, acc_ws, tickets2, dz);
   return check_launch("ntx_grad_kernel");
 }
 
