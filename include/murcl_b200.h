@@ -247,6 +247,16 @@ int murcl_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, fl
 /* Given dh_new: dgi, dgh [B,3H] and dh_prev [B,H] (the direct z*dh term; the caller adds dgh.W_hh). */
 int murcl_gru_cell_bwd(const float* dh_new, const float* gates, const float* gh, const float* h_prev, float* dgi,
                        float* dgh, float* dh_prev, int B, int H, void* stream);
+
+/* The same cell for the recurrent-head tape (murcl_b200/headtape.py), which differentiates Full_layer (rlmil.py:208-220)
+ * over all T x 2 calls of an optimiser step in ONE batched pass.  _fwd_tape also writes h_new in the GEMM storage type
+ * `dtype` (h_new_s and a second copy h_new_s2, either may be NULL) and always writes the gates.  _bwd_tape takes dh as the sum of up to three addends
+ * (dh_a, dh_b in `dtype`; dh_c fp32; any may be NULL) and writes the gate gradients dgi, dgh [B, 3H] in `dtype` - the
+ * operands of the batched weight-gradient GEMMs - plus dh_prev = z * dh (fp32, may be NULL). */
+int murcl_gru_cell_fwd_tape(const float* gi, const float* gh, const float* h_prev, float* h_new, void* h_new_s, void* h_new_s2,
+                            float* gates, int B, int H, int dtype, void* stream);
+int murcl_gru_cell_bwd_tape(const void* dh_a, const void* dh_b, const float* dh_c, const float* gates, const float* gh,
+                            const float* h_prev, void* dgi, void* dgh, float* dh_prev, int B, int H, int dtype, void* stream);
 /* Actor head: mean = sigmoid(logits); a = clip(mean + std*eps, 0, 1); logprob of a under
  * N(mean, std^2 I) (rlmil.py:82-90). */
 int murcl_actor_head(const float* logits, const float* eps, float std, float* action, float* logprob, float* mean,

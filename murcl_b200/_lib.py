@@ -59,6 +59,8 @@ SIGNATURES = {
     "murcl_ntxent_fwd_bwd_slab": (_i, [_p, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p]),
     "murcl_gru_cell_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_gru_cell_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "murcl_gru_cell_fwd_tape": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "murcl_gru_cell_bwd_tape": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "murcl_actor_head": (_i, [_p, _p, _f, _p, _p, _p, _i, _i, _p]),
     "murcl_cast": (_i, [_p, _i, _p, _i, _l, _p]),
     "murcl_row_segments": (_i, [_p, _i, _p, _p]),

@@ -56,6 +56,69 @@ __global__ void __launch_bounds__(256) gru_cell_bwd_kernel(const float* __restri
   if (dh_prev) dh_prev[i] = dh * z;
 }
 
+// ---- recurrent-head tape (murcl_b200/headtape.py): the same cell, laid out for a BATCHED backward over all the patch-steps ----
+// Forward: also writes h' in the GEMM storage type (the operand of the next step's W_hh product and of the output layer), so
+// no cast launch sits between the cell and the GEMMs.
+template <typename TS>
+__global__ void __launch_bounds__(256) gru_cell_fwd_tape_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                                                const float* __restrict__ h_prev, float* __restrict__ h_new,
+                                                                TS* __restrict__ h_new_s, TS* __restrict__ h_new_s2,
+                                                                float* __restrict__ gates, int B, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * H) return;
+  const int b = (int)(i / H), j = (int)(i % H);
+  const float* a = gi + (int64_t)b * 3 * H;
+  const float* c = gh + (int64_t)b * 3 * H;
+  const float r = sigmoidf_(a[j] + c[j]);
+  const float z = sigmoidf_(a[H + j] + c[H + j]);
+  const float n = tanhf(a[2 * H + j] + r * c[2 * H + j]);
+  const float hp = h_prev ? h_prev[i] : 0.f;
+  const float hn = (1.f - z) * n + z * hp;
+  h_new[i] = hn;
+  if (h_new_s) Store<TS>::store(h_new_s + i, hn);
+  if (h_new_s2) Store<TS>::store(h_new_s2 + i, hn);      // the next call's h_prev slot of the batched W_hh weight gradient
+  float* g = gates + (int64_t)b * 3 * H;
+  g[j] = r;
+  g[H + j] = z;
+  g[2 * H + j] = n;
+}
+
+// Backward: dh = dh_a + dh_b (storage type: the output layer's and the next cell's W_hh input gradients) + dh_c (fp32: the
+// next cell's direct z * dh term), any of them NULL; the gate gradients leave in the storage type, ready to be the operands
+// of the batched weight-gradient GEMMs and of the W_hh / W_ih input-gradient GEMMs.
+template <typename TS>
+__global__ void __launch_bounds__(256) gru_cell_bwd_tape_kernel(const TS* __restrict__ dh_a, const TS* __restrict__ dh_b,
+                                                                const float* __restrict__ dh_c, const float* __restrict__ gates,
+                                                                const float* __restrict__ gh, const float* __restrict__ h_prev,
+                                                                TS* __restrict__ dgi, TS* __restrict__ dgh,
+                                                                float* __restrict__ dh_prev, int B, int H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * H) return;
+  const int b = (int)(i / H), j = (int)(i % H);
+  const float* g = gates + (int64_t)b * 3 * H;
+  const float r = g[j], z = g[H + j], n = g[2 * H + j];
+  const float hn = gh[(int64_t)b * 3 * H + 2 * H + j];
+  const float hp = h_prev ? h_prev[i] : 0.f;
+  float dh = 0.f;
+  if (dh_a) dh += Store<TS>::load(dh_a + i);
+  if (dh_b) dh += Store<TS>::load(dh_b + i);
+  if (dh_c) dh += dh_c[i];
+  const float dn = dh * (1.f - z);
+  const float dz = dh * (hp - n);
+  const float dan = dn * (1.f - n * n);
+  const float dar = dan * hn * r * (1.f - r);
+  const float daz = dz * z * (1.f - z);
+  TS* o = dgi + (int64_t)b * 3 * H;
+  TS* q = dgh + (int64_t)b * 3 * H;
+  Store<TS>::store(o + j, dar);
+  Store<TS>::store(o + H + j, daz);
+  Store<TS>::store(o + 2 * H + j, dan);
+  Store<TS>::store(q + j, dar);
+  Store<TS>::store(q + H + j, daz);
+  Store<TS>::store(q + 2 * H + j, dan * r);
+  if (dh_prev) dh_prev[i] = dh * z;
+}
+
 __global__ void __launch_bounds__(128) actor_head_kernel(const float* __restrict__ logits, const float* __restrict__ eps,
                                                          float std, float* __restrict__ action, float* __restrict__ logprob,
                                                          float* __restrict__ mean, int B, int K) {
@@ -226,6 +289,37 @@ int murcl_gru_cell_bwd(const float* dh_new, const float* gates, const float* gh,
   gru_cell_bwd_kernel<<<ceil_div((int64_t)B * H, 256), 256, 0, as_stream(stream)>>>(dh_new, gates, gh, h_prev, dgi, dgh,
                                                                                      dh_prev, B, H);
   return check_launch("gru_cell_bwd_kernel");
+}
+
+int murcl_gru_cell_fwd_tape(const float* gi, const float* gh, const float* h_prev, float* h_new, void* h_new_s, void* h_new_s2,
+                            float* gates, int B, int H, int dtype, void* stream) {
+  MURCL_REQUIRE(gi && gh && h_new && gates, "gru_cell_fwd_tape: null pointer");
+  MURCL_REQUIRE(B >= 0 && H > 0, "gru_cell_fwd_tape: bad shape");
+  MURCL_REQUIRE(dtype == MURCL_F32 || dtype == MURCL_BF16, "gru_cell_fwd_tape: bad dtype %d", dtype);
+  if (B == 0) return MURCL_OK;
+  const int grid = ceil_div((int64_t)B * H, 256);
+  if (dtype == MURCL_BF16)
+    gru_cell_fwd_tape_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(gi, gh, h_prev, h_new, (__nv_bfloat16*)h_new_s,
+                                                                                 (__nv_bfloat16*)h_new_s2, gates, B, H);
+  else
+    gru_cell_fwd_tape_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(gi, gh, h_prev, h_new, (float*)h_new_s, (float*)h_new_s2, gates, B, H);
+  return check_launch("gru_cell_fwd_tape_kernel");
+}
+
+int murcl_gru_cell_bwd_tape(const void* dh_a, const void* dh_b, const float* dh_c, const float* gates, const float* gh,
+                            const float* h_prev, void* dgi, void* dgh, float* dh_prev, int B, int H, int dtype, void* stream) {
+  MURCL_REQUIRE(gates && gh && dgi && dgh, "gru_cell_bwd_tape: null pointer");
+  MURCL_REQUIRE(B >= 0 && H > 0, "gru_cell_bwd_tape: bad shape");
+  MURCL_REQUIRE(dtype == MURCL_F32 || dtype == MURCL_BF16, "gru_cell_bwd_tape: bad dtype %d", dtype);
+  if (B == 0) return MURCL_OK;
+  const int grid = ceil_div((int64_t)B * H, 256);
+  if (dtype == MURCL_BF16)
+    gru_cell_bwd_tape_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)dh_a, (const __nv_bfloat16*)dh_b, dh_c, gates, gh, h_prev, (__nv_bfloat16*)dgi, (__nv_bfloat16*)dgh, dh_prev, B, H);
+  else
+    gru_cell_bwd_tape_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dh_a, (const float*)dh_b, dh_c, gates, gh, h_prev,
+                                                                         (float*)dgi, (float*)dgh, dh_prev, B, H);
+  return check_launch("gru_cell_bwd_tape_kernel");
 }
 
 int murcl_actor_head(const float* logits, const float* eps, float std, float* action, float* logprob, float* mean, int B,

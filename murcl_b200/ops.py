@@ -148,9 +148,10 @@ def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None, relu_bits=False):
+def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None, relu_bits=False, out=None):
     """act(x w^T + bias).  ``relu_bits=True`` (ReLU layers, N % 64 == 0) also returns the 1-bit-per-output mask
-    ``[N/64, M]`` int64 that ``linear_bwd_input`` takes instead of re-reading the activation."""
+    ``[N/64, M]`` int64 that ``linear_bwd_input`` takes instead of re-reading the activation.  ``out`` (contiguous
+    ``[M, N]``) receives the result instead of a fresh tensor."""
     _chk(x, "linear_fwd.x"); _chk(w, "linear_fwd.w")
     if x.dtype != w.dtype:
         raise MurclError(f"linear_fwd: x is {x.dtype} but w is {w.dtype}")
@@ -158,8 +159,14 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None, relu_bits=False):
     N = w.shape[0]
     if w.shape[1] != K:
         raise MurclError(f"linear_fwd: shape mismatch x{tuple(x.shape)} w{tuple(w.shape)}")
-    out_dtype = out_dtype or x.dtype
-    y = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    if out is not None:
+        _chk(out, "linear_fwd.out")
+        if tuple(out.shape) != (M, N):
+            raise MurclError(f"linear_fwd: out is {tuple(out.shape)}, expected {(M, N)}")
+        out_dtype, y = out.dtype, out
+    else:
+        out_dtype = out_dtype or x.dtype
+        y = torch.empty((M, N), device=x.device, dtype=out_dtype)
     if bias is not None:
         _chk(bias, "linear_fwd.bias", torch.float32)
     bits = torch.empty((N // 64, M), device=x.device, dtype=torch.int64) if relu_bits else None
@@ -170,7 +177,7 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None, relu_bits=False):
 
 
 def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg=None, col_sum=None, out_scale=1.0,
-                     relu_bits=None):
+                     relu_bits=None, out=None):
     _chk(dy, "linear_bwd_input.dy"); _chk(w, "linear_bwd_input.w")
     if dy.dtype != w.dtype:
         raise MurclError(f"linear_bwd_input: dy is {dy.dtype} but w is {w.dtype}")
@@ -178,7 +185,11 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
     K = w.shape[1]
     if w.shape[0] != N:
         raise MurclError(f"linear_bwd_input: shape mismatch dy{tuple(dy.shape)} w{tuple(w.shape)}")
-    dx = torch.empty((M, K), device=dy.device, dtype=dy.dtype)
+    if out is not None:
+        _chk(out, "linear_bwd_input.out", dy.dtype)
+        if tuple(out.shape) != (M, K):
+            raise MurclError(f"linear_bwd_input: out is {tuple(out.shape)}, expected {(M, K)}")
+    dx = out if out is not None else torch.empty((M, K), device=dy.device, dtype=dy.dtype)
     if relu_src is not None:
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
     with _Timed("linear_bwd_input" if M >= 4096 else "head_bwd_input", 2.0 * M * N * K):

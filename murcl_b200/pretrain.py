@@ -7,6 +7,7 @@ PPO object are the drop-in modules, used through the same methods the reference 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -83,6 +84,12 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
     losses = []
     states = None
     sim_last = None
+    tape = None
+    if (stage != 2 and backward and getattr(fc, "fc_rnn", False) and hasattr(fc, "forward_views")
+            and os.environ.get("MURCL_DISABLE_HEADTAPE", "0") != "1"):
+        # Full_layer over the T x 2 calls of this step on the recurrent-head tape: batched backward (headtape.py)
+        from .headtape import HeadTape
+        tape = HeadTape(fc, T, 2, B, dev, getattr(fc, "precision", None) or precision or ops.default_precision())
     grad_mode = torch.no_grad() if stage == 2 else torch.enable_grad()
     with grad_mode:
         for t in range(T):
@@ -103,7 +110,9 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
                 draw = (actions, lams, perms)
             x_all = pack_views(store, draw, feat_size, dt, slot_bag)
             outputs, states = encode_views(model, x_all)
-            if hasattr(fc, "forward_views"):
+            if tape is not None:
+                outputs = tape.forward_views(outputs, restart=(t == 0))
+            elif hasattr(fc, "forward_views"):
                 outputs = fc.forward_views(outputs, restart=(t == 0))
             else:
                 outputs = [fc(o, restart=(t == 0)) for o in outputs]
@@ -119,6 +128,12 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
     if stage == 2:
         for m in memories:
             ppo.update(m)
+    elif backward and tape is not None:
+        # loss -> projections (the loss kernels' own tiny graph), projections -> bag embeddings (the tape, one batched pass),
+        # bag embeddings -> everything upstream (the aggregators' graphs, one per patch-step)
+        dzs = torch.autograd.grad(total, tape.z_leaves)
+        d_outs = tape.backward(dzs)
+        torch.autograd.backward(tape.x_inputs, d_outs)
     elif backward:
         total.backward()
     if memories is not None and not keep_memory:
