@@ -168,6 +168,7 @@ class Job:
         from murcl_b200.arena import ParamArena
         self.arena = ParamArena(self.params, shadow_dtype=torch.bfloat16 if self.precision == "bf16" else None)
         self.opt = torch.optim.Adam(self.arena.optimizer_params(), lr=1e-4, weight_decay=1e-5, capturable=True)
+        self.head_range = self.arena.range_of(list(self.fc.parameters()))      # Full_layer: 80 % of the gradient bytes
         self.mdist = mdist
         self.graphs = {}
         self.launches_per_step = None
@@ -205,11 +206,22 @@ class Job:
     def step(self, store, slot_bag):
         from murcl_b200 import pretrain
         self.arena.zero_grad()
+        pending = []
+        lo, hi = self.head_range
+
+        def exchange_heads():       # the head gradients are final here: their all-reduce overlaps the aggregators' backward
+            pending.append(self.arena.allreduce(lo=lo, hi=hi, async_op=True))
+
         loss, _ = pretrain.pretrain_step(store, self.model, self.fc, self.crit, T=self.a.T, feat_size=self.a.feat_size,
                                          alpha=0.9, stage=3, ppo=self.ppo, memories=self.memories,
-                                         precision=self.precision, slot_bag=slot_bag)
+                                         precision=self.precision, slot_bag=slot_bag,
+                                         after_head_backward=exchange_heads if self.world > 1 else None)
         if self.world > 1:
-            self.arena.allreduce()
+            self.arena.allreduce(lo=0, hi=lo)
+            self.arena.allreduce(lo=hi)
+            for w in pending:
+                if w is not None:
+                    w.wait()
         self.opt.step()
         self.arena.refresh()
         return loss

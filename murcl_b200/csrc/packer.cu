@@ -92,20 +92,37 @@ __global__ void __launch_bounds__(512) pack_select_kernel(const int32_t* __restr
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
   int32_t* out = sel_idx + (int64_t)slot * FS;
-  for (int64_t start = lo; start < hi; start += blockDim.x) {
+  // Stream compaction of the selection predicate in patch order.  A thread takes PER = 4 consecutive patches per
+  // round (a round covers 4 * blockDim patches, so a 15k-patch slide needs 8 rounds instead of 30; every round costs
+  // two CTA barriers and a dependent global load), positions come from a warp prefix over the per-thread counts plus the
+  // running base.
+  constexpr int PER = 4;
+  for (int64_t start = lo; start < hi; start += (int64_t)blockDim.x * PER) {
     const int base = s_base;
     if (base >= FS) break;                       // uniform: s_base is read after a barrier
-    const int64_t p = start + threadIdx.x;
-    bool keep = false;
-    if (p < hi) {
-      const int c = patch_cluster[p];
-      if (c >= 0 && c < K) {
-        const int r = patch_rank[p];
-        keep = (r >= w_start[c]) && (r < w_stop[c]);
+    const int64_t p0 = start + (int64_t)threadIdx.x * PER;
+    bool keep[PER];
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      const int64_t p = p0 + e;
+      keep[e] = false;
+      if (p < hi) {
+        const int c = patch_cluster[p];
+        if (c >= 0 && c < K) {
+          const int r = patch_rank[p];
+          keep[e] = (r >= w_start[c]) && (r < w_stop[c]);
+        }
       }
+      cnt += keep[e] ? 1 : 0;
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_tot[w] = __popc(ballot);
+    int incl = cnt;                              // inclusive prefix of the counts within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[w] = incl;
     __syncthreads();
     int before = 0, total = 0;
     for (int ww = 0; ww < nw; ++ww) {
@@ -113,8 +130,14 @@ __global__ void __launch_bounds__(512) pack_select_kernel(const int32_t* __restr
       before += (ww < w) ? t : 0;
       total += t;
     }
-    const int pos = base + before + __popc(ballot & ((1u << lane) - 1u));
-    if (keep && pos < FS) out[pos] = (int32_t)p;
+    int pos = base + before + incl - cnt;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      if (keep[e]) {
+        if (pos < FS) out[pos] = (int32_t)(p0 + e);
+        ++pos;
+      }
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_base = base + total;
     __syncthreads();

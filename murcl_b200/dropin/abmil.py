@@ -36,7 +36,9 @@ class ABMIL(nn.Module):
         rows of each bag to ``forward`` (same number of bags, in the same order, on every rank; a rank may hold none of a
         bag's rows only if another holds some).  Pooling partials are merged with one all-gather; the outputs are the
         whole-bag results on every rank and the parameter gradients are per-rank partial sums (sum them with
-        ``dist.allreduce_grads``, as for data parallelism)."""
+        ``dist.allreduce_grads``, as for data parallelism).  The decoder works on the merged, replicated bag vector: its
+        parameter gradients are pre-divided by the group size so that the same sum over ranks is exact for them too.  Any
+        layer applied AFTER this module sees replicated inputs as well (average, do not sum, its gradients)."""
         self.shard_rows, self.shard_group = bool(enabled), group
         return self
 
@@ -56,7 +58,15 @@ class ABMIL(nn.Module):
         M, p, _s, _il, _pr = ops.mil_aggregate(rows.rows, rows.offsets, rows.row_seg, self._meta(rows),
                                                self.attention[0].weight, self.attention[0].bias,
                                                self.attention[2].weight, self.attention[2].bias, None, None, enc)
-        out = ops.linear(M, self.decoder[0].weight, self.decoder[0].bias, ops.ACT_RELU, self._meta(rows)["dtype"])
+        dw, db = self.decoder[0].weight, self.decoder[0].bias
+        if self.shard_rows:
+            # the pooled vectors are identical on every rank of the shard group, so the decoder's parameter gradients are
+            # complete on each of them already: pre-divide by the group size so that the usual sum over ranks is exact
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.shard_group) > 1:
+                f = 1.0 / dist.get_world_size(self.shard_group)
+                dw, db = ops.scale_grad(dw, f), ops.scale_grad(db, f)
+        out = ops.linear(M, dw, db, ops.ACT_RELU, self._meta(rows)["dtype"])
         self.last_attention = p             # [n_rows] pooling weights incl. the 1/sqrt(N) post-scale (abmil.py:40-41)
         return out, p
 

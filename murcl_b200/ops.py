@@ -454,6 +454,23 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, a
     return _Linear.apply(x, w, b, act, dtype)
 
 
+class _ScaleGrad(torch.autograd.Function):
+    """Identity in the forward pass; the gradient is multiplied by ``factor`` on the way back."""
+
+    @staticmethod
+    def forward(ctx, t, factor):
+        ctx.factor = factor
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.factor, None
+
+
+def scale_grad(t: torch.Tensor, factor: float) -> torch.Tensor:
+    return _ScaleGrad.apply(t, float(factor))
+
+
 class _GRUCell(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gi, gh, h_prev):

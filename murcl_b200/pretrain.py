@@ -59,7 +59,7 @@ def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
 def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_size: int = 1024, alpha: float = 0.9,
                   stage: int = 1, ppo=None, memories=None, draws: Optional[Sequence[Draw]] = None,
                   precision: Optional[str] = None, backward: bool = True, eps=None, keep_memory: bool = False,
-                  slot_bag: Optional[torch.Tensor] = None):
+                  slot_bag: Optional[torch.Tensor] = None, after_head_backward=None):
     """Returns ``(loss, per-step losses)``.  ``stage`` follows train_MuRCL.py: 1 = random actions; 3 = the PPO actor
     chooses the actions of patch-steps >= 1 (the actor is not updated, :292-295); 2 = the same rollout under ``no_grad``
     with the MIL model frozen, then ``ppo.update(m)`` for each view's memory instead of the optimiser step (:244-247,
@@ -67,7 +67,10 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
     ``None`` actions at ``t >= 1`` in stages 2/3 mean "ask the actor", with ``eps[t]`` (one ``[B, K]`` tensor per view) as
     its Gaussian draws.  ``keep_memory`` leaves the rollout in ``memories`` (the reference clears it, :301-302).
     ``slot_bag`` (int32 ``[2B]`` on the device: the store's bag index of every packed slot, view 0 then view 1) selects
-    the step's B slides out of a larger resident store (``csr.ResidentSlides``); default: all bags of ``store``."""
+    the step's B slides out of a larger resident store (``csr.ResidentSlides``); default: all bags of ``store``.
+    ``after_head_backward`` (callable) runs once the projection head's parameter gradients are complete - i.e. right after
+    the recurrent-head tape's batched backward and before the aggregators' - so that a data-parallel trainer can start
+    exchanging them (``ParamArena.allreduce(..., async_op=True)``) under the rest of the backward pass."""
     if stage not in (1, 2, 3):
         raise ValueError("train_stage must be 1, 2 or 3")
     if stage != 1 and (ppo is None or memories is None):
@@ -133,6 +136,8 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         # bag embeddings -> everything upstream (the aggregators' graphs, one per patch-step)
         dzs = torch.autograd.grad(total, tape.z_leaves)
         d_outs = tape.backward(dzs)
+        if after_head_backward is not None:
+            after_head_backward()
         torch.autograd.backward(tape.x_inputs, d_outs)
     elif backward:
         total.backward()
