@@ -386,8 +386,8 @@ def epoch_batches(n_slides, bags, n_epochs, seed):
 
 
 def measure_fp32(a, rank, world, device):
-    """Secondary measurement: the same optimiser step in fp32 mode (the reference's precision: fp32 slide store, exact
-    FFMA GEMMs, 1e-5 parity budget), eager launches (a 0.3 s step is not launch-bound)."""
+    """Secondary measurement: the same optimiser step in fp32 mode (the reference's precision: fp32 slide store, fp32-exact
+    GEMMs - bf16 tensor cores on 3-plane splits of the fp32 operands -, 1e-5 parity budget), eager launches."""
     from murcl_b200.csr import BagStore
     host = make_host_batch(a, seed=3000 + rank, pin=False, precision="fp32")
     store = BagStore.empty_like_host(host, device)
@@ -399,7 +399,8 @@ def measure_fp32(a, rank, world, device):
     ms = timed(lambda i: job.step(store, slot_bag), a.fp32_steps, world, device)
     out = {"dtype": "f32", "value": round(a.bags * world * a.fp32_steps / (ms * 1e-3), 2), "unit": UNIT,
            "ms_per_step": round(ms / a.fp32_steps, 3), "steps": a.fp32_steps, "warmup": 2, "cuda_graph": False,
-           "slide_store_dtype": "f32", "note": "same cfg3 step, fp32 storage and exact FFMA arithmetic (1e-5 parity mode)"}
+           "slide_store_dtype": "f32", "gemm": "tcgen05 split precision: 3 bf16 planes per fp32 operand, 6 exact products (MURCL_FP32_GEMM=split3)",
+           "note": "same cfg3 step in the reference's precision: fp32 storage, fp32-exact arithmetic (1e-5 parity mode)"}
     del job, store, host
     torch.cuda.empty_cache()
     return out

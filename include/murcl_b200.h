@@ -113,6 +113,30 @@ int64_t murcl_linear_bwd_weight_workspace(int64_t M, int N, int K);
 int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db, int64_t M, int N, int K,
                             int dtype, int backend, float* workspace, int accumulate, void* stream);
 
+/* ---- exact-fp32 dense layers on the bf16 tensor cores (split precision) -------------------------------------------
+ * The reference computes in fp32; the 1e-5 parity mode used to run on FFMA only (25 TFLOP/s).  An fp32 value
+ * is the exact sum of bf16 planes  x = hi + mid (+ lo)  (hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid)), a
+ * product of two bf16 numbers is exact in the fp32 accumulator of tcgen05.mma, so  x.y = sum of plane products:  with two
+ * planes the three products hi.hi + hi.mid + mid.hi drop terms up to 3 * 2^-18 |x||y| (measured: 6e-6 of the output scale
+ * per layer - outside the 1e-5 budget once layers compound), with three planes six products reach 2^-24 (measured 1e-6:
+ * the default of the fp32 mode).  murcl_split_planes writes the planes stacked along the
+ * rows, [planes][plane_rows][cols] bf16, rows [rows, plane_rows) zero; plane_rows % 64 == 0 whenever the rows are a
+ * reduction dimension (weights: always; activations: for the weight gradient).  The *_split GEMMs take such stacks for both
+ * operands and write fp32; their fused epilogues are those of murcl_linear_fwd / murcl_linear_bwd_input (the ReLU bit mask
+ * and the column sums are separate passes here).  murcl_linear_split_supported(M, N, K): M >= 1024, N % 64 == 0 (>= 128),
+ * K % 64 == 0. */
+int murcl_split_planes(const float* src, int64_t rows, int cols, int planes, int64_t plane_rows, void* dst, void* stream);
+int murcl_linear_split_supported(int64_t M, int N, int K);
+int murcl_linear_fwd_split(const void* xp, const void* wp, const float* bias, float* y, int64_t M, int N, int K, int act,
+                           int planes, int64_t x_plane_rows, int64_t w_plane_rows, uint64_t* relu_bits, void* stream);
+int murcl_linear_bwd_input_split(const void* dyp, const void* wp, float* dx, int64_t M, int N, int K, const float* row_scale,
+                                 const float* row_vec, const int32_t* row_seg, float* col_sum, float out_scale,
+                                 const uint64_t* relu_bits, int planes, int64_t dy_plane_rows, int64_t w_plane_rows,
+                                 void* stream);
+int64_t murcl_linear_bwd_weight_split_workspace(int64_t M, int N, int K);
+int murcl_linear_bwd_weight_split(const void* dyp, const void* xp, float* dw, int64_t M, int N, int K, int planes,
+                                  int64_t plane_rows, float* workspace, int accumulate, void* stream);
+
 /* ---- (2) attention pooling: abmil.py:38-42, clam.py:37-60,139-170 --------------------- */
 
 /* Raw attention score s[n] = sum_d wc[d]*g[n,d] + bc with g = u (gated=0, uv is [N,D]) or

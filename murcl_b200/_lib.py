@@ -34,6 +34,12 @@ SIGNATURES = {
     "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _p, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),
     "murcl_linear_bwd_weight": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _p, _i, _p]),
+    "murcl_split_planes": (_i, [_p, _l, _i, _i, _l, _p, _p]),
+    "murcl_linear_split_supported": (_i, [_l, _i, _i]),
+    "murcl_linear_fwd_split": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _l, _l, _p, _p]),
+    "murcl_linear_bwd_input_split": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _f, _p, _i, _l, _l, _p]),
+    "murcl_linear_bwd_weight_split_workspace": (_l, [_l, _i, _i]),
+    "murcl_linear_bwd_weight_split": (_i, [_p, _p, _p, _l, _i, _i, _i, _l, _p, _i, _p]),
     "murcl_attn_score_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p]),
     "murcl_seg_softmax": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "murcl_attnpool_supported": (_i, [_i, _i, _i, _i]),

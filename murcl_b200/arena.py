@@ -77,6 +77,9 @@ class ParamArena:
         change of the fp32 values: ``load_state_dict``, manual edits)."""
         if self.shadow is not None:
             ops.cast_into(self.flat, self.shadow)
+        # the optimiser updates the flat leaf: the parameter views' own version counters do not move, so every cache keyed
+        # on them (bf16 casts outside the arena, the split-precision planes of the fp32 mode) is dropped explicitly
+        ops.invalidate_weight_cache()
 
     def range_of(self, params) -> tuple:
         """Flat element range ``(lo, hi)`` covering ``params``, which must be consecutive members of the arena."""

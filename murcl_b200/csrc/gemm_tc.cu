@@ -64,6 +64,13 @@ struct Params {
   int64_t k_chunk;    // reduction range per split (multiple of BLOCK_K)
   int64_t split_stride;
   int m_tiles, n_tiles;
+  // Split-precision mode (exact-fp32 GEMMs on the bf16 tensor cores): the operands are stacks of bf16 PLANES of an fp32
+  // tensor (x = hi + mid [+ lo], planes stacked along the rows, `*_plane_rows` apart) and a tile accumulates `terms`
+  // products A_plane[pa[i]] . B_plane[pb[i]] over the same reduction range into one fp32 TMEM accumulator, smallest
+  // terms first.  terms <= 1: plain bf16 GEMM.
+  int terms;
+  int pa[6], pb[6];
+  int a_plane_rows, b_plane_rows;
 };
 
 // CG = cta_group: 1 = one SM per 128 x BN tile; 2 = a CTA pair shares a 256 x BN tile (each CTA holds its 128 rows of A
@@ -213,6 +220,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         k_range(sp, k0, nkb);
         const int m0 = (mb * CG + (int)cta_rank) * BLOCK_M;                   // this CTA's 128 rows of the tile
         const int n0 = nb * BN + (int)cta_rank * (BN / CG);                    // this CTA's share of the B rows
+        const int nterms = p.terms > 1 ? p.terms : 1;
+        for (int term = 0; term < nterms; ++term) {
+        const int ra = p.terms > 1 ? p.pa[term] * p.a_plane_rows : 0;         // row offset of this term's A / B plane
+        const int rb = p.terms > 1 ? p.pb[term] * p.b_plane_rows : 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t a_dst = tiles + s * C::STAGE_BYTES;
@@ -233,32 +244,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // both CTAs load their halves; all bytes are counted on the LEADER's full barrier (it issues the MMAs)
             if (leader) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
             const uint32_t fb = mapa(full_bar(s), 0);
-            tma_load_2d_2sm(a_dst, &map_a, fb, kk, m0);
+            tma_load_2d_2sm(a_dst, &map_a, fb, kk, m0 + ra);
             if (!B_MN) {
-              tma_load_2d_2sm(b_dst, &map_b, fb, kk, n0);
+              tma_load_2d_2sm(b_dst, &map_b, fb, kk, n0 + rb);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / CG / 64; ++j) tma_load_2d_2sm(b_dst + j * 8192, &map_b, fb, n0 + 64 * j, kk);
+              for (int j = 0; j < BN / CG / 64; ++j) tma_load_2d_2sm(b_dst + j * 8192, &map_b, fb, n0 + 64 * j, kk + rb);
             }
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
             continue;
           }
           mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
           if (!A_MN) {
-            tma_load_2d(a_dst, &map_a, full_bar(s), kk, m0);                    // box {64 k, 128 rows}
+            tma_load_2d(a_dst, &map_a, full_bar(s), kk, m0 + ra);               // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)                               // box {64 m, 64 k-rows}
-              tma_load_2d(a_dst + j * 8192, &map_a, full_bar(s), m0 + 64 * j, kk);
+              tma_load_2d(a_dst + j * 8192, &map_a, full_bar(s), m0 + 64 * j, kk + ra);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &map_b, full_bar(s), kk, n0);                    // box {64 k, BN rows}
+            tma_load_2d(b_dst, &map_b, full_bar(s), kk, n0 + rb);               // box {64 k, BN rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * 8192, &map_b, full_bar(s), n0 + 64 * j, kk);
+              tma_load_2d(b_dst + j * 8192, &map_b, full_bar(s), n0 + 64 * j, kk + rb);
           }
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
         }
       }
     }
@@ -282,7 +294,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           p.trace[((t - tile_first) / tile_step) * 24 + 0] = ts;
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nkb_all = nkb * (p.terms > 1 ? p.terms : 1);              // split precision: every term adds nkb k-blocks
+        for (int kb = 0; kb < nkb_all; ++kb) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
           const uint32_t a_src = tiles + s * C::STAGE_BYTES;
@@ -918,6 +931,115 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
   p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
+                 : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
+  if (rc != MURCL_OK) return rc;
+  const int64_t n = (int64_t)N * K;
+  return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);
+}
+
+// ---- split-precision (exact-fp32) entry points -----------------------------------------------------------------
+// Operands are stacks of bf16 planes [planes][plane_rows][cols] of fp32 tensors (murcl_split_planes).  planes == 2:
+// x ~ hi + mid, three products (mid.hi, hi.mid, hi.hi): every product is exact in the fp32 accumulator and the dropped
+// terms are below 3 * 2^-18 of |x||y|; planes == 3: six products, all terms down to 2^-24.  Smallest terms first.
+static void split_terms(Params& p, int planes, int64_t a_plane_rows, int64_t b_plane_rows) {
+  static const int t2a[3] = {1, 0, 0}, t2b[3] = {0, 1, 0};
+  static const int t3a[6] = {2, 0, 1, 1, 0, 0}, t3b[6] = {0, 2, 1, 0, 1, 0};
+  p.terms = planes == 2 ? 3 : 6;
+  for (int i = 0; i < p.terms; ++i) {
+    p.pa[i] = planes == 2 ? t2a[i] : t3a[i];
+    p.pb[i] = planes == 2 ? t2b[i] : t3b[i];
+  }
+  p.a_plane_rows = (int)a_plane_rows;
+  p.b_plane_rows = (int)b_plane_rows;
+}
+
+bool tc_split_supported(int64_t M, int N, int K) {
+  return tc_enabled() && M >= 1024 && N >= 128 && N % 64 == 0 && K >= 64 && K % 64 == 0 && 3 * ((M + 63) / 64 * 64) < (1ll << 31);
+}
+
+// y[M,N] fp32 = act(x w^T + bias); xp planes [planes][xpr][K], wp planes [planes][wpr][K]
+int tc_split_fwd(const void* xp, const void* wp, const float* bias, float* y, int64_t M, int N, int K, int act, int planes,
+                 int64_t xpr, int64_t wpr, cudaStream_t st) {
+  if (!aligned16(xp) || !aligned16(wp) || !aligned16(y) || (bias && !aligned16(bias))) {
+    set_error("linear_fwd_split: operands must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ma, mb, mc;
+  int rc = make_map(&ma, xp, planes * xpr, K, BLOCK_K, BLOCK_M);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, wp, planes * wpr, K, BLOCK_K, BN);
+  if (rc != MURCL_OK) return rc;
+  rc = make_store_map(&mc, y, M, N, 4);
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = y; p.bias = bias; p.act = act;
+  p.splits = 1; p.k_chunk = ((int64_t)K + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
+  split_terms(p, planes, xpr, wpr);
+  return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, mc, p, st)
+                   : launch<128, false, false, EPI_FWD, float>(ma, mb, mc, p, st);
+}
+
+// dx[M,K] fp32 = (dy w) with the fused epilogue terms; dyp planes [planes][dpr][N], wp planes [planes][wpr][K]
+int tc_split_bwd_input(const void* dyp, const void* wp, float* dx, int64_t M, int N, int K, const float* row_scale,
+                       const float* row_vec, const int32_t* row_seg, float out_scale, const unsigned long long* relu_bits,
+                       int planes, int64_t dpr, int64_t wpr, cudaStream_t st) {
+  if (!aligned16(dyp) || !aligned16(wp) || !aligned16(dx) || (row_vec && !aligned16(row_vec))) {
+    set_error("linear_bwd_input_split: operands must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  const int BN = (K % 256 == 0) ? 256 : 128;
+  CUtensorMap ma, mb, mc;
+  int rc = make_map(&ma, dyp, planes * dpr, N, BLOCK_K, BLOCK_M);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, wp, planes * wpr, K, 64, BLOCK_K);                  // MN-major: rows = reduction index n (+ plane offset)
+  if (rc != MURCL_OK) return rc;
+  rc = make_store_map(&mc, dx, M, K, 4);
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = M; p.N = K; p.K = N; p.ldc = K; p.C = dx;
+  p.row_scale = row_scale; p.row_vec = row_vec; p.row_seg = row_seg;
+  p.out_scale = out_scale; p.bits_in = relu_bits;
+  p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  split_terms(p, planes, dpr, wpr);
+  return BN == 256 ? launch<256, false, true, EPI_DGRAD, float>(ma, mb, mc, p, st)
+                   : launch<128, false, true, EPI_DGRAD, float>(ma, mb, mc, p, st);
+}
+
+int64_t tc_split_bwd_weight_workspace(int64_t M, int N, int K) {
+  int BN, splits;
+  int64_t kc;
+  wgrad_plan(M, N, K, BN, splits, kc);
+  return (int64_t)splits * N * K;
+}
+
+// dw[N,K] (+)= dy^T x; dyp planes [planes][pr][N], xp planes [planes][pr][K]; pr % 64 == 0 with zero padding rows
+int tc_split_bwd_weight(const void* dyp, const void* xp, float* dw, int64_t M, int N, int K, int planes, int64_t pr,
+                        float* workspace, cudaStream_t st, int accumulate) {
+  if (!aligned16(dyp) || !aligned16(xp) || !aligned16(dw) || !aligned16(workspace) || workspace == nullptr) {
+    set_error("linear_bwd_weight_split: operands must be 16-byte aligned and a workspace is required");
+    return MURCL_EINVAL;
+  }
+  if (pr % BLOCK_K != 0) {
+    set_error("linear_bwd_weight_split: plane pitch %lld must be a multiple of %d rows", (long long)pr, BLOCK_K);
+    return MURCL_EINVAL;
+  }
+  int BN, splits;
+  int64_t k_chunk;
+  wgrad_plan(M, N, K, BN, splits, k_chunk);
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dyp, planes * pr, N, 64, BLOCK_K);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, xp, planes * pr, K, 64, BLOCK_K);
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
+  p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
+  p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  split_terms(p, planes, pr, pr);
   rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
                  : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
   if (rc != MURCL_OK) return rc;

@@ -147,6 +147,32 @@ __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ src, T
   }
 }
 
+// fp32 -> stack of bf16 planes: hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid); plane p at rows
+// [p * plane_rows, +rows), the padding rows [rows, plane_rows) are written as zeros (they take part in reductions over rows).
+template <int PLANES>
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t plane_rows,
+                                                           __nv_bfloat16* __restrict__ dst) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;        // element index within a padded plane
+  const int64_t n_pad = plane_rows * cols;
+  if (i >= n_pad) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < rows * (int64_t)cols) v = *reinterpret_cast<const float4*>(src + i);
+  float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int pl = 0; pl < PLANES; ++pl) {
+    __nv_bfloat16 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h[e] = __float2bfloat16_rn(r[e]);
+      r[e] -= __bfloat162float(h[e]);                                              // exact: the residual of an RN rounding
+    }
+    uint2 q;
+    q.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    q.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    *reinterpret_cast<uint2*>(dst + (int64_t)pl * n_pad + i) = q;
+  }
+}
+
 __global__ void __launch_bounds__(256) row_segments_kernel(const int64_t* __restrict__ offsets, int32_t* __restrict__ row_seg) {
   const int b = blockIdx.x;
   const int64_t lo = offsets[b], hi = offsets[b + 1];
@@ -320,6 +346,18 @@ int murcl_gru_cell_bwd_tape(const void* dh_a, const void* dh_b, const float* dh_
     gru_cell_bwd_tape_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dh_a, (const float*)dh_b, dh_c, gates, gh, h_prev,
                                                                          (float*)dgi, (float*)dgh, dh_prev, B, H);
   return check_launch("gru_cell_bwd_tape_kernel");
+}
+
+int murcl_split_planes(const float* src, int64_t rows, int cols, int planes, int64_t plane_rows, void* dst, void* stream) {
+  MURCL_REQUIRE(src && dst, "split_planes: null pointer");
+  MURCL_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && plane_rows >= rows && (planes == 2 || planes == 3),
+                "split_planes: bad shape rows=%lld cols=%d plane_rows=%lld planes=%d", (long long)rows, cols, (long long)plane_rows, planes);
+  MURCL_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "split_planes: 16-byte alignment");
+  if (plane_rows == 0) return MURCL_OK;
+  const int grid = ceil_div(plane_rows * cols, 1024);
+  if (planes == 2) split_planes_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(src, rows, cols, plane_rows, (__nv_bfloat16*)dst);
+  else split_planes_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(src, rows, cols, plane_rows, (__nv_bfloat16*)dst);
+  return check_launch("split_planes_kernel");
 }
 
 int murcl_actor_head(const float* logits, const float* eps, float std, float* action, float* logprob, float* mean, int B,

@@ -22,6 +22,12 @@ int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
 int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t, int accumulate);
 
 int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st, int accumulate = 0);
+bool tc_split_supported(int64_t M, int N, int K);
+int tc_split_fwd(const void*, const void*, const float*, float*, int64_t, int, int, int, int, int64_t, int64_t, cudaStream_t);
+int tc_split_bwd_input(const void*, const void*, float*, int64_t, int, int, const float*, const float*, const int32_t*, float,
+                       const unsigned long long*, int, int64_t, int64_t, cudaStream_t);
+int64_t tc_split_bwd_weight_workspace(int64_t, int, int);
+int tc_split_bwd_weight(const void*, const void*, float*, int64_t, int, int, int, int64_t, float*, cudaStream_t, int);
 }  // namespace murcl
 
 using namespace murcl;
@@ -107,6 +113,52 @@ int murcl_linear_bwd_weight(const void* dy, const void* x, float* dw, float* db,
   }
   if (backend != MURCL_GEMM_SIMT && tc_ok) return tc_linear_bwd_weight(dy, x, dw, M, N, K, workspace, st, accumulate);
   return simt_linear_bwd_weight(dy, x, dw, M, N, K, dtype, workspace, st, accumulate);
+}
+
+/* ---- exact-fp32 dense layers on the bf16 tensor cores (split precision) ---- */
+int murcl_linear_split_supported(int64_t M, int N, int K) { return tc_split_supported(M, N, K) ? 1 : 0; }
+
+int murcl_linear_fwd_split(const void* xp, const void* wp, const float* bias, float* y, int64_t M, int N, int K, int act,
+                           int planes, int64_t x_plane_rows, int64_t w_plane_rows, uint64_t* relu_bits, void* stream) {
+  MURCL_REQUIRE(xp && wp && y, "linear_fwd_split: null pointer");
+  MURCL_REQUIRE(tc_split_supported(M, N, K) && (planes == 2 || planes == 3), "linear_fwd_split: unsupported shape M=%lld N=%d K=%d",
+                (long long)M, N, K);
+  MURCL_REQUIRE(x_plane_rows >= M && w_plane_rows >= N, "linear_fwd_split: plane pitch smaller than the tensor");
+  MURCL_REQUIRE(act >= MURCL_ACT_NONE && act <= MURCL_ACT_TANH_SIGMOID, "linear_fwd_split: bad activation %d", act);
+  MURCL_REQUIRE(relu_bits == nullptr || (act == MURCL_ACT_RELU && N % 64 == 0), "linear_fwd_split: bit mask needs ReLU and N %% 64 == 0");
+  int rc = tc_split_fwd(xp, wp, bias, y, M, N, K, act, planes, x_plane_rows, w_plane_rows, as_stream(stream));
+  if (rc != MURCL_OK || relu_bits == nullptr) return rc;
+  return launch_relu_bits(y, M, N, MURCL_F32, reinterpret_cast<unsigned long long*>(relu_bits), as_stream(stream));
+}
+
+int murcl_linear_bwd_input_split(const void* dyp, const void* wp, float* dx, int64_t M, int N, int K, const float* row_scale,
+                                 const float* row_vec, const int32_t* row_seg, float* col_sum, float out_scale,
+                                 const uint64_t* relu_bits, int planes, int64_t dy_plane_rows, int64_t w_plane_rows,
+                                 void* stream) {
+  MURCL_REQUIRE(dyp && wp && dx, "linear_bwd_input_split: null pointer");
+  MURCL_REQUIRE(tc_split_supported(M, K, N) && (planes == 2 || planes == 3), "linear_bwd_input_split: unsupported shape M=%lld N=%d K=%d",
+                (long long)M, N, K);
+  MURCL_REQUIRE((row_scale == nullptr) == (row_vec == nullptr) && (row_scale == nullptr) == (row_seg == nullptr),
+                "linear_bwd_input_split: row_scale, row_vec and row_seg must be given together");
+  MURCL_REQUIRE(dy_plane_rows >= M && w_plane_rows >= N && w_plane_rows % 64 == 0, "linear_bwd_input_split: bad plane pitch");
+  if (out_scale == 0.f) out_scale = 1.f;
+  MURCL_REQUIRE(out_scale == 1.f || relu_bits != nullptr, "linear_bwd_input_split: out_scale is the dropout factor of a masked ReLU");
+  int rc = tc_split_bwd_input(dyp, wp, dx, M, N, K, row_scale, row_vec, row_seg, out_scale,
+                              reinterpret_cast<const unsigned long long*>(relu_bits), planes, dy_plane_rows, w_plane_rows,
+                              as_stream(stream));
+  if (rc != MURCL_OK || col_sum == nullptr) return rc;
+  return colsum_impl(dx, M, K, MURCL_F32, col_sum, as_stream(stream), 1);
+}
+
+int64_t murcl_linear_bwd_weight_split_workspace(int64_t M, int N, int K) { return tc_split_bwd_weight_workspace(M, N, K); }
+
+int murcl_linear_bwd_weight_split(const void* dyp, const void* xp, float* dw, int64_t M, int N, int K, int planes,
+                                  int64_t plane_rows, float* workspace, int accumulate, void* stream) {
+  MURCL_REQUIRE(dyp && xp && dw && workspace, "linear_bwd_weight_split: null pointer");
+  MURCL_REQUIRE(M >= 1024 && N >= 128 && N % 64 == 0 && K >= 128 && K % 64 == 0 && (planes == 2 || planes == 3),
+                "linear_bwd_weight_split: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+  MURCL_REQUIRE(plane_rows >= M && plane_rows % 64 == 0, "linear_bwd_weight_split: plane pitch must be >= M and a multiple of 64");
+  return tc_split_bwd_weight(dyp, xp, dw, M, N, K, planes, plane_rows, workspace, as_stream(stream), accumulate);
 }
 
 }  // extern "C"

@@ -132,7 +132,12 @@ def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     Un-versioned ``.data`` edits need ``invalidate_weight_cache()``."""
     if w.dtype == dtype:
         d = w.detach()
-        return d if d.is_contiguous() else d.contiguous()
+        d = d if d.is_contiguous() else d.contiguous()
+        try:
+            d._murcl_src = w             # lets the split-precision path cache the weight's bf16 planes on the parameter
+        except AttributeError:
+            pass
+        return d
     sh = getattr(w, "_murcl_shadow", None)          # ParamArena: one multi-tensor cast per optimiser step keeps it fresh
     if sh is not None and sh.dtype == dtype and sh.device == w.device:
         return sh
@@ -143,6 +148,64 @@ def weight_as(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     out = cast(w.detach().contiguous(), dtype)
     try:
         w._murcl_cast = (key, out)
+    except AttributeError:
+        pass
+    return out
+
+
+# ---- exact-fp32 GEMMs on the bf16 tensor cores (split precision; include/murcl_b200.h) -------------------------------
+def fp32_gemm_planes() -> int:
+    """MURCL_FP32_GEMM = split3 (default: 3 bf16 planes, 6 products, every term down to 2^-24: holds the 1e-5 budget on
+    attention weights with a 10x margin) | split2 (2 planes, 3 products: ~6e-6 of the output scale per layer, measured
+    1.1e-5 on attention weights - NOT within the parity budget, a faster approximate mode) | simt (FFMA only)."""
+    m = os.environ.get("MURCL_FP32_GEMM", "split3").lower()
+    if m not in ("simt", "split2", "split3"):
+        raise MurclError(f"MURCL_FP32_GEMM must be simt, split2 or split3, got {m!r}")
+    return {"simt": 0, "split2": 2, "split3": 3}[m]
+
+
+def _split_ok(M, N, K, *tensors) -> int:
+    planes = fp32_gemm_planes()
+    if planes == 0 or _backend() == GEMM_SIMT or any(t.dtype != torch.float32 for t in tensors):
+        return 0
+    return planes if _lib.load().murcl_linear_split_supported(int(M), int(N), int(K)) else 0
+
+
+def split_planes(t: torch.Tensor, planes: int):
+    """fp32 [rows, cols] -> (bf16 [planes, plane_rows, cols], plane_rows) with plane_rows = rows rounded up to 64 (zero rows)."""
+    _chk(t, "split_planes.t", torch.float32)
+    rows, cols = t.shape
+    pr = (rows + 63) // 64 * 64
+    buf = torch.empty((planes, pr, cols), device=t.device, dtype=torch.bfloat16)
+    check(_lib.load().murcl_split_planes(_p(t), rows, cols, planes, pr, _p(buf), _s()), "murcl_split_planes")
+    return buf, pr
+
+
+_last_planes = [None]        # (tensor object, version, planes, (buf, pr)): the gradient a layer's dgrad and wgrad both split
+
+
+def _act_planes(t: torch.Tensor, planes: int, remember: bool = False):
+    hit = _last_planes[0]
+    if hit is not None and hit[0] is t and hit[1] == t._version and hit[2] == planes:
+        return hit[3]
+    out = split_planes(t, planes)
+    if remember:
+        _last_planes[0] = (t, t._version, planes, out)      # holds `t` alive, so its address cannot be recycled under the key
+    return out
+
+
+def _weight_planes(w: torch.Tensor, planes: int):
+    """Planes of a weight, cached on the PARAMETER it was detached from (``weight_as`` tags the detached view)."""
+    src = getattr(w, "_murcl_src", None)
+    if src is None:
+        return split_planes(w, planes)
+    key = (src.data_ptr(), src.device, src._version, planes, tuple(src.shape), _weight_epoch)
+    hit = getattr(src, "_murcl_planes", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    out = split_planes(w, planes)
+    try:
+        src._murcl_planes = (key, out)
     except AttributeError:
         pass
     return out
@@ -170,6 +233,13 @@ def linear_fwd(x, w, bias, act=ACT_NONE, out_dtype=None, relu_bits=False, out=No
     if bias is not None:
         _chk(bias, "linear_fwd.bias", torch.float32)
     bits = torch.empty((N // 64, M), device=x.device, dtype=torch.int64) if relu_bits else None
+    planes = _split_ok(M, N, K, x, w, y)
+    if planes:
+        (xp, xpr), (wp, wpr) = _act_planes(x, planes), _weight_planes(w, planes)
+        with _Timed("linear_fwd", 2.0 * M * N * K):
+            check(_lib.load().murcl_linear_fwd_split(_p(xp), _p(wp), _p(bias), _p(y), M, N, K, act, planes, xpr, wpr, _p(bits), _s()),
+                  "murcl_linear_fwd_split")
+        return (y, bits) if relu_bits else y
     with _Timed("linear_fwd" if M >= 4096 else "head_fwd", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_fwd(_p(x), _p(w), _p(bias), _p(y), M, N, K, act, _dt(x), _DT[out_dtype], _backend(),
                                            _p(bits), _s()), "murcl_linear_fwd")
@@ -192,6 +262,14 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
     dx = out if out is not None else torch.empty((M, K), device=dy.device, dtype=dy.dtype)
     if relu_src is not None:
         _chk(relu_src, "linear_bwd_input.relu_src", dy.dtype)
+    planes = _split_ok(M, K, N, dy, w) if (relu_src is None or relu_bits is not None) else 0
+    if planes:
+        (dp, dpr), (wp, wpr) = _act_planes(dy, planes, remember=True), _weight_planes(w, planes)
+        with _Timed("linear_bwd_input", 2.0 * M * N * K):
+            check(_lib.load().murcl_linear_bwd_input_split(_p(dp), _p(wp), _p(dx), M, N, K, _p(row_scale), _p(row_vec), _p(row_seg),
+                                                           _p(col_sum), float(out_scale), _p(relu_bits), planes, dpr, wpr, _s()),
+                  "murcl_linear_bwd_input_split")
+        return dx
     with _Timed("linear_bwd_input" if M >= 4096 else "head_bwd_input", 2.0 * M * N * K):
         check(_lib.load().murcl_linear_bwd_input(_p(dy), _p(w), _p(dx), M, N, K, _p(relu_src), _p(row_scale), _p(row_vec),
                                                  _p(row_seg), _p(col_sum), float(out_scale), _p(relu_bits), _dt(dy), _backend(),
@@ -219,6 +297,21 @@ def linear_bwd_weight(dy, x, want_bias=True, dw_into=None, db_into=None):
     db = None
     if want_bias:
         db = db_into if acc else torch.empty((N,), device=dy.device, dtype=torch.float32)
+    planes = _split_ok(M, N, K, dy, x) if (K >= 128 and K % 64 == 0) else 0
+    if planes:
+        (dp, pr), (xp, pr2) = _act_planes(dy, planes, remember=True), _act_planes(x, planes)
+        ws = torch.empty((max(int(lib.murcl_linear_bwd_weight_split_workspace(M, N, K)), 1),), device=dy.device, dtype=torch.float32)
+        with _Timed("linear_bwd_weight", 2.0 * M * N * K):
+            check(lib.murcl_linear_bwd_weight_split(_p(dp), _p(xp), _p(dw), M, N, K, planes, pr, _p(ws), int(acc), _s()),
+                  "murcl_linear_bwd_weight_split")
+        if want_bias:
+            part = torch.empty((N,), device=dy.device, dtype=torch.float32)
+            check(lib.murcl_colsum(_p(dy), M, N, _dt(dy), _p(part), _s()), "murcl_colsum")
+            if acc:
+                db.add_(part)
+            else:
+                db = part
+        return dw, db
     nws = int(lib.murcl_linear_bwd_weight_workspace(M, N, K))
     ws = torch.empty((max(nws, 1),), device=dy.device, dtype=torch.float32)
     with _Timed("linear_bwd_weight" if M >= 4096 else "head_bwd_weight", 2.0 * M * N * K):

@@ -112,13 +112,19 @@ def softmax_pool(scores: Tensor, h: Tensor, post_scale: float = 1.0) -> Tuple[Te
     return p @ h, p
 
 
-def abmil_bag(x: Tensor, sd: StateDict, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+def abmil_bag(x: Tensor, sd: StateDict, masks: Optional[Dict[str, Tensor]] = None,
+              relu_masks: Optional[Sequence[Tensor]] = None) -> Tensor:
     """One bag through ABMIL (models/abmil.py:35-45): 3x(Linear+ReLU) encoder (:12-21),
     tanh attention (:23-27), softmax over N then / sqrt(N) (:40-41), A.H (:42), Linear+ReLU
-    decoder (:29-32,44).  ``fc`` (:33) is never applied.  x [N, D_in] -> [1, L]."""
+    decoder (:29-32,44).  ``fc`` (:33) is never applied.  x [N, D_in] -> [1, L].
+    ``relu_masks`` (tests only): three boolean [N, L] tensors that REPLACE the encoder's ReLU decisions
+    (h = z * mask).  A pre-activation within rounding distance of zero may fall on either side of the ReLU in
+    two correct fp32 evaluations; gradients then differ by that unit's whole contribution, which says nothing
+    about arithmetic accuracy.  Adopting the device's decisions makes the gradient comparison exact."""
     h = x
     for j, i in enumerate((0, 3, 6)):
-        h = F.relu(F.linear(h, sd[f"encoder.{i}.weight"], sd[f"encoder.{i}.bias"]))
+        z = F.linear(h, sd[f"encoder.{i}.weight"], sd[f"encoder.{i}.bias"])
+        h = F.relu(z) if relu_masks is None else z * relu_masks[j].to(z.dtype)
         if masks is not None and f"enc{j}" in masks:      # train-mode nn.Dropout (:15,18): multiplicative keep/(1-p)
             h = h * masks[f"enc{j}"]
     u = torch.tanh(F.linear(h, sd["attention.0.weight"], sd["attention.0.bias"]))

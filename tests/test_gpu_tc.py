@@ -4,6 +4,7 @@ final rounding of the output to its storage type."""
 import math
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -118,3 +119,49 @@ def test_tc_matches_simt_on_pretrain_shapes():
     os.environ["MURCL_GEMM"] = "simt"
     y_simt = ops.linear_fwd(xd, wd, bd, ops.ACT_RELU, torch.float32)
     assert_close(y_tc, y_simt, 2e-6, "tc vs simt")
+
+
+# ------------------------------------------------------------------------------------------------
+# exact-fp32 dense layers on the bf16 tensor cores (split precision)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("planes,tol", [(2, 8e-6), (3, 1e-6)])
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 512), (3000, 128, 512), (1111, 512, 128), (2048, 256, 64)])
+def test_split_precision_gemms_match_fp64(monkeypatch, planes, tol, M, N, K):
+    """murcl_linear_{fwd,bwd_input,bwd_weight}_split against fp64 on the SAME fp32 operands.  Tolerance is relative to the
+    largest output magnitude: two planes (three products) keep everything above 3 * 2^-18 |x||y|, three planes 2^-24."""
+    from murcl_b200 import ops
+    monkeypatch.setenv("MURCL_FP32_GEMM", f"split{planes}")
+    g = synth.gen(M + N + K + planes)
+    x = torch.clamp_min(0.5 * torch.randn(M, K, generator=g) + 0.2, 0)          # post-ReLU-like activations
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = 0.1 * torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    xd, wd, bd, dyd = (t.to(DEV) for t in (x, w, b, dy))
+    assert ops._split_ok(M, N, K, xd, wd) == planes
+    # forward + ReLU + bit mask
+    y, bits = ops.linear_fwd(xd, wd, bd, ops.ACT_RELU, relu_bits=(N % 64 == 0))
+    want = torch.relu(x.double() @ w.double().t() + b.double())
+    assert_close(y.cpu(), want.float(), tol, "forward")
+    # input gradient through the ReLU mask of a layer of width K (mask from a forward of that width)
+    if K % 64 == 0 and K >= 128:
+        pre = torch.randn(M, K, generator=g)
+        # the layout murcl_linear_fwd writes: [K / 64][M] 64-bit words, bit (c % 64) of word [c // 64][m] = (pre[m, c] > 0)
+        on = (pre > 0).numpy().astype(np.uint64).reshape(M, K // 64, 64)
+        words = (on << np.arange(64, dtype=np.uint64)).sum(-1, dtype=np.uint64).T.copy()
+        kb = torch.from_numpy(words.view(np.int64)).to(DEV)
+        dx = ops.linear_bwd_input(dyd, wd, relu_bits=kb)
+        want_dx = (dy.double() @ w.double()) * (pre > 0)
+        assert_close(dx.cpu(), want_dx.float(), tol, "input gradient (masked)")
+    dx = ops.linear_bwd_input(dyd, wd) if K >= 128 else None
+    if dx is not None:
+        assert_close(dx.cpu(), (dy.double() @ w.double()).float(), tol, "input gradient")
+    # weight gradient (+ bias), plain and accumulated into an existing buffer
+    if K >= 128:
+        dw, db = ops.linear_bwd_weight(dyd, xd, True)
+        want_dw = dy.double().t() @ x.double()
+        assert_close(dw.cpu(), want_dw.float(), tol, "weight gradient")
+        assert_close(db.cpu(), dy.double().sum(0).float(), 1e-5, "bias gradient")
+        acc_w, acc_b = torch.ones(N, K, device=DEV), torch.ones(N, device=DEV)
+        ops.linear_bwd_weight(dyd, xd, True, dw_into=acc_w, db_into=acc_b)
+        assert_close(acc_w.cpu(), (want_dw + 1).float(), tol, "accumulated weight gradient")
+        assert_close(acc_b.cpu(), (dy.double().sum(0) + 1).float(), 1e-5, "accumulated bias gradient")
