@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--e2e-epochs", type=int, default=10, help="epochs of the dataset shard in the end-to-end region (first one cold)")
     ap.add_argument("--fp32-steps", type=int, default=3, help="timed steps of the secondary fp32-mode measurement (0 = skip)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the fp32-mode / strong-scaling / cfg5 measurements")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="exchange the head gradients under the aggregators' backward (measured slower: NCCL's CTAs take SMs from "
+                         "the persistent one-CTA-per-SM GEMMs, whose last CTAs then run as a second wave)")
     ap.add_argument("--cpu-bags", type=int, default=8, help="slides in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,13 +218,16 @@ class Job:
         loss, _ = pretrain.pretrain_step(store, self.model, self.fc, self.crit, T=self.a.T, feat_size=self.a.feat_size,
                                          alpha=0.9, stage=3, ppo=self.ppo, memories=self.memories,
                                          precision=self.precision, slot_bag=slot_bag,
-                                         after_head_backward=exchange_heads if self.world > 1 else None)
+                                         after_head_backward=exchange_heads if (self.world > 1 and self.a.overlap_allreduce) else None)
         if self.world > 1:
-            self.arena.allreduce(lo=0, hi=lo)
-            self.arena.allreduce(lo=hi)
-            for w in pending:
-                if w is not None:
-                    w.wait()
+            if self.a.overlap_allreduce:
+                self.arena.allreduce(lo=0, hi=lo)
+                self.arena.allreduce(lo=hi)
+                for w in pending:
+                    if w is not None:
+                        w.wait()
+            else:
+                self.arena.allreduce()      # ONE all-reduce of the flat gradient buffer (24 MB), after the backward
         self.opt.step()
         self.arena.refresh()
         return loss

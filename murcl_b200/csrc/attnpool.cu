@@ -30,6 +30,15 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+// Timeline tracing / phase skipping (MURCL_DEBUG_EPI, MURCL_DEBUG_ATTNPOOL*) is compiled in only with -DMURCL_TRACE: the
+// production kernels carry no instrumentation.
+#ifdef MURCL_TRACE
+#define MURCL_TRACE_ON 1
+#else
+#define MURCL_TRACE_ON 0
+#endif
+
+
 namespace murcl {
 namespace ap {
 
@@ -80,7 +89,7 @@ struct Params {
 };
 
 #define AP_STAMP(slot)                                                              \
-  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 128) {                 \
+  if (MURCL_TRACE_ON && p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 128) {                 \
     unsigned long long ts_;                                                         \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));                         \
     p.trace[(it >> 1) * 8 + (slot)] = ts_;                                          \
@@ -278,7 +287,7 @@ attnpool_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             part = fmaf(w4.z, g23.x, part);
             part = fmaf(w4.w, g23.y, part);
           }
-          if (p.uv != nullptr && !(p.skip & 2)) {
+          if (p.uv != nullptr && !(MURCL_TRACE_ON && p.skip & 2)) {
             // stage the 32 x 32 unit swizzled like the TMA box and hand it to the bulk-store engine (a direct store
             // would touch 32 different 128-byte lines per instruction); rows >= n_rows are clipped by the tensor map
             if (k == 0) {
@@ -289,7 +298,7 @@ attnpool_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             st_shared_v4(unit + my_row_off + (((uint32_t)(2 * k + 1) ^ swz) << 4), up[4], up[5], up[6], up[7]);
           }
         }
-        if (p.uv != nullptr && !(p.skip & 2)) {
+        if (p.uv != nullptr && !(MURCL_TRACE_ON && p.skip & 2)) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -325,7 +334,7 @@ attnpool_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       team_sync(team);
       AP_STAMP(3)
       // ---- per bag segment of the tile: softmax statistics + exp-weighted column sums of the tile's rows (L2 hits) ----
-      for (int b = b_lo; b <= b_hi && !(p.skip & 4); ++b) {
+      for (int b = b_lo; b <= b_hi && !(MURCL_TRACE_ON && p.skip & 4); ++b) {
         const int64_t o0 = o_next, o1 = __ldg(p.offsets + b + 1);
         o_next = o1;
         const int r_begin = (int)(o0 > row0 ? o0 - row0 : 0);
@@ -343,7 +352,7 @@ attnpool_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           float acc[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-          if (act0 && !(p.skip & 1)) {
+          if (act0 && !(MURCL_TRACE_ON && p.skip & 1)) {
             const __nv_bfloat16* base = p.h + row0 * L + 8 * lane;
             int rr = r_begin + wt;
             for (; rr + 24 < r_end; rr += 32) {                            // four rows in flight

@@ -25,6 +25,15 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+// Timeline tracing / phase skipping (MURCL_DEBUG_EPI, MURCL_DEBUG_ATTNPOOL*) is compiled in only with -DMURCL_TRACE: the
+// production kernels carry no instrumentation.
+#ifdef MURCL_TRACE
+#define MURCL_TRACE_ON 1
+#else
+#define MURCL_TRACE_ON 0
+#endif
+
+
 namespace murcl {
 
 // defined in gemm_simt.cu
@@ -99,7 +108,7 @@ struct Cfg {
 };
 
 #define MURCL_STAMP(slot)                                                                         \
-  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && c0 == 0) {                              \
+  if (MURCL_TRACE_ON && p.trace && blockIdx.x == 0 && threadIdx.x == 0 && c0 == 0) {                              \
     unsigned long long ts_;                                                                     \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));                                     \
     p.trace[(int64_t)24 * 2048 + ((t - tile_first) / tile_step) * 8 + (slot)] = ts_;            \
@@ -288,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         k_range(sp, k0, nkb);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tcgen05_fence_after();
-        if (p.trace && blockIdx.x == 0) {
+        if (MURCL_TRACE_ON && p.trace && blockIdx.x == 0) {
           unsigned long long ts;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
           p.trace[((t - tile_first) / tile_step) * 24 + 0] = ts;
@@ -315,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (CG == 1) tcgen05_commit(tfull_bar(as));        // accumulator complete
         else tcgen05_commit_2sm(tfull_bar(as));
-        if (p.trace && blockIdx.x == 0) {
+        if (MURCL_TRACE_ON && p.trace && blockIdx.x == 0) {
           unsigned long long ts;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
           p.trace[((t - tile_first) / tile_step) * 24 + 1] = ts;      // all MMAs of the tile ISSUED
@@ -412,7 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+      if (MURCL_TRACE_ON && p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
         p.trace[((t - tile_first) / tile_step) * 24 + 2] = ts;        // accumulator complete, epilogue starts
@@ -596,7 +605,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      if (p.trace && blockIdx.x < 2 && lane == 0 && ew < 8) {
+      if (MURCL_TRACE_ON && p.trace && blockIdx.x < 2 && lane == 0 && ew < 8) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
         p.trace[((t - tile_first) / tile_step) * 24 + 4 + blockIdx.x * 8 + ew] = ts;   // per-warp end, CTAs 0 and 1

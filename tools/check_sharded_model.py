@@ -40,7 +40,10 @@ def main():
     cot = torch.randn(len(sizes), 512, generator=synth.gen(73)).to(dev)
     ok = True
     for kind in ("clam", "abmil"):
-        for precision, tol, gtol in (("bf16", 2e-2, 6e-2), ("fp32", 1e-5, 2e-4)):
+        # fp32 gradients: the shards see different GEMM tilings than the whole bag, so a handful of ReLU decisions at
+        # pre-activations that are zero to rounding can differ (tests/test_gpu_parity.py::test_abmil_full_size measures
+        # the effect: up to a few 1e-4 of a layer's weight gradient per flipped unit)
+        for precision, tol, gtol in (("bf16", 2e-2, 6e-2), ("fp32", 1e-5, 2e-3)):
             m = build(kind, dim, precision, dev).shard_bags(world > 1)
             local = []
             for f in feats:
