@@ -38,10 +38,62 @@ __device__ __forceinline__ KeyIdx block_best(KeyIdx k, KeyIdx* red) {
   return red[0];
 }
 
-// One CTA per (bag, end).  k rounds of block arg-best; each round only considers elements that
+// Single pass (k <= 8): one CTA per (bag, end).  Every thread keeps the k best of its strided share of the bag in a
+// sorted register list (insertion by compile-time shifts); the bag's k best are among those 256 x k candidates and are
+// drawn by k rounds of block arg-best over the list heads (the winner's owner pops its head).  p is read ONCE per end
+// (the multi-pass kernel below reads it k times); same (value desc, index asc) order, so the same indices, ties included.
+template <int KMAX>
+__global__ void __launch_bounds__(256) seg_topk_ends_kernel(const float* __restrict__ p, const int64_t* __restrict__ offsets, int k,
+                                                            int32_t* __restrict__ top_idx, int32_t* __restrict__ bot_idx) {
+  __shared__ KeyIdx red[32];
+  const int b = blockIdx.x, end = blockIdx.y;
+  const int64_t lo = offsets[b], hi = offsets[b + 1];
+  const float sign = end == 0 ? 1.f : -1.f;
+  int32_t* out = (end == 0 ? top_idx : bot_idx) + (int64_t)b * k;
+  KeyIdx lst[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) { lst[j].v = 0.f; lst[j].i = -1; }
+  auto consider = [&](float val, int idx) {
+    KeyIdx c;
+    c.v = sign * val;
+    c.i = idx;
+    if (lst[KMAX - 1].i < 0 || before(c, lst[KMAX - 1])) {
+      // insert c, keeping the list sorted: every slot takes the better of (its left neighbour, c) once c belongs left of it
+#pragma unroll
+      for (int j = KMAX - 1; j > 0; --j) {
+        const bool left = lst[j - 1].i < 0 || before(c, lst[j - 1]);      // c goes somewhere left of slot j
+        const bool here = lst[j].i < 0 || before(c, lst[j]);              // c goes at or left of slot j
+        if (left) lst[j] = lst[j - 1];
+        else if (here) lst[j] = c;
+      }
+      if (lst[0].i < 0 || before(c, lst[0])) lst[0] = c;
+    }
+  };
+  constexpr int UNR = 8;                                   // loads of a thread in flight (the insertions are branchy and serial)
+  int64_t n = lo + threadIdx.x;
+  for (; n + (int64_t)(UNR - 1) * blockDim.x < hi; n += (int64_t)UNR * blockDim.x) {
+    float v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) v[u] = __ldg(p + n + (int64_t)u * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) consider(v[u], (int)(n + (int64_t)u * blockDim.x - lo));
+  }
+  for (; n < hi; n += blockDim.x) consider(__ldg(p + n), (int)(n - lo));
+  for (int r = 0; r < k; ++r) {
+    const KeyIdx best = block_best(lst[0], red);
+    if (threadIdx.x == 0) out[r] = best.i >= 0 ? (int32_t)(lo + best.i) : -1;
+    if (best.i >= 0 && lst[0].i == best.i) {                               // the owner pops its head
+#pragma unroll
+      for (int j = 0; j < KMAX - 1; ++j) lst[j] = lst[j + 1];
+      lst[KMAX - 1].i = -1;
+    }
+  }
+}
+
+// Multi-pass fallback (k > 8): one CTA per (bag, end).  k rounds of block arg-best; each round only considers elements that
 // come strictly after the previous winner in the (value desc, index asc) order, so no marks are
 // needed and the result is deterministic.  end 0: largest p, end 1: smallest p (sign flipped).
-__global__ void __launch_bounds__(256) seg_topk_ends_kernel(const float* __restrict__ p,
+__global__ void __launch_bounds__(256) seg_topk_ends_multipass_kernel(const float* __restrict__ p,
                                                             const int64_t* __restrict__ offsets, int k,
                                                             int32_t* __restrict__ top_idx, int32_t* __restrict__ bot_idx) {
   __shared__ KeyIdx red[32];
@@ -182,8 +234,12 @@ int murcl_seg_topk_ends(const float* p, const int64_t* offsets, int B, int k, in
   MURCL_REQUIRE(p && offsets && top_idx && bot_idx, "seg_topk_ends: null pointer");
   MURCL_REQUIRE(B >= 0 && k > 0 && k <= 1024, "seg_topk_ends: bad B=%d k=%d", B, k);
   if (B == 0) return MURCL_OK;
-  seg_topk_ends_kernel<<<dim3(B, 2), 256, 0, as_stream(stream)>>>(p, offsets, k, top_idx, bot_idx);
-  return check_launch("seg_topk_ends_kernel");
+  if (k <= 8) {
+    seg_topk_ends_kernel<8><<<dim3(B, 2), 256, 0, as_stream(stream)>>>(p, offsets, k, top_idx, bot_idx);
+    return check_launch("seg_topk_ends_kernel");
+  }
+  seg_topk_ends_multipass_kernel<<<dim3(B, 2), 256, 0, as_stream(stream)>>>(p, offsets, k, top_idx, bot_idx);
+  return check_launch("seg_topk_ends_multipass_kernel");
 }
 
 int murcl_seg_argmax(const float* c, const int64_t* offsets, int B, int C, int32_t* idx, void* stream) {

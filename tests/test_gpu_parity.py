@@ -972,3 +972,32 @@ def test_ntxent_gradient_slab(B, d, b0, nb):
     mask = torch.ones(2 * B, dtype=torch.bool)
     mask[rows] = False
     assert float(dz.cpu()[mask].abs().max() if mask.any() else 0.0) == 0.0, "rows outside the slab must stay zero"
+
+
+@pytest.mark.parametrize("k", [1, 8, 12])
+def test_seg_topk_ends_matches_torch_topk(k):
+    """murcl_seg_topk_ends (single pass for k <= 8, multi-pass beyond) against torch.topk per bag (clam.py:107-110), on
+    ragged bags incl. one with exactly k rows, a 100k-row bag and heavy ties (identical zero-pad rows give identical
+    weights; the kernel breaks ties by lowest index, and the VALUES at the chosen indices must equal topk's)."""
+    from murcl_b200 import ops
+    g = synth.gen(400 + k)
+    sizes = [k, 37, 5000, 100000, 1024, 300]
+    parts = [torch.softmax(3 * torch.randn(n, generator=g), 0) for n in sizes]
+    parts[4][200:] = parts[4][200]                      # 824 tied weights (zero-pad rows)
+    parts[5][:] = 1.0 / 300                             # everything tied
+    p = torch.cat(parts).to(DEV)
+    off = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64, device=DEV)
+    top, bot = ops.seg_topk_ends(p, off, len(sizes), k)
+    lo = 0
+    for b, n in enumerate(sizes):
+        pb = parts[b]
+        tv, ti = torch.topk(pb, k)
+        bv, bi = torch.topk(-pb, k)
+        got_t, got_b = top[b].cpu().long() - lo, bot[b].cpu().long() - lo
+        assert got_t.min() >= 0 and got_t.max() < n and len(set(got_t.tolist())) == k
+        assert got_b.min() >= 0 and got_b.max() < n and len(set(got_b.tolist())) == k
+        assert torch.equal(pb[got_t], tv), f"bag {b}: top-{k} values"
+        assert torch.equal(-pb[got_b], bv), f"bag {b}: bottom-{k} values"
+        if b < 4:                                       # no ties: the indices themselves are determined
+            assert torch.equal(got_t, ti) and torch.equal(got_b, bi)
+        lo += n
