@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("MURCL_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--bags", type=int, default=128, help="slides per GPU per step")
     ap.add_argument("--T", type=int, default=6)
+    ap.add_argument("--stage", type=int, default=3, choices=[1, 3],
+                    help="train_stage of the step: 3 (default, the headline: the PPO actor chooses the windows) or 1 (random windows)")
     ap.add_argument("--feat-size", type=int, default=1024)
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--clusters", type=int, default=10)
@@ -216,7 +218,7 @@ class Job:
             pending.append(self.arena.allreduce(lo=lo, hi=hi, async_op=True))
 
         loss, _ = pretrain.pretrain_step(store, self.model, self.fc, self.crit, T=self.a.T, feat_size=self.a.feat_size,
-                                         alpha=0.9, stage=3, ppo=self.ppo, memories=self.memories,
+                                         alpha=0.9, stage=self.a.stage, ppo=self.ppo, memories=self.memories,
                                          precision=self.precision, slot_bag=slot_bag,
                                          after_head_backward=exchange_heads if (self.world > 1 and self.a.overlap_allreduce) else None)
         if self.world > 1:

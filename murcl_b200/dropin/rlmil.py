@@ -40,10 +40,15 @@ class ActorCritic(nn.Module):
     def __init__(self, feature_dim, state_dim, hidden_state_dim=1024, policy_conv=False, action_std=0.1, action_size=2):
         super(ActorCritic, self).__init__()
         if policy_conv:
-            raise NotImplementedError("policy_conv=True (conv state encoder) is unused by the reference's run scripts")
-        self.state_encoder = nn.Sequential(
-            nn.Linear(state_dim, 2048), nn.ReLU(),
-            nn.Linear(2048, hidden_state_dim), nn.ReLU())
+            # rlmil.py:30-37: 1x1 convolution over the feature map of the state, then one dense layer.  A 1x1 convolution is
+            # a dense layer over the channels applied at every position, so it runs on the same GEMM kernels (_encode)
+            self.state_encoder = nn.Sequential(
+                nn.Conv2d(feature_dim, 32, kernel_size=1, stride=1, padding=0, bias=False), nn.ReLU(), nn.Flatten(),
+                nn.Linear(int(state_dim * 32 / feature_dim), hidden_state_dim), nn.ReLU())
+        else:
+            self.state_encoder = nn.Sequential(
+                nn.Linear(state_dim, 2048), nn.ReLU(),
+                nn.Linear(2048, hidden_state_dim), nn.ReLU())
         self.gru = nn.GRU(hidden_state_dim, hidden_state_dim, batch_first=False)
         self.actor = nn.Sequential(nn.Linear(hidden_state_dim, action_size), nn.Sigmoid())
         self.critic = nn.Sequential(nn.Linear(hidden_state_dim, 1))
@@ -59,8 +64,19 @@ class ActorCritic(nn.Module):
 
     def _encode(self, state):
         dt = _dtype(self)
+        if self.policy_conv:
+            # state [N, F, r, r]: channels-last rows -> dense F -> 32 (+ReLU) -> back to the NCHW flattening order (rlmil.py:31-36)
+            n, f, h, w = state.shape
+            rows = state.permute(0, 2, 3, 1).reshape(n * h * w, f).contiguous()
+            c = ops.linear(rows, self.state_encoder[0].weight.reshape(32, f), None, ops.ACT_RELU, dt)
+            flat = c.reshape(n, h * w, 32).permute(0, 2, 1).reshape(n, 32 * h * w).contiguous()
+            return ops.linear(flat, self.state_encoder[3].weight, self.state_encoder[3].bias, ops.ACT_RELU, dt)
         s = ops.linear(state, self.state_encoder[0].weight, self.state_encoder[0].bias, ops.ACT_RELU, dt)
         return ops.linear(s, self.state_encoder[2].weight, self.state_encoder[2].bias, ops.ACT_RELU, dt)
+
+    def _state_rows(self, state_ini):
+        """[N, ...] states as the encoder wants them: flattened vectors, or the [N, F, r, r] feature map (rlmil.py:71-74)."""
+        return state_ini.float().contiguous() if self.policy_conv else state_ini.flatten(1).float().contiguous()
 
     def act(self, state_ini, memory, restart_batch=False, training=False, eps=None):
         """rlmil.py:66-97.  ``eps`` optionally supplies the standard-normal draw (parity tests); by default it
@@ -69,8 +85,7 @@ class ActorCritic(nn.Module):
             if restart_batch:
                 del memory.hidden[:]
                 memory.hidden.append(torch.zeros(1, state_ini.size(0), self.hidden_state_dim, device=state_ini.device))
-            state = state_ini.flatten(1).float().contiguous()
-            enc = self._encode(state)
+            enc = self._encode(self._state_rows(state_ini))
             h = ops.gru_step(enc, memory.hidden[-1][0].contiguous(), *_gru_params(self.gru), dtype=_dtype(self))
             memory.hidden.append(h.unsqueeze(0))
             logits = ops.linear(h, self.actor[0].weight, self.actor[0].bias)
@@ -95,8 +110,7 @@ class ActorCritic(nn.Module):
                 for m in memories:
                     del m.hidden[:]
                     m.hidden.append(torch.zeros(1, b, self.hidden_state_dim, device=states[0].device))
-            state = torch.cat([s.flatten(1).float() for s in states], 0).contiguous()
-            enc = self._encode(state)
+            enc = self._encode(torch.cat([self._state_rows(s) for s in states], 0).contiguous())
             h_prev = torch.cat([m.hidden[-1][0] for m in memories], 0).contiguous()
             h = ops.gru_step(enc, h_prev, *_gru_params(self.gru), dtype=_dtype(self))
             logits = ops.linear(h, self.actor[0].weight, self.actor[0].bias)
@@ -121,7 +135,10 @@ class ActorCritic(nn.Module):
     def evaluate(self, state, action):
         """rlmil.py:99-127: log-prob, value and entropy of stored (state, action) sequences ``[T, B, ...]``."""
         seq_l, batch_size = state.size(0), state.size(1)
-        flat = state.flatten(2).reshape(seq_l * batch_size, -1).float().contiguous()
+        if self.policy_conv:
+            flat = state.reshape((seq_l * batch_size,) + tuple(state.shape[2:])).float().contiguous()     # rlmil.py:107
+        else:
+            flat = state.flatten(2).reshape(seq_l * batch_size, -1).float().contiguous()
         enc = self._encode(flat).reshape(seq_l, batch_size, -1)
         h = torch.zeros(batch_size, self.hidden_state_dim, device=state.device)
         outs = []

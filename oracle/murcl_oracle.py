@@ -287,9 +287,7 @@ def actor_act(state: Tensor, h_prev: Optional[Tensor], sd: StateDict, action_std
     sample mean + std*eps with scale_tril=diag(action_std) (:84-86; ``action_var`` holds the
     std, :56), clip to [0,1] through two ReLUs (:88-89), log-prob of the clipped action (:90).
     ``eps`` is the standard-normal draw.  Returns (action, logprob, h_new, mean)."""
-    s = state.flatten(1)
-    s = F.relu(F.linear(s, sd["state_encoder.0.weight"], sd["state_encoder.0.bias"]))
-    s = F.relu(F.linear(s, sd["state_encoder.2.weight"], sd["state_encoder.2.bias"]))
+    s = actor_encode_state(state, sd)
     if h_prev is None:
         h_prev = s.new_zeros(s.shape[0], sd["gru.weight_hh_l0"].shape[1])
     h = gru_cell(s, h_prev, sd["gru.weight_ih_l0"], sd["gru.weight_hh_l0"], sd["gru.bias_ih_l0"], sd["gru.bias_hh_l0"])
@@ -301,15 +299,25 @@ def actor_act(state: Tensor, h_prev: Optional[Tensor], sd: StateDict, action_std
     return action, logprob, h, mean
 
 
+def actor_encode_state(state: Tensor, sd: StateDict) -> Tensor:
+    """The state encoder of ActorCritic (models/rlmil.py:29-45).  policy_conv=False: flatten -> Linear(2048) -> ReLU ->
+    Linear(hidden) -> ReLU (:40-45, :71-72).  policy_conv=True (recognised by the ``state_encoder.3`` keys): 1x1 convolution
+    without bias over the [N, F, r, r] state -> ReLU -> NCHW flatten -> Linear(hidden) -> ReLU (:30-37, :73-74)."""
+    if "state_encoder.3.weight" in sd:
+        w = sd["state_encoder.0.weight"]
+        c = F.relu(torch.einsum("nfhw,cf->nchw", state, w.reshape(w.shape[0], w.shape[1])))
+        return F.relu(F.linear(c.flatten(1), sd["state_encoder.3.weight"], sd["state_encoder.3.bias"]))
+    s = F.relu(F.linear(state.flatten(1), sd["state_encoder.0.weight"], sd["state_encoder.0.bias"]))
+    return F.relu(F.linear(s, sd["state_encoder.2.weight"], sd["state_encoder.2.bias"]))
+
+
 def actor_evaluate(states: Tensor, actions: Tensor, sd: StateDict, action_std: float):
     """ActorCritic.evaluate with policy_conv=False (models/rlmil.py:99-127): the stored states ``[T, B, ...]`` go
     through the state MLP (:109), one ``nn.GRU`` pass over the T steps from a ZERO hidden state (:112), the sigmoid
     actor head (:115) and the critic (:124); the action log-probability and the entropy are those of
     ``MultivariateNormal(mean, scale_tril=diag(action_std))`` (:117-122).  Returns (logprob, value, entropy), each [T, B]."""
     T, B = states.shape[0], states.shape[1]
-    s = states.flatten(2).reshape(T * B, -1)
-    s = F.relu(F.linear(s, sd["state_encoder.0.weight"], sd["state_encoder.0.bias"]))
-    s = F.relu(F.linear(s, sd["state_encoder.2.weight"], sd["state_encoder.2.bias"])).reshape(T, B, -1)
+    s = actor_encode_state(states.reshape((T * B,) + tuple(states.shape[2:])), sd).reshape(T, B, -1)
     h = s.new_zeros(B, sd["gru.weight_hh_l0"].shape[1])
     feats = []
     for t in range(T):

@@ -265,6 +265,47 @@ def golden_actor():
     save("actor", **arrays)
 
 
+def golden_actor_conv():
+    """ActorCritic(policy_conv=True) (models/rlmil.py:30-37,71-74,104-107): act over two steps and evaluate with its
+    gradients, states are [B, feature_dim, r, r] feature maps."""
+    import torch.distributions.multivariate_normal as mvn
+    fdim, r, hid, k, b, std = 8, 2, 24, 5, 6, 0.5
+    sdim = fdim * r * r
+    ppo = rlmil.PPO(fdim, sdim, hid, True, action_std=std, action_size=k)
+    g = synth.gen(121)
+    sd = {n: 0.3 * torch.randn(p.shape, generator=g) for n, p in ppo.policy.state_dict().items()}
+    ppo.policy.load_state_dict(sd)
+    ppo.policy_old.load_state_dict(sd)
+    eps_log = []
+    orig = mvn._standard_normal
+
+    def recording(shape, dtype, device):
+        e = orig(shape, dtype, device)
+        eps_log.append(e.clone())
+        return e
+
+    mvn._standard_normal = recording
+    mem = rlmil.Memory()
+    arrays = dict(dims=np.asarray([fdim, r, hid, k, b]), std=std)
+    arrays.update({f"sd.{n}": npy(v) for n, v in sd.items()})
+    torch.manual_seed(122)
+    for t in range(2):
+        state = torch.randn(b, fdim, r, r, generator=g)
+        action = ppo.select_action(state, mem, restart_batch=(t == 0))
+        arrays[f"state{t}"], arrays[f"action{t}"] = npy(state), npy(action)
+        arrays[f"eps{t}"], arrays[f"logprob{t}"] = npy(eps_log[-1]), npy(mem.logprobs[-1])
+    mvn._standard_normal = orig
+    lp, val, ent = ppo.policy.evaluate(torch.stack(mem.states, 0), torch.stack(mem.actions, 0))
+    arrays["eval_logprob"], arrays["eval_value"] = npy(lp), npy(val)
+    cot_l, cot_v = torch.randn(lp.shape, generator=g), torch.randn(val.shape, generator=g)
+    arrays["cot_l"], arrays["cot_v"] = npy(cot_l), npy(cot_v)
+    ppo.policy.zero_grad()
+    ((lp * cot_l).sum() + (val * cot_v).sum()).backward()
+    for n, p in ppo.policy.named_parameters():
+        arrays[f"grad.{n}"] = npy(p.grad)
+    save("actor_conv", **arrays)
+
+
 def golden_ppo_update():
     """PPO.evaluate / PPO.update (models/rlmil.py:99-127,152-184) on a 4-step rollout produced by the reference's own
     ``select_action`` with recorded Gaussian draws and fixed rewards: the evaluate outputs, the first epoch's
@@ -441,7 +482,7 @@ if __name__ == "__main__":
     assert REF.exists(), f"reference not found at {REF}"
     print("writing fixtures to", HERE)
     makers = [golden_selection, golden_get_feats, golden_mixup, golden_abmil, golden_clam, golden_dsmil, golden_ntxent,
-              golden_full_layer, golden_actor, golden_ppo_update, golden_pretrain_step, golden_stage3_step]
+              golden_full_layer, golden_actor, golden_actor_conv, golden_ppo_update, golden_pretrain_step, golden_stage3_step]
     only = set(sys.argv[1:])            # e.g. `make_golden.py golden_ppo_update` regenerates one fixture
     for fn in makers:
         if not only or fn.__name__ in only:

@@ -1001,3 +1001,30 @@ def test_seg_topk_ends_matches_torch_topk(k):
         if b < 4:                                       # no ties: the indices themselves are determined
             assert torch.equal(got_t, ti) and torch.equal(got_b, bi)
         lo += n
+
+
+def test_actor_conv_golden(golden):
+    """ActorCritic(policy_conv=True) (rlmil.py:30-37): the 1x1-convolution state encoder on the GEMM kernels, against the
+    reference's own act / evaluate run incl. all parameter gradients."""
+    from murcl_b200.dropin import rlmil
+    g = golden("actor_conv")
+    fdim, r, hid, k, b = g["dims"].tolist()
+    ppo = rlmil.PPO(fdim, fdim * r * r, hid, True, action_std=float(g["std"]), action_size=k)
+    sd = {n[3:]: torch.from_numpy(v) for n, v in g.items() if n.startswith("sd.")}
+    ppo.policy.load_state_dict(sd, strict=True)
+    ppo.policy_old.load_state_dict(sd, strict=True)
+    mem = rlmil.Memory()
+    for t in range(2):
+        state = torch.from_numpy(g[f"state{t}"]).to(DEV)
+        action = ppo.policy_old.act(state, mem, restart_batch=(t == 0), training=True, eps=torch.from_numpy(g[f"eps{t}"]).to(DEV))
+        assert_close(action, g[f"action{t}"], FP32_OUT, f"action{t}")
+        assert_close(mem.logprobs[-1], g[f"logprob{t}"], FP32_OUT, f"logprob{t}")
+    lp, val, _ = ppo.policy.evaluate(torch.stack(mem.states, 0), torch.stack(mem.actions, 0))
+    assert_close(lp, g["eval_logprob"], FP32_OUT, "evaluate.logprob")
+    assert_close(val, g["eval_value"], FP32_OUT, "evaluate.value")
+    ppo.policy.zero_grad()
+    ((lp * torch.from_numpy(g["cot_l"]).to(DEV)).sum() + (val * torch.from_numpy(g["cot_v"]).to(DEV)).sum()).backward()
+    gr = _grads(ppo.policy)
+    for key, v in g.items():
+        if key.startswith("grad."):
+            assert_close(gr[key[5:]].numpy(), v, FP32_GRAD, key, floor=1e-6)

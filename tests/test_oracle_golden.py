@@ -301,3 +301,23 @@ def test_stage3_step(golden):
     for key, val in g.items():
         if key.startswith("ppo_delta."):
             assert_close(sample((params[key[10:]].detach() - sd_a[key[10:]]).numpy()), val, 2e-2, key, floor=1e-5)
+
+
+def test_actor_conv(golden):
+    """ActorCritic(policy_conv=True): the 1x1-convolution state encoder (models/rlmil.py:30-37)."""
+    g = golden("actor_conv")
+    sd = leaf_state({n[3:]: torch.from_numpy(v) for n, v in g.items() if n.startswith("sd.")})
+    std = float(g["std"])
+    h, states, actions = None, [], []
+    for t in range(2):
+        st = torch.from_numpy(g[f"state{t}"])
+        a, lp, h, _ = O.actor_act(st, h, sd, std, torch.from_numpy(g[f"eps{t}"]))
+        assert_close(a, g[f"action{t}"], TOL, f"action{t}")
+        assert_close(lp, g[f"logprob{t}"], TOL, f"logprob{t}")
+        states.append(st)
+        actions.append(a.detach())
+    lp, val, _ = O.actor_evaluate(torch.stack(states, 0), torch.stack(actions, 0), sd, std)
+    assert_close(lp, g["eval_logprob"], TOL, "evaluate.logprob")
+    assert_close(val, g["eval_value"], TOL, "evaluate.value")
+    ((lp * torch.from_numpy(g["cot_l"])).sum() + (val * torch.from_numpy(g["cot_v"])).sum()).backward()
+    _check_grads(g, sd)
