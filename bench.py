@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fp32-store", action="store_true", help="keep the slide store in fp32 even in bf16 mode")
+    ap.add_argument("--rng", default="batched", choices=["batched", "reference"],
+                    help="random draws of the step: issued once up front (default) or per patch-step in the reference's call order")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -172,7 +174,13 @@ class Job:
         # clears them, one cast refreshes the bf16 weights, one all-reduce exchanges them, Adam updates one tensor
         from murcl_b200.arena import ParamArena
         self.arena = ParamArena(self.params, shadow_dtype=torch.bfloat16 if self.precision == "bf16" else None)
-        self.opt = torch.optim.Adam(self.arena.optimizer_params(), lr=1e-4, weight_decay=1e-5, capturable=True)
+        # Adam as upstream (train_MuRCL.py:154-171), as ONE fused launch over the arena that also refreshes the bf16 shadow
+        # weights (murcl_adam_step); MURCL_TORCH_ADAM=1 runs torch's multi-tensor Adam + the separate cast instead
+        if os.environ.get("MURCL_TORCH_ADAM", "0") == "1":
+            self.opt = torch.optim.Adam(self.arena.optimizer_params(), lr=1e-4, weight_decay=1e-5, capturable=True)
+        else:
+            from murcl_b200.optim import ArenaAdam
+            self.opt = ArenaAdam(self.arena, lr=1e-4, weight_decay=1e-5)
         self.head_range = self.arena.range_of(list(self.fc.parameters()))      # Full_layer: 80 % of the gradient bytes
         self.mdist = mdist
         self.graphs = {}
@@ -219,7 +227,7 @@ class Job:
 
         loss, _ = pretrain.pretrain_step(store, self.model, self.fc, self.crit, T=self.a.T, feat_size=self.a.feat_size,
                                          alpha=0.9, stage=self.a.stage, ppo=self.ppo, memories=self.memories,
-                                         precision=self.precision, slot_bag=slot_bag,
+                                         precision=self.precision, slot_bag=slot_bag, rng=self.a.rng,
                                          after_head_backward=exchange_heads if (self.world > 1 and self.a.overlap_allreduce) else None)
         if self.world > 1:
             if self.a.overlap_allreduce:
@@ -231,7 +239,8 @@ class Job:
             else:
                 self.arena.allreduce()      # ONE all-reduce of the flat gradient buffer (24 MB), after the backward
         self.opt.step()
-        self.arena.refresh()
+        if isinstance(self.opt, torch.optim.Optimizer):
+            self.arena.refresh()
         return loss
 
 

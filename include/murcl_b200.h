@@ -298,6 +298,20 @@ int murcl_dropout(void* x, int64_t n, float p, const int64_t* seed_dev, int dtyp
 /* dz = dy * (y > 0) elementwise (ReLU backward), same storage dtype. */
 int murcl_relu_bwd(const void* dy, const void* y, void* dz, int64_t n, int dtype, void* stream);
 
+/* ---- optimiser step over the flat parameter arena: train_MuRCL.py:154-171 (torch.optim.Adam), :296 (step) ---- */
+
+/* One fused Adam step (L2 weight decay folded into the gradient, bias correction, no amsgrad - torch.optim.Adam's
+ * defaults as the reference uses them) over n contiguous fp32 parameters:
+ *   g' = grad_scale * grad + weight_decay * param;  m = m + (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
+ *   param -= lr / (1-beta1^t) * m / (sqrt(v) / sqrt(1-beta2^t) + eps),   t = state[0] + 1.
+ * shadow_bf16 (may be NULL) receives the bf16 copy of the updated parameters that the tcgen05 GEMMs read.
+ * The hyper-parameters are doubles: 1 - beta and the bias corrections are formed in double and rounded once, as torch does.
+ * lr_dev (may be NULL) overrides lr from device memory (a schedule that changes between CUDA-graph replays).
+ * state: int64[2] on the device, zero-initialised: [0] = steps taken (advanced by the kernel), [1] = scratch. */
+int murcl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                    const float* lr_dev, int64_t* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ class MurclError(RuntimeError):
     pass
 
 
-_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); must list every symbol declared in include/murcl_b200.h
 SIGNATURES = {
@@ -73,6 +73,7 @@ SIGNATURES = {
     "murcl_colsum": (_i, [_p, _l, _i, _i, _p, _p]),
     "murcl_relu_bwd": (_i, [_p, _p, _p, _l, _i, _p]),
     "murcl_dropout": (_i, [_p, _l, _f, _p, _i, _p]),
+    "murcl_adam_step": (_i, [_p, _p, _p, _p, _p, _l, _d, _d, _d, _d, _d, _d, _p, _p, _p]),
 }
 
 _lib = None

@@ -80,6 +80,10 @@ struct Params {
   int terms;
   int pa[6], pb[6];
   int a_plane_rows, b_plane_rows;
+  // L2 prefetch distance of the TMA producer (cp.async.bulk.prefetch.tensor): B-stationary kernels pull the A k-blocks of
+  // the tile `l2pf` tiles ahead into L2, streaming kernels the operand k-blocks `l2pf` k-blocks ahead.  The shared-memory
+  // ring alone looks ahead ~1 us of MMA time (4 x 16 KB of A beside the resident B tile), less than the loaded HBM latency.
+  int l2pf;
 };
 
 // CG = cta_group: 1 = one SM per 128 x BN tile; 2 = a CTA pair shares a 256 x BN tile (each CTA holds its 128 rows of A
@@ -119,7 +123,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const Params p) {
   using C = Cfg<BN, EPI, CG, (int)sizeof(TOUT), BSTAT>;
-  static_assert(CG == 1 || !A_MN, "the CTA-pair kernel takes a K-major A operand");
   static_assert(!BSTAT || (!A_MN && EPI != EPI_SPLIT), "B-stationary: forward / input-gradient kernels only");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
@@ -230,6 +233,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m0 = (mb * CG + (int)cta_rank) * BLOCK_M;                   // this CTA's 128 rows of the tile
         const int n0 = nb * BN + (int)cta_rank * (BN / CG);                    // this CTA's share of the B rows
         const int nterms = p.terms > 1 ? p.terms : 1;
+        if (BSTAT && p.l2pf > 0) {
+          // the A rows of a later tile of this CTA: in L2 by the time the ring asks for them
+          const int tn = t + p.l2pf * tile_step;
+          if (tn < total_tiles) {
+            int mbn, nbn, spn;
+            tile_coords(tn, mbn, nbn, spn);
+            const int m0n = (mbn * CG + (int)cta_rank) * BLOCK_M;
+            for (int kb = 0; kb < nkb; ++kb) tma_prefetch_l2_2d(&map_a, kb * BLOCK_K, m0n);
+          }
+        }
         for (int term = 0; term < nterms; ++term) {
         const int ra = p.terms > 1 ? p.pa[term] * p.a_plane_rows : 0;         // row offset of this term's A / B plane
         const int rb = p.terms > 1 ? p.pb[term] * p.b_plane_rows : 0;
@@ -249,11 +262,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++s == C::STAGES) { s = 0; ph ^= 1u; }
             continue;
           }
+          if (!BSTAT && p.l2pf > 0 && p.terms <= 1 && kb + p.l2pf < nkb) {
+            const int kp = kk + p.l2pf * BLOCK_K;
+            if (!A_MN) {
+              tma_prefetch_l2_2d(&map_a, kp, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_prefetch_l2_2d(&map_a, m0 + 64 * j, kp);
+            }
+            if (!B_MN) {
+              tma_prefetch_l2_2d(&map_b, kp, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / CG / 64; ++j) tma_prefetch_l2_2d(&map_b, n0 + 64 * j, kp);
+            }
+          }
           if (CG == 2) {
             // both CTAs load their halves; all bytes are counted on the LEADER's full barrier (it issues the MMAs)
             if (leader) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
             const uint32_t fb = mapa(full_bar(s), 0);
-            tma_load_2d_2sm(a_dst, &map_a, fb, kk, m0 + ra);
+            if (!A_MN) {
+              tma_load_2d_2sm(a_dst, &map_a, fb, kk, m0 + ra);
+            } else {                                                            // weight gradient: two 64-wide MN blocks
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d_2sm(a_dst + j * 8192, &map_a, fb, m0 + 64 * j, kk + ra);
+            }
             if (!B_MN) {
               tma_load_2d_2sm(b_dst, &map_b, fb, kk, n0 + rb);
             } else {
@@ -720,6 +753,16 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   Params pp = p;
   pp.debug = debug;
+  {
+    static int pf_tiles = -1, pf_kb = -1;
+    if (pf_tiles < 0) {
+      const char* e = getenv("MURCL_GEMM_L2PF");          // B-stationary kernels: tiles ahead (default 1; 0 = off)
+      pf_tiles = e ? atoi(e) : 1;
+      const char* f = getenv("MURCL_GEMM_L2PF_KB");       // streaming kernels: k-blocks ahead (default 0 = off)
+      pf_kb = f ? atoi(f) : 0;
+    }
+    pp.l2pf = BSTAT ? pf_tiles : pf_kb;
+  }
   static unsigned long long* trace_buf = nullptr;
   if (debug & 8) {
     if (!trace_buf) cudaMalloc(&trace_buf, sizeof(unsigned long long) * 24 * 4096);
@@ -897,10 +940,22 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
                    : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, p, st);
 }
 
+// The weight gradient is operand-load bound with one CTA per 128 x 256 tile (48 KB of operands per 512 tensor-pipe clocks):
+// a CTA pair on a 256 x 256 tile pulls 32 KB per CTA for the same MMA work and fits a deeper ring.
+static bool wgrad_pair(int64_t M, int N, int K) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MURCL_WGRAD_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && pair_ok(M, N) && K % 256 == 0;
+}
+
 static void wgrad_plan(int64_t M, int N, int K, int& BN, int& splits, int64_t& k_chunk) {
   BN = (K % 256 == 0) ? 256 : 128;
-  const int tiles = ceil_div(N, BLOCK_M) * ceil_div(K, BN);
-  splits = sm_count() / tiles;                                     // one wave
+  const bool pair = wgrad_pair(M, N, K);
+  const int tiles = ceil_div(N, pair ? 2 * BLOCK_M : BLOCK_M) * ceil_div(K, BN);
+  splits = (pair ? sm_count() / 2 : sm_count()) / tiles;           // one wave
   if (splits < 1) splits = 1;
   const int64_t kb_total = (M + BLOCK_K - 1) / BLOCK_K;
   if (splits > kb_total) splits = (int)kb_total;
@@ -940,8 +995,13 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
   p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
-  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
-                 : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
+  if (wgrad_pair(M, N, K)) {
+    p.m_tiles = ceil_div(N, 2 * BLOCK_M);
+    rc = launch<256, true, true, EPI_SPLIT, float, 2>(ma, mb, ma, p, st);
+  } else {
+    rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
+                   : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
+  }
   if (rc != MURCL_OK) return rc;
   const int64_t n = (int64_t)N * K;
   return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);
@@ -963,6 +1023,17 @@ static void split_terms(Params& p, int planes, int64_t a_plane_rows, int64_t b_p
   p.b_plane_rows = (int)b_plane_rows;
 }
 
+// CTA pairs for the split-precision forward / input-gradient GEMMs (six products per tile: operand loads are what bounds
+// the one-CTA kernel, and a pair halves the B bytes per MMA).  MURCL_SPLIT_PAIR=0 restores the one-CTA kernels.
+static bool split_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MURCL_SPLIT_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool tc_split_supported(int64_t M, int N, int K) {
   return tc_enabled() && M >= 1024 && N >= 128 && N % 64 == 0 && K >= 64 && K % 64 == 0 && 3 * ((M + 63) / 64 * 64) < (1ll << 31);
 }
@@ -975,10 +1046,11 @@ int tc_split_fwd(const void* xp, const void* wp, const float* bias, float* y, in
     return MURCL_EINVAL;
   }
   const int BN = (N % 256 == 0) ? 256 : 128;
+  const bool pair = split_pair() && pair_ok(M, N);
   CUtensorMap ma, mb, mc;
   int rc = make_map(&ma, xp, planes * xpr, K, BLOCK_K, BLOCK_M);
   if (rc != MURCL_OK) return rc;
-  rc = make_map(&mb, wp, planes * wpr, K, BLOCK_K, BN);
+  rc = make_map(&mb, wp, planes * wpr, K, BLOCK_K, pair ? BN / 2 : BN);     // a CTA of a pair loads half of the B tile
   if (rc != MURCL_OK) return rc;
   rc = make_store_map(&mc, y, M, N, 4);
   if (rc != MURCL_OK) return rc;
@@ -987,6 +1059,10 @@ int tc_split_fwd(const void* xp, const void* wp, const float* bias, float* y, in
   p.splits = 1; p.k_chunk = ((int64_t)K + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(N, BN);
   split_terms(p, planes, xpr, wpr);
+  if (pair) {
+    p.m_tiles = ceil_div(M, 2 * BLOCK_M);
+    return launch<256, false, false, EPI_FWD, float, 2>(ma, mb, mc, p, st);
+  }
   return BN == 256 ? launch<256, false, false, EPI_FWD, float>(ma, mb, mc, p, st)
                    : launch<128, false, false, EPI_FWD, float>(ma, mb, mc, p, st);
 }
@@ -1014,6 +1090,10 @@ int tc_split_bwd_input(const void* dyp, const void* wp, float* dx, int64_t M, in
   p.splits = 1; p.k_chunk = ((int64_t)N + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
   split_terms(p, planes, dpr, wpr);
+  if (split_pair() && pair_ok(M, K)) {
+    p.m_tiles = ceil_div(M, 2 * BLOCK_M);
+    return launch<256, false, true, EPI_DGRAD, float, 2>(ma, mb, mc, p, st);
+  }
   return BN == 256 ? launch<256, false, true, EPI_DGRAD, float>(ma, mb, mc, p, st)
                    : launch<128, false, true, EPI_DGRAD, float>(ma, mb, mc, p, st);
 }
@@ -1049,8 +1129,13 @@ int tc_split_bwd_weight(const void* dyp, const void* xp, float* dw, int64_t M, i
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
   split_terms(p, planes, pr, pr);
-  rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
-                 : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
+  if (wgrad_pair(M, N, K)) {
+    p.m_tiles = ceil_div(N, 2 * BLOCK_M);
+    rc = launch<256, true, true, EPI_SPLIT, float, 2>(ma, mb, ma, p, st);
+  } else {
+    rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
+                   : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
+  }
   if (rc != MURCL_OK) return rc;
   const int64_t n = (int64_t)N * K;
   return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);

@@ -837,6 +837,47 @@ def test_pretrain_step_golden(golden):
     assert n >= 10
 
 
+def test_batched_step_draws_are_the_reference_draws_in_one_go(golden, monkeypatch):
+    """``rng="batched"``: every draw of the step issued up front (``draw_step_batched``).  The distributions are the
+    reference's (datasets.py:266-267: lam in [alpha, 1), one permutation per view inside its own half) and the step
+    computed from them is bit-identical to the same numbers injected patch-step by patch-step."""
+    from murcl_b200 import pretrain
+    from murcl_b200.csr import BagStore
+    from murcl_b200.dropin import abmil, cl, losses, rlmil
+    g = golden("pretrain_step")
+    b, k, d, fs, T, L, D, hid, proj = g["cfg"].tolist()
+    torch.manual_seed(5)
+    act, lam, perm = pretrain.draw_step_batched(T, b, k, 0.9, DEV, True)
+    assert act.shape == (T, 2 * b, k) and lam.shape == (T, 2 * b) and perm.shape == (T, 2 * b) and perm.dtype == torch.int32
+    assert float(lam.min()) >= 0.9 and float(lam.max()) < 1.0 and float(act.min()) >= 0.0 and float(act.max()) < 1.0
+    ident = torch.arange(b, device=DEV, dtype=torch.int32)
+    for t in range(T):
+        assert torch.equal(perm[t, :b].sort().values, ident) and torch.equal(perm[t, b:].sort().values, ident + b)
+    assert pretrain.draw_step_batched(T, b, k, 0.9, DEV, False)[0].shape == (1, 2 * b, k)
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), d, k, seed=91)
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    crit = losses.NT_Xent(b, float(g["tau"]))
+    results = []
+    for mode in ("batched", "injected"):
+        enc = _load(abmil.ABMIL(d, L=L, D=D, dim_out=proj, precision="fp32"), synth.abmil_state(d, L, D, proj, seed=92))
+        model = cl.CL(enc, projection_dim=proj, n_features=L)
+        fc = _load(rlmil.Full_layer(L, hid, True, proj), synth.full_layer_state(L, hid, proj, seed=93))
+        if mode == "batched":
+            monkeypatch.setattr(pretrain, "draw_step_batched", lambda *a, **kw: (act, lam, perm))
+            loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=0.9, precision="fp32", rng="batched")
+        else:
+            draws = [([act[t, :b], act[t, b:]], [lam[t, :b].view(b, 1), lam[t, b:].view(b, 1)],
+                      [perm[t, :b].long(), perm[t, b:].long() - b]) for t in range(T)]
+            loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=0.9, precision="fp32", draws=draws)
+        results.append((loss.clone(), _grads(enc), _grads(fc)))
+    assert torch.equal(results[0][0], results[1][0])
+    for ga, gb in ((results[0][1], results[1][1]), (results[0][2], results[1][2])):
+        for key in ga:
+            assert_close(ga[key], gb[key], 1e-6, f"grad {key} batched vs injected draws", floor=1e-6)
+    with pytest.raises(ValueError):
+        pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, rng="nope")
+
+
 # ------------------------------------------------------------------------------------------------
 # resident slide cache, slot_bag addressing, row-sharded bags
 # ------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """CUDA-event timing of the tcgen05 dense-layer entry points on given shapes (bf16): fwd / input gradient / weight gradient.
+cuBLAS (torch.matmul, bf16, no epilogue) on the same shapes is printed beside them as a yardstick.
 usage: bench_gemm_shapes.py M,N,K [M,N,K ...]"""
 import os
 import sys
@@ -36,7 +37,12 @@ for spec in sys.argv[1:]:
     t_f = timeit(lambda: ops.linear_fwd(x, w, b, ops.ACT_NONE))
     t_f32 = timeit(lambda: ops.linear_fwd(x, w, b, ops.ACT_NONE, torch.float32))
     t_d = timeit(lambda: ops.linear_bwd_input(dy, w))
-    t_w = timeit(lambda: ops.linear_bwd_weight(dy, x, True))
+    dw_acc = torch.zeros(N, K, device=DEV)
+    t_w = timeit(lambda: ops.linear_bwd_weight(dy, x, False, dw_into=dw_acc))
+    wt = w.t().contiguous()
+    c_f = timeit(lambda: torch.matmul(x, wt))                 # [M,K] @ [K,N]
+    c_d = timeit(lambda: torch.matmul(dy, w))                  # [M,N] @ [N,K]
+    c_w = timeit(lambda: torch.matmul(dy.t(), x))              # [N,M] @ [M,K]
     fl = 2.0 * M * N * K
     print(f"M={M} N={N} K={K}: fwd {t_f:.1f} us ({fl / t_f / 1e6:.0f} TF)  fwd->fp32 {t_f32:.1f} us  dgrad {t_d:.1f} us ({fl / t_d / 1e6:.0f} TF)  "
-          f"wgrad {t_w:.1f} us ({fl / t_w / 1e6:.0f} TF)")
+          f"wgrad {t_w:.1f} us ({fl / t_w / 1e6:.0f} TF) | cuBLAS fwd {c_f:.1f} dgrad {c_d:.1f} wgrad {c_w:.1f} us")
