@@ -18,6 +18,7 @@ summation order over the calls differs.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Sequence
 
 import torch
@@ -114,10 +115,13 @@ class HeadTape:
         return torch.zeros(want_shape, device=param.device, dtype=torch.float32), True
 
     @torch.no_grad()
-    def backward(self, dzs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    def backward(self, dzs: Sequence[torch.Tensor], side=None) -> List[torch.Tensor]:
         """``dzs``: gradient of the loss w.r.t. every leaf returned by ``forward_views`` (same order).  Accumulates the
         gradients of the six Full_layer parameters and returns the gradient w.r.t. every input ``x`` (same order as the
-        calls' views), to be pushed into the graph that produced them."""
+        calls' views), to be pushed into the graph that produced them.  ``side`` (a CUDA stream): the three batched
+        weight-gradient GEMMs - which nothing downstream of this call reads - are issued there, beside the recurrence and
+        the start of the aggregators' backward; the CALLER joins it (``current_stream().wait_stream(side)``) before the
+        parameter gradients are used.  The operands stay referenced by the tape until it is dropped."""
         nv, B, H, F, C = self.nv, self.B, self.H, self.F, self.C
         n = self.step * nv
         if len(dzs) != n:
@@ -131,8 +135,15 @@ class HeadTape:
         for name, prm in (("w_ih", w_ih), ("w_hh", w_hh), ("b_ih", b_ih), ("b_hh", b_hh), ("w_fc", w_fc), ("b_fc", b_fc)):
             grads[name], own[name] = self._grad_into(prm, prm.shape)
         # output layer over all calls
+        if any(own.values()):
+            side = None          # gradients returned through .grad are combined on the calling stream right below
+        main = torch.cuda.current_stream()
+        on_side = (lambda: torch.cuda.stream(side)) if side is not None else contextlib.nullcontext
         dHd = ops.linear_bwd_input(DZs.view(n * B, C), self.w_fc_s).view(n, B, H)
-        ops.linear_bwd_weight(DZs.view(n * B, C), self.Hs[:n].view(n * B, H), True, dw_into=grads["w_fc"], db_into=grads["b_fc"])
+        if side is not None:
+            side.wait_stream(main)
+        with on_side():
+            ops.linear_bwd_weight(DZs.view(n * B, C), self.Hs[:n].view(n * B, H), True, dw_into=grads["w_fc"], db_into=grads["b_fc"])
         # the recurrence, last call first
         DGI = torch.empty((n, B, 3 * H), device=dev, dtype=self.dt)
         DGH = torch.empty((n, B, 3 * H), device=dev, dtype=self.dt)
@@ -154,8 +165,12 @@ class HeadTape:
                 flip ^= 1
                 have_carry = True
         # weight gradients of the recurrence over all calls (h_prev rows of restarting calls are zeros: exact)
-        ops.linear_bwd_weight(DGH.view(n * B, 3 * H), self.HPs[:n].view(n * B, H), True, dw_into=grads["w_hh"], db_into=grads["b_hh"])
-        ops.linear_bwd_weight(DGI.view(n * B, 3 * H), self.Xs[:n].view(n * B, F), True, dw_into=grads["w_ih"], db_into=grads["b_ih"])
+        if side is not None:
+            side.wait_stream(main)
+            self._keep = (dz, DZs, DGI, DGH)            # read on the side stream: must outlive this call
+        with on_side():
+            ops.linear_bwd_weight(DGH.view(n * B, 3 * H), self.HPs[:n].view(n * B, H), True, dw_into=grads["w_hh"], db_into=grads["b_hh"])
+            ops.linear_bwd_weight(DGI.view(n * B, 3 * H), self.Xs[:n].view(n * B, F), True, dw_into=grads["w_ih"], db_into=grads["b_ih"])
         dX = ops.linear_bwd_input(DGI.view(n * B, 3 * H), self.w_ih_s)
         dX = dX.float() if dX.dtype != torch.float32 else dX
         for name, prm in (("w_ih", w_ih), ("w_hh", w_hh), ("b_ih", b_ih), ("b_hh", b_hh), ("w_fc", w_fc), ("b_fc", b_fc)):

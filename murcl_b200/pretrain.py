@@ -7,6 +7,7 @@ PPO object are the drop-in modules, used through the same methods the reference 
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import List, Optional, Sequence, Tuple
 
@@ -74,7 +75,8 @@ def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
 def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_size: int = 1024, alpha: float = 0.9,
                   stage: int = 1, ppo=None, memories=None, draws: Optional[Sequence[Draw]] = None,
                   precision: Optional[str] = None, backward: bool = True, eps=None, keep_memory: bool = False,
-                  slot_bag: Optional[torch.Tensor] = None, after_head_backward=None, rng: str = "reference"):
+                  slot_bag: Optional[torch.Tensor] = None, after_head_backward=None, rng: str = "reference",
+                  overlap_heads: Optional[bool] = None):
     """Returns ``(loss, per-step losses)``.  ``stage`` follows train_MuRCL.py: 1 = random actions; 3 = the PPO actor
     chooses the actions of patch-steps >= 1 (the actor is not updated, :292-295); 2 = the same rollout under ``no_grad``
     with the MIL model frozen, then ``ppo.update(m)`` for each view's memory instead of the optimiser step (:244-247,
@@ -88,7 +90,12 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
     exchanging them (``ParamArena.allreduce(..., async_op=True)``) under the rest of the backward pass.
     ``rng`` (used when ``draws`` is None): ``"reference"`` issues the random draws patch-step by patch-step in the
     reference's call order (train_MuRCL.py:235,256-258; datasets.py:266-267); ``"batched"`` draws everything the step
-    needs up front (``draw_step_batched``: same distributions, ~110 fewer small launches per step)."""
+    needs up front (``draw_step_batched``: same distributions, ~110 fewer small launches per step).
+    ``overlap_heads`` (default: on with the recurrent-head tape, ``MURCL_OVERLAP_HEADS=0`` turns it off): the projection
+    head and the loss of patch-step t (``Full_layer`` on both views, NT-Xent, the reward) run on a side stream.  Nothing
+    the NEXT patch-step needs depends on them - the actor reads the bag embeddings, not the loss - so their ~15 short,
+    dependent launches overlap the actor's own chain and the window selection instead of preceding them; the streams
+    join before the losses are summed."""
     if rng not in ("reference", "batched"):
         raise ValueError("rng must be 'reference' or 'batched'")
     if stage not in (1, 2, 3):
@@ -113,6 +120,9 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         # Full_layer over the T x 2 calls of this step on the recurrent-head tape: batched backward (headtape.py)
         from .headtape import HeadTape
         tape = HeadTape(fc, T, 2, B, dev, getattr(fc, "precision", None) or precision or ops.default_precision())
+    if overlap_heads is None:
+        overlap_heads = tape is not None and os.environ.get("MURCL_OVERLAP_HEADS", "1") != "0"
+    side = head_stream(dev) if (overlap_heads and torch.device(dev).type == "cuda") else None
     pre = draw_step_batched(T, B, K, alpha, dev, stage == 1) if (draws is None and rng == "batched") else None
     grad_mode = torch.no_grad() if stage == 2 else torch.enable_grad()
     with grad_mode:
@@ -138,20 +148,25 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
                     draw = (actions, lams, perms)
                 x_all = pack_views(store, draw, feat_size, dt, slot_bag)
             outputs, states = encode_views(model, x_all)
-            if tape is not None:
-                outputs = tape.forward_views(outputs, restart=(t == 0))
-            elif hasattr(fc, "forward_views"):
-                outputs = fc.forward_views(outputs, restart=(t == 0))
-            else:
-                outputs = [fc(o, restart=(t == 0)) for o in outputs]
-            loss = criterion(outputs[0], outputs[1])
-            losses.append(loss)
-            sim = criterion.last_cosine.view(1, -1)          # by-product of the loss kernel (train_MuRCL.py:253,282)
-            if t >= 1 and memories is not None:
-                reward = sim_last - sim
-                for m in memories:
-                    m.rewards.append(reward)
-            sim_last = sim
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())           # fork: the bag embeddings are complete
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                if tape is not None:
+                    outputs = tape.forward_views(outputs, restart=(t == 0))
+                elif hasattr(fc, "forward_views"):
+                    outputs = fc.forward_views(outputs, restart=(t == 0))
+                else:
+                    outputs = [fc(o, restart=(t == 0)) for o in outputs]
+                loss = criterion(outputs[0], outputs[1])
+                losses.append(loss)
+                sim = criterion.last_cosine.view(1, -1)      # by-product of the loss kernel (train_MuRCL.py:253,282)
+                if t >= 1 and memories is not None:
+                    reward = sim_last - sim
+                    for m in memories:
+                        m.rewards.append(reward)
+                sim_last = sim
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)                   # join: every loss / reward is complete
     total = sum(losses) / T
     if stage == 2:
         for m in memories:
@@ -160,10 +175,16 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         # loss -> projections (the loss kernels' own tiny graph), projections -> bag embeddings (the tape, one batched pass),
         # bag embeddings -> everything upstream (the aggregators' graphs, one per patch-step)
         dzs = torch.autograd.grad(total, tape.z_leaves)
-        d_outs = tape.backward(dzs)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)      # the loss nodes' backward ran where their forward did
+        # the head's weight-gradient GEMMs go to the side stream unless a data-parallel hook wants those gradients right away
+        wgrad_side = side if (after_head_backward is None and os.environ.get("MURCL_OVERLAP_HEAD_WGRAD", "1") != "0") else None
+        d_outs = tape.backward(dzs, side=wgrad_side)
         if after_head_backward is not None:
             after_head_backward()
         torch.autograd.backward(tape.x_inputs, d_outs)
+        if wgrad_side is not None:
+            torch.cuda.current_stream().wait_stream(wgrad_side)
     elif backward:
         total.backward()
     if memories is not None and not keep_memory:
@@ -176,6 +197,20 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
     if isinstance(hid, torch.Tensor) and hid.requires_grad:
         fc.hidden = hid.detach()
     return total.detach(), [l.detach() for l in losses]
+
+
+_HEAD_STREAMS = {}
+
+
+def head_stream(device) -> torch.cuda.Stream:
+    """The per-device side stream of the projection-head / loss chain (high priority: its kernels are a few CTAs each and
+    should not queue behind the pending CTAs of a persistent GEMM)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _HEAD_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=key, priority=-1)
+        _HEAD_STREAMS[key] = st
+    return st
 
 
 class GraphedStep:
