@@ -323,6 +323,37 @@ def roofline_probe(job, store, slot_bag, peaks):
             "timing": "CUDA events around every launch of one extra eager step on the launch stream"}
 
 
+def gemm_yardstick(rows, n=512, k=512, reps=20):
+    """The dominant GEMM shape timed ALONE (burst clocks, back-to-back launches, inputs larger than L2): this repo's fused
+    forward kernel (bias + ReLU + bit mask) beside cuBLAS through torch.matmul (no epilogue).  Context for `roofline.frac`:
+    a [rows, 512] x [512, 512] product sits at the HBM / tensor ridge, where no kernel reaches the square-GEMM peak."""
+    from murcl_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(rows, k, generator=g).to("cuda", torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to("cuda", torch.bfloat16)
+    b = torch.zeros(n, device="cuda")
+    wt = w.t().contiguous()
+
+    def t_us(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    own = t_us(lambda: ops.linear_fwd(x, w, b, ops.ACT_RELU, relu_bits=True))
+    lib = t_us(lambda: torch.matmul(x, wt))
+    fl = 2.0 * rows * n * k
+    return {"shape": [rows, n, k], "own_fused_fwd_us": round(own, 1), "own_fused_fwd_tflops": round(fl / own / 1e6, 1),
+            "cublas_us": round(lib, 1), "cublas_tflops": round(fl / lib / 1e6, 1),
+            "note": "timed alone at burst clocks (the step runs power-capped, see clocks); cuBLAS = torch.matmul, bf16, no epilogue"}
+
+
 def cpu_baseline(a, threads=None, reps=2):
     """The oracle's restatement of the same step on the host cores, on a bounded sample (a.cpu_bags slides)."""
     from murcl_b200 import synth
@@ -604,6 +635,11 @@ def main():
                        "rank-0 host-clock marks inside the device-timed region"}
 
     roof = roofline_probe(job, store, slot_bag, peaks)      # every rank runs it: the step contains collectives
+    if roof is not None and rank == 0 and a.precision == "bf16":
+        try:
+            roof["yardstick"] = gemm_yardstick(2 * a.bags * a.feat_size)
+        except Exception as e:                               # noqa: BLE001 - context only, never fatal
+            roof["yardstick"] = {"error": f"{type(e).__name__}: {e}"}
     vlog("roofline probe done")
 
     secondary = {}

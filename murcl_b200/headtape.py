@@ -56,6 +56,7 @@ class HeadTape:
         self.HPs = torch.zeros((n + 1, B, H), **st)      # h_prev of every chain step (zeros where the chain restarts)
         self.restart: List[bool] = []
         self.x_inputs: List[torch.Tensor] = []
+        self.stacked_inputs: List[bool] = []                 # per call: one stacked input instead of one per view
         self.z_leaves: List[torch.Tensor] = []
         self.step = 0
         w_ih, w_hh, self.b_ih, self.b_hh = fc.rnn.weight_ih_l0, fc.rnn.weight_hh_l0, fc.rnn.bias_ih_l0, fc.rnn.bias_hh_l0
@@ -65,25 +66,31 @@ class HeadTape:
 
     # ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_views(self, xs: Sequence[torch.Tensor], restart: bool = False) -> List[torch.Tensor]:
+    def forward_views(self, xs: Sequence[torch.Tensor], restart: bool = False, stacked: torch.Tensor = None) -> List[torch.Tensor]:
         """``[fc(x, restart) for x in xs]`` (train_MuRCL.py:243,272): returns one LEAF tensor per view (``requires_grad``);
-        their gradients are what ``backward`` consumes."""
+        their gradients are what ``backward`` consumes.  ``stacked`` (``[n_views * B, F]``, the tensor the views ``xs`` are
+        consecutive row blocks of): recorded as the call's ONE input instead of the views, so that ``backward`` returns a
+        single gradient for it and autograd does not rebuild it from per-view slices (two fills and an add per call)."""
         nv, B, H = self.nv, self.B, self.H
         if len(xs) != nv or any(tuple(x.shape) != (B, self.F) for x in xs):
             raise ops.MurclError(f"HeadTape: expected {nv} views of shape {(B, self.F)}")
+        if stacked is not None and tuple(stacked.shape) != (nv * B, self.F):
+            raise ops.MurclError(f"HeadTape: stacked input must be {(nv * B, self.F)}")
         if self.step >= self.n_calls:
             raise ops.MurclError("HeadTape: more calls than the tape was sized for")
         if self.step == 0 and not restart:
             raise ops.MurclError("HeadTape: the first call of a tape must restart the hidden state (train_MuRCL.py:243)")
         lib = _lib.load()
         c0 = self.step * nv
-        for v, x in enumerate(xs):
+        for v, x in enumerate([stacked] if stacked is not None else xs):
             src = x.detach().contiguous()
+            dst = self.Xs[c0:c0 + nv] if stacked is not None else self.Xs[c0 + v]
             if src.dtype == self.dt:
-                self.Xs[c0 + v].copy_(src)
+                dst.view(src.shape).copy_(src)
             else:
-                ops.cast_into(src.float() if src.dtype != torch.float32 else src, self.Xs[c0 + v])
+                ops.cast_into(src.float() if src.dtype != torch.float32 else src, dst)
             self.x_inputs.append(x)
+        self.stacked_inputs.append(stacked is not None)
         ops.linear_fwd(self.Xs[c0:c0 + nv].view(nv * B, self.F), self.w_ih_s, self.bias[0], out=self.GI[c0:c0 + nv].view(nv * B, 3 * H))
         if restart and self.step > 0:
             self.HPs[c0:c0 + nv + 1].zero_()                                   # (a fresh tape is zero already)
@@ -117,8 +124,8 @@ class HeadTape:
     @torch.no_grad()
     def backward(self, dzs: Sequence[torch.Tensor], side=None) -> List[torch.Tensor]:
         """``dzs``: gradient of the loss w.r.t. every leaf returned by ``forward_views`` (same order).  Accumulates the
-        gradients of the six Full_layer parameters and returns the gradient w.r.t. every input ``x`` (same order as the
-        calls' views), to be pushed into the graph that produced them.  ``side`` (a CUDA stream): the three batched
+        gradients of the six Full_layer parameters and returns the gradient w.r.t. every recorded input (``x_inputs``: one per
+        view, or one per call where ``stacked`` was given), to be pushed into the graph that produced them.  ``side`` (a CUDA stream): the three batched
         weight-gradient GEMMs - which nothing downstream of this call reads - are issued there, beside the recurrence and
         the start of the aggregators' backward; the CALLER joins it (``current_stream().wait_stream(side)``) before the
         parameter gradients are used.  The operands stay referenced by the tape until it is dropped."""
@@ -177,4 +184,10 @@ class HeadTape:
             if own[name]:
                 prm.grad = grads[name] if prm.grad is None else prm.grad + grads[name]
         dX = dX.view(n, B, F)
-        return [dX[c] for c in range(n)]
+        out = []
+        for call, stacked in enumerate(self.stacked_inputs):     # same order as x_inputs
+            if stacked:
+                out.append(dX[call * nv:(call + 1) * nv].reshape(nv * B, F))
+            else:
+                out.extend(dX[call * nv + v] for v in range(nv))
+        return out

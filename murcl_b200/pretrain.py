@@ -59,6 +59,19 @@ def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dty
     return store.pack(act, feat_size, lam, perm, out_dtype, slot_bag)
 
 
+def _encode_stacked(model, x_all: torch.Tensor, n_views: int = 2):
+    """``encode_views`` that also hands back the un-split ``[n_views * B, F]`` encoder output (None when the model is not
+    the CL wrapper): the recurrent-head tape takes it as one input."""
+    from .dropin.cl import CL
+    B = x_all.shape[0] // n_views
+    if isinstance(model, CL):
+        out = model.encoder(x_all)[0]
+        outs = [out[v * B:(v + 1) * B] for v in range(n_views)]
+        return out, outs, [o.detach() for o in outs]
+    outs, states = model([x_all[v * B:(v + 1) * B] for v in range(n_views)])
+    return None, outs, states
+
+
 def encode_views(model, x_all: torch.Tensor, n_views: int = 2):
     """``model(x_views)`` of train_MuRCL.py:242,271 -> ``(outputs, detached states)``.  Bags are independent, so
     when the model is the CL wrapper all views go through its encoder in ONE batched call (half the launches,
@@ -147,12 +160,12 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
                         actions = [torch.rand((B, K), device=dev) for _ in range(2)]
                     draw = (actions, lams, perms)
                 x_all = pack_views(store, draw, feat_size, dt, slot_bag)
-            outputs, states = encode_views(model, x_all)
+            out_all, outputs, states = _encode_stacked(model, x_all)
             if side is not None:
                 side.wait_stream(torch.cuda.current_stream())           # fork: the bag embeddings are complete
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 if tape is not None:
-                    outputs = tape.forward_views(outputs, restart=(t == 0))
+                    outputs = tape.forward_views(outputs, restart=(t == 0), stacked=out_all)
                 elif hasattr(fc, "forward_views"):
                     outputs = fc.forward_views(outputs, restart=(t == 0))
                 else:

@@ -42,6 +42,18 @@ def gpu_time(fn, reps=7):
     return ts[len(ts) // 2]
 
 
+def graphed(step):
+    """The same step replayed as ONE CUDA graph (pretrain.GraphedStep): the single-bag configurations are bound by the
+    host's ~40 us per launch, not by the kernels; fixed shapes (RLMIL trains on fixed-size windows) make them capturable."""
+    from murcl_b200 import pretrain
+    try:
+        g = pretrain.GraphedStep(step, warmup=2)
+        return lambda: g()
+    except Exception as e:                                   # noqa: BLE001
+        sys.stderr.write(f"[bench_configs] graph capture failed: {type(e).__name__}: {e}\n")
+        return None
+
+
 def cpu_time(fn, reps=2):
     fn()
     ts = []
@@ -67,9 +79,12 @@ def main():
         x = feats[0].to(DEV)
 
         def step():
-            m.zero_grad(set_to_none=True)
+            m.zero_grad(set_to_none=False)
             m(x.unsqueeze(0))[0].sum().backward()
         row[prec] = round(1.0 / gpu_time(step), 1)
+        gs = graphed(step)
+        if gs is not None:
+            row[prec + "_cuda_graph"] = round(1.0 / gpu_time(gs), 1)
     sdl = leaf(sd)
     row["cpu_oracle"] = round(1.0 / cpu_time(lambda: O.abmil_forward(feats, sdl).sum().backward()), 2)
     out.append(row)
@@ -112,10 +127,13 @@ def main():
         x = feats[0].unsqueeze(0).to(DEV)
 
         def step():
-            m.zero_grad(set_to_none=True)
+            m.zero_grad(set_to_none=False)
             c, b, _ = m(x)
             (c.sum() + b.sum()).backward()
         row[prec] = round(1.0 / gpu_time(step), 1)
+        gs = graphed(step)
+        if gs is not None:
+            row[prec + "_cuda_graph"] = round(1.0 / gpu_time(gs), 1)
     sdl = leaf(sd)
 
     def cpu_step4():

@@ -89,6 +89,18 @@ def main():
         ops.ntxent_raw(z, B, 1.0, True)
     alg["ntxent"] = 2 * (2 * B * 128 * 4) + B * 4 + 4                       # z in, dz out, cosines, loss
 
+    # ---- fused Adam over a parameter arena of the bench's size (6 M parameters, bf16 shadow) ----------------------------
+    from murcl_b200.arena import ParamArena
+    from murcl_b200.optim import ArenaAdam
+    n_par = 6_037_000
+    big = torch.nn.Parameter(torch.randn(n_par, generator=g).to(dev))
+    arena = ParamArena([big])
+    opt = ArenaAdam(arena, lr=1e-4, weight_decay=1e-5)
+    arena.grad.copy_(torch.randn(arena.grad.numel(), generator=g).to(dev))
+    for _ in range(2):
+        opt.step()
+    alg["adam_step_kernel"] = arena.flat.numel() * 30                       # p, g, m, v in; p, m, v + bf16 shadow out
+
     torch.cuda.synchronize()
     out = ROOT / "gpurun_out" / "prof_hbm_alg_bytes.json"
     out.parent.mkdir(exist_ok=True)
