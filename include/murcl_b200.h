@@ -81,6 +81,17 @@ int murcl_pack_select(const int32_t* patch_cluster, const int32_t* patch_rank, c
 int murcl_pack_gather(const void* feats, int feat_dtype, int D, const int32_t* sel_idx, int S, int FS,
                       const float* lam, const int32_t* perm, void* out, int out_dtype, void* stream);
 
+/* The same gather with the grid walking the output slots in `slot_order` (a permutation of [0,S), may be NULL = plain
+ * order).  Results are identical; the order only decides which source rows are still in L2 when their second reader
+ * (the slot they are mixed into) arrives.  murcl_perm_cycle_order writes, for each of n_perm permutations of S slots
+ * (perm[n_perm*S], the mixup partner of every slot as passed to the gather), the slots listed cycle by cycle - partner
+ * after partner - which makes every source row a DRAM read once instead of twice (datasets.py:263-271 mixes slot s with
+ * slot perm[s]). */
+int murcl_perm_cycle_order(const int32_t* perm, int n_perm, int S, int32_t* order, void* stream);
+int murcl_pack_gather_ordered(const void* feats, int feat_dtype, int D, const int32_t* sel_idx, int S, int FS,
+                              const float* lam, const int32_t* perm, const int32_t* slot_order, void* out,
+                              int out_dtype, void* stream);
+
 /* ---- dense layers: every nn.Linear on the path (abmil.py:12-32, clam.py:18-77,
  *      dsmil.py:9,54-59, rlmil.py:40-53,199-200) ----------------------------------------- */
 
@@ -261,6 +272,21 @@ int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float*
  * d <= 256 and a 16-byte aligned z unless the slab is the whole batch. */
 int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, int b0, int nb, float* loss, float* dz,
                               float* cos_pair, float* workspace, void* stream);
+
+/* The two passes of the slab form as separate entry points, for ranks >= 4 where evaluating the log-sum-exp of ALL
+ * 2B global rows on every rank (2B x 2B x d FMAs, redundantly) costs more than one more tiny collective:
+ *   murcl_ntxent_lse_slab   log-sum-exp pass over the rows of the samples [b0, b0+nb) of both views only: writes
+ *                           inv_norm[a] = 1/max(|z_a|, eps) and lse[a] at those 2*nb GLOBAL row indices a (other entries
+ *                           untouched), loss_share[1] = (1/2B) sum over those rows of (lse_a - s_a,pos(a)) - the shares of
+ *                           all ranks add up to the loss -, cos_pair[b] for b in [b0, b0+nb) (may be NULL);
+ *   (the caller all-gathers inv_norm / lse of every rank's rows and the loss shares)
+ *   murcl_ntxent_grad_slab  gradient rows of the same samples from the COMPLETE inv_norm[2B] and lse[2B].
+ * workspace: murcl_ntxent_slab_workspace(B, d, nb) floats for either call, 16-byte aligned. */
+int64_t murcl_ntxent_slab_workspace(int B, int d, int nb);
+int murcl_ntxent_lse_slab(const float* z, int B, int d, float temperature, int b0, int nb, float* inv_norm, float* lse,
+                          float* loss_share, float* cos_pair, float* workspace, void* stream);
+int murcl_ntxent_grad_slab(const float* z, int B, int d, float temperature, int b0, int nb, const float* inv_norm,
+                           const float* lse, float* dz, float* workspace, void* stream);
 
 /* ---- (5) recurrent heads: rlmil.py:66-97 (actor), :187-220 (Full_layer) --------------- */
 

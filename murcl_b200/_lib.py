@@ -30,6 +30,8 @@ SIGNATURES = {
     "murcl_csr_rank_patches": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "murcl_pack_select": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "murcl_pack_gather": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _p]),
+    "murcl_perm_cycle_order": (_i, [_p, _i, _i, _p, _p]),
+    "murcl_pack_gather_ordered": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _p]),
     "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p, _p]),
     "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _p, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),
@@ -63,6 +65,9 @@ SIGNATURES = {
     "murcl_ntxent_workspace": (_l, [_i, _i]),
     "murcl_ntxent_fwd_bwd": (_i, [_p, _i, _i, _f, _p, _p, _p, _p, _p]),
     "murcl_ntxent_fwd_bwd_slab": (_i, [_p, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p]),
+    "murcl_ntxent_slab_workspace": (_l, [_i, _i, _i]),
+    "murcl_ntxent_lse_slab": (_i, [_p, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "murcl_ntxent_grad_slab": (_i, [_p, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p]),
     "murcl_gru_cell_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_gru_cell_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "murcl_gru_cell_fwd_tape": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),

@@ -7,6 +7,8 @@ its rank inside that cluster, which is all the selection rule needs (SURVEY.md s
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -143,16 +145,30 @@ class BagStore:
         return sel_idx, sel_cnt
 
     def gather(self, sel_idx: torch.Tensor, lam: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
-               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+               out_dtype: torch.dtype = torch.float32, order: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Gather + zero pad (+ mixup) -> ``[S, FS, D]``."""
-        return gather_rows_padded(self.feats, sel_idx, lam, perm, out_dtype)
+        return gather_rows_padded(self.feats, sel_idx, lam, perm, out_dtype, order)
 
-    def pack(self, actions, feat_size, lam=None, perm=None, out_dtype=torch.float32, slot_bag=None):
+    def pack(self, actions, feat_size, lam=None, perm=None, out_dtype=torch.float32, slot_bag=None, order=None):
         sel_idx, _ = self.select(actions, feat_size, slot_bag)
-        return self.gather(sel_idx, lam, perm, out_dtype)
+        return self.gather(sel_idx, lam, perm, out_dtype, order)
 
 
-def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, perm=None, out_dtype=torch.float32):
+def perm_cycle_order(perm: torch.Tensor) -> torch.Tensor:
+    """``perm`` int32 ``[n, S]`` (or ``[S]``): mixup partners of the S output slots of n gathers -> the slots of each gather
+    listed cycle by cycle (``murcl_perm_cycle_order``), the walk order that makes every source row a single DRAM read."""
+    if not perm.is_cuda or perm.dtype != torch.int32 or not perm.is_contiguous():
+        raise MurclError("perm_cycle_order: perm must be a contiguous int32 CUDA tensor")
+    flat = perm.reshape(-1, perm.shape[-1])
+    order = torch.empty_like(flat)
+    check(_lib.load().murcl_perm_cycle_order(flat.data_ptr(), flat.shape[0], flat.shape[1], order.data_ptr(), _s()),
+          "murcl_perm_cycle_order")
+    return order.view(perm.shape)
+
+
+def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, perm=None, out_dtype=torch.float32, order=None):
+    """``order`` (int32 ``[S]``, a permutation of the slots): the sequence in which the kernel walks the output slots;
+    default with mixup: the cycle order of ``perm`` (``MURCL_GATHER_ORDER=0``: plain order).  Never changes the result."""
     if not feats.is_cuda or feats.dtype not in (torch.float32, torch.bfloat16) or not feats.is_contiguous():
         raise MurclError("gather: feats must be a contiguous fp32 or bf16 CUDA tensor")
     S, FS = sel_idx.shape
@@ -163,11 +179,17 @@ def gather_rows_padded(feats: torch.Tensor, sel_idx: torch.Tensor, lam=None, per
         perm = perm.detach().reshape(-1).to(torch.int32).contiguous()
         if lam.numel() != S or perm.numel() != S:
             raise MurclError("gather: lam / perm must have one entry per output slot")
+        if order is None and S >= 16 and os.environ.get("MURCL_GATHER_ORDER", "1") != "0":
+            order = perm_cycle_order(perm)
+    if order is not None:
+        if not order.is_cuda or order.dtype != torch.int32 or order.numel() != S or not order.is_contiguous():
+            raise MurclError("gather: order must be a contiguous int32 CUDA tensor with one entry per output slot")
     code_of = {torch.float32: F32, torch.bfloat16: BF16}
     code = code_of[out_dtype]
-    check(_lib.load().murcl_pack_gather(feats.data_ptr(), code_of[feats.dtype], D, sel_idx.data_ptr(), S, FS,
-                                        None if lam is None else lam.data_ptr(), None if perm is None else perm.data_ptr(),
-                                        out.data_ptr(), code, _s()), "murcl_pack_gather")
+    check(_lib.load().murcl_pack_gather_ordered(feats.data_ptr(), code_of[feats.dtype], D, sel_idx.data_ptr(), S, FS,
+                                                None if lam is None else lam.data_ptr(), None if perm is None else perm.data_ptr(),
+                                                None if order is None else order.data_ptr(), out.data_ptr(), code, _s()),
+          "murcl_pack_gather_ordered")
     return out
 
 

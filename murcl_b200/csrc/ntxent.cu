@@ -195,8 +195,8 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 // grid (row blocks of 16 rows, splits of the b range).  Every CTA merges its tiles into one partial (max, sum-exp) per
 // row; the last split of a row block (ticket) merges the partials into lse / loss term / cosine; the last row block
 // to finish sums the loss terms in index order (deterministic).
-__global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ z, int B, int d, float inv_tau, int tiles_per_split,
-                                                      float* __restrict__ inv_norm, float* __restrict__ lse,
+__global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ z, int B, int d, float inv_tau, int sb0, int nb,
+                                                      int tiles_per_split, float* __restrict__ inv_norm, float* __restrict__ lse,
                                                       float* __restrict__ row_loss, float* __restrict__ cos_pair,
                                                       float* __restrict__ part /* [row blocks*16][splits][2] */,
                                                       float* __restrict__ pos_s /* [R] */, float* __restrict__ loss,
@@ -211,17 +211,23 @@ __global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ 
   float* inva = red_l + NTX_RA2 * NTX_TB;       // [16]
   __shared__ float red[32];
   __shared__ bool is_last;
+  __shared__ int a_of[NTX_RA2];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int a0 = blockIdx.x * NTX_RA2;
+  const int a0 = blockIdx.x * NTX_RA2;                       // first LOCAL row of the block: the rows are the slab's
   const int n_splits = gridDim.y;
+  if (t < NTX_RA2) {                                         // samples [sb0, sb0 + nb) of both views (nb == B: every row)
+    const int r = a0 + t;
+    a_of[t] = r < nb ? sb0 + r : (r < 2 * nb ? B + sb0 + (r - nb) : -1);
+  }
+  __syncthreads();
   for (int rr = w; rr < NTX_RA2; rr += 8) {                  // rows a: a warp normalises rows w, w + 8
-    const int a = a0 + rr;
+    const int a = a_of[rr];
     float ss = 0.f;
-    if (a < R)
+    if (a >= 0)
       for (int j = lane; j < d; j += 32) { const float v = z[(int64_t)a * d + j]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
     const float inv = 1.f / fmaxf(sqrtf(ss), COS_EPS);
-    for (int j = lane; j < d; j += 32) za[rr * d + j] = (a < R) ? z[(int64_t)a * d + j] * inv : 0.f;
+    for (int j = lane; j < d; j += 32) za[rr * d + j] = (a >= 0) ? z[(int64_t)a * d + j] * inv : 0.f;
     if (lane == 0) inva[rr] = inv;
   }
   const int bl = t & 63, ag = t >> 6;                       // thread: column bl of the tile, rows 4ag .. 4ag + 3
@@ -257,10 +263,10 @@ __global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ 
       const float sc = invb[bl] * inv_tau;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int a = a0 + 4 * ag + i;
+        const int a = a_of[4 * ag + i];
         const float sv = acc[i] * sc;
         if (b != a) { const float mn = fmaxf(m4[i], sv); l4[i] = l4[i] * expf(m4[i] - mn) + expf(sv - mn); m4[i] = mn; }
-        if (a < R && b == (a < B ? a + B : a - B)) pos_s[a] = sv;
+        if (a >= 0 && b == (a < B ? a + B : a - B)) pos_s[a] = sv;
       }
     }
   }
@@ -289,14 +295,15 @@ __global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ 
   if (!is_last) return;
   __threadfence();
   for (int rr = w; rr < NTX_RA2; rr += 8) {                  // last split of the row block: merge the splits' partials
-    const int a = a0 + rr;
-    if (a >= R) continue;
+    const int a = a_of[rr];
+    if (a < 0) continue;
+    const int64_t lr = a0 + rr;                              // the partials are indexed by the LOCAL row
     float m = -INFINITY;
-    for (int sidx = lane; sidx < n_splits; sidx += 32) m = fmaxf(m, __ldcg(part + ((int64_t)a * n_splits + sidx) * 2));
+    for (int sidx = lane; sidx < n_splits; sidx += 32) m = fmaxf(m, __ldcg(part + (lr * n_splits + sidx) * 2));
     m = warp_max(m);
     float l = 0.f;
     for (int sidx = lane; sidx < n_splits; sidx += 32) {
-      const float pm = __ldcg(part + ((int64_t)a * n_splits + sidx) * 2), pl = __ldcg(part + ((int64_t)a * n_splits + sidx) * 2 + 1);
+      const float pm = __ldcg(part + (lr * n_splits + sidx) * 2), pl = __ldcg(part + (lr * n_splits + sidx) * 2 + 1);
       if (pl > 0.f) l += pl * expf(pm - m);
     }
     l = warp_sum(l);
@@ -314,8 +321,8 @@ __global__ void __launch_bounds__(256) ntx_lse_kernel(const float* __restrict__ 
   __syncthreads();
   if (is_last) {                                             // the last row block sums the loss terms in index order
     __threadfence();
-    float sacc = 0.f;
-    for (int i = t; i < R; i += 256) sacc += __ldcg(row_loss + i);
+    float sacc = 0.f;                                        // nb < B: this slab's share of the loss (the caller adds the shares)
+    for (int r = t; r < 2 * nb; r += 256) sacc += __ldcg(row_loss + (r < nb ? sb0 + r : B + sb0 + (r - nb)));
     sacc = block_sum(sacc, red);
     if (t == 0) loss[0] = sacc / (float)R;
   }
@@ -465,8 +472,8 @@ int64_t murcl_ntxent_workspace(int B, int d) {
   const int64_t R = 2 * (int64_t)B;
   const int64_t legacy = R * d /*zn*/ + 4 * R /*inv_norm, lse, row_loss, pad*/ + R * R /*gram / coefficients*/ + R * d /*C zn*/ +
                          32 * R * d /*split-K scratch of the C zn product*/;
-  const int64_t fused = 4 * R /*inv_norm, lse, row_loss, pos_s*/ + (R + 16) * ((R + 63) / 64) * 2 /*(max, sum-exp) partials*/ +
-                        2 * (R / 16 + 2) + 16 /*tickets*/ + R * d /*dzn accumulator*/;
+  const int64_t fused = 4 * R /*inv_norm, lse, row_loss, pad*/ + R /*pos_s*/ + (R + 16) * ((R + 63) / 64) * 2 /*(max, sum-exp) partials*/ +
+                        2 * (R / 16 + 2) + 64 /*tickets, alignment*/ + R * d /*dzn accumulator*/;
   return ntx_fused_ok(d) ? fused : legacy;
 }
 
@@ -515,6 +522,86 @@ static int ntxent_legacy(const float* z, int B, int d, float temperature, float*
   return check_launch("ntx_finish_kernel");
 }
 
+namespace {
+
+struct NtxPlan {
+  int R, n_tiles;
+  float inv_tau;
+  static void split(int blocks, int n_tiles, int& splits, int& tps) {     // ~2 CTAs per SM, every split >= 1 tile
+    splits = ceil_div(2 * sm_count(), blocks > 0 ? blocks : 1);
+    if (splits > n_tiles) splits = n_tiles;
+    if (splits < 1) splits = 1;
+    tps = ceil_div(n_tiles, splits);
+    splits = ceil_div(n_tiles, tps);
+  }
+};
+
+int ntx_configure() {
+  static PerDeviceOnce configured;
+  if (const int slot = configured.pending(); slot >= 0) {
+    MURCL_CUDA(cudaFuncSetAttribute(ntx_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured.mark(slot);
+  }
+  return MURCL_OK;
+}
+
+// Log-sum-exp pass over the rows of the samples [b0, b0 + nb) of both views (nb == B: all rows): inv_norm / lse / row_loss
+// of THOSE rows (global row index), their loss share, cos of those samples.  scratch: pos_s [R] | part | tickets.
+int ntx_lse_pass(const float* z, int B, int d, float inv_tau, int b0, int nb, float* inv_norm, float* lse, float* row_loss,
+                 float* loss, float* cos_pair, float* scratch, cudaStream_t st) {
+  const int R = 2 * B, n_tiles = ceil_div(R, NTX_TB);
+  const int rb = ceil_div(2 * nb, NTX_RA2);
+  int splits, tps;
+  NtxPlan::split(rb, n_tiles, splits, tps);
+  float* pos_s = scratch;
+  float* part = pos_s + R;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(part + (int64_t)rb * NTX_RA2 * n_tiles * 2);
+  const int64_t n_tickets = 2 + (int64_t)rb;
+  MURCL_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned int) * (size_t)n_tickets, st));
+  int rc = ntx_configure();
+  if (rc != MURCL_OK) return rc;
+  const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_TB + 2 * NTX_RA2 * NTX_TB + NTX_RA2);
+  ntx_lse_kernel<<<dim3(rb, splits), 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps, inv_norm, lse, row_loss, cos_pair, part, pos_s,
+                                                     loss, tickets);
+  return check_launch("ntx_lse_kernel");
+}
+
+// Gradient rows of the samples [b0, b0 + nb) of both views, given inv_norm / lse of ALL rows.  scratch: tickets | accumulator.
+int ntx_grad_pass(const float* z, int B, int d, float inv_tau, int b0, int nb, const float* inv_norm, const float* lse, float* dz,
+                  float* scratch, cudaStream_t st) {
+  const int R = 2 * B, n_tiles = ceil_div(R, NTX_TB);
+  const int row_blocks = ceil_div(2 * nb, NTX_RA2);
+  int splits, tps;
+  NtxPlan::split(row_blocks, n_tiles, splits, tps);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(scratch);
+  const int64_t n_tickets = ((int64_t)row_blocks + 3) / 4 * 4;
+  float* acc_ws = scratch + n_tickets;                                    // [2 nb, d], 16-byte aligned
+  // one memset node clears the tickets and, right behind them, the gradient accumulator
+  MURCL_CUDA(cudaMemsetAsync(tickets, 0, sizeof(float) * ((size_t)n_tickets + (size_t)2 * nb * d), st));
+  int rc = ntx_configure();
+  if (rc != MURCL_OK) return rc;
+  const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_RA2 * (NTX_TB + 1) + NTX_TB + NTX_RA2);
+  const dim3 grid(row_blocks, splits);
+  if (d <= 128)
+    ntx_grad_kernel<1><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps, inv_norm, lse, acc_ws, tickets, dz);
+  else
+    ntx_grad_kernel<2><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps, inv_norm, lse, acc_ws, tickets, dz);
+  return check_launch("ntx_grad_kernel");
+}
+
+int64_t ntx_lse_scratch(int R, int rows) {            // pos_s | part | tickets (floats)
+  const int64_t rb = (rows + NTX_RA2 - 1) / NTX_RA2;
+  return R + rb * NTX_RA2 * ((R + NTX_TB - 1) / NTX_TB) * 2 + rb + 2 + 8;
+}
+int64_t ntx_grad_scratch(int rows, int d) {           // tickets | accumulator (floats)
+  const int64_t rb = (rows + NTX_RA2 - 1) / NTX_RA2;
+  return (rb + 3) / 4 * 4 + (int64_t)rows * d + 8;
+}
+
+}  // namespace
+
 int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, int b0, int nb, float* loss, float* dz,
                               float* cos_pair, float* workspace, void* stream) {
   MURCL_REQUIRE(z && loss && workspace, "ntxent: null pointer");
@@ -528,53 +615,43 @@ int murcl_ntxent_fwd_bwd_slab(const float* z, int B, int d, float temperature, i
   }
   const int R = 2 * B;
   const float inv_tau = 1.f / temperature;
-  const int n_tiles = ceil_div(R, NTX_TB);
-  const int rb_all = ceil_div(R, NTX_RA2);                              // row blocks of the log-sum-exp pass (all rows)
-  const int row_blocks = ceil_div(2 * nb, NTX_RA2);                      // row blocks of the gradient pass (the slab)
-  auto plan = [&](int blocks, int& splits, int& tps) {                   // ~2 CTAs per SM, every split >= 1 tile
-    splits = ceil_div(2 * sm_count(), blocks > 0 ? blocks : 1);
-    if (splits > n_tiles) splits = n_tiles;
-    if (splits < 1) splits = 1;
-    tps = ceil_div(n_tiles, splits);
-    splits = ceil_div(n_tiles, tps);
-  };
-  int splits1, tps1, splits2, tps2;
-  plan(rb_all, splits1, tps1);
-  plan(row_blocks, splits2, tps2);
-  // workspace: inv_norm [R] | lse [R] | row_loss [R] | pos_s [R] | part [rb_all*16][n_tiles][2] | tickets | accumulator
+  // workspace: inv_norm [R] | lse [R] | row_loss [R] | pad [R] | lse-pass scratch | gradient-pass scratch
   float* inv_norm = workspace;
   float* lse = inv_norm + R;
   float* row_loss = lse + R;
-  float* pos_s = row_loss + R;
-  float* part = pos_s + R;
-  const int64_t n_tickets = 2 + (int64_t)rb_all + row_blocks;
-  unsigned int* tickets = reinterpret_cast<unsigned int*>(part + (int64_t)rb_all * NTX_RA2 * n_tiles * 2);
-  float* acc_ws = reinterpret_cast<float*>(tickets) + ((n_tickets + 3) / 4) * 4;   // [2 nb, d], 16-byte aligned
-  const bool want_grad = dz != nullptr && nb > 0;
-  // one memset node clears the tickets and, right behind them, the gradient accumulator
-  MURCL_CUDA(cudaMemsetAsync(tickets, 0, sizeof(float) * ((size_t)((n_tickets + 3) / 4) * 4 + (want_grad ? (size_t)2 * nb * d : 0)), st));
-  {
-    const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_TB + 2 * NTX_RA2 * NTX_TB + NTX_RA2);
-    static PerDeviceOnce configured;
-    if (const int slot = configured.pending(); slot >= 0) {
-      MURCL_CUDA(cudaFuncSetAttribute(ntx_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      MURCL_CUDA(cudaFuncSetAttribute(ntx_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      configured.mark(slot);
-    }
-    ntx_lse_kernel<<<dim3(rb_all, splits1), 256, smem, st>>>(z, B, d, inv_tau, tps1, inv_norm, lse, row_loss, cos_pair, part, pos_s,
-                                                            loss, tickets);
-    int rc = check_launch("ntx_lse_kernel");
-    if (rc != MURCL_OK || !want_grad) return rc;
-  }
-  const size_t smem = sizeof(float) * (size_t)(NTX_RA2 * d + NTX_TB * (d + 4) + NTX_RA2 * (NTX_TB + 1) + NTX_TB + NTX_RA2);
-  const dim3 grid(row_blocks, splits2);
-  unsigned int* tickets2 = tickets + 1 + rb_all;
-  if (d <= 128)
-    ntx_grad_kernel<1><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps2, inv_norm, lse, acc_ws, tickets2, dz);
-  else
-    ntx_grad_kernel<2><<<grid, 256, smem, st>>>(z, B, d, inv_tau, b0, nb, tps2, inv_norm, lse, acc_ws, tickets2, dz);
-  return check_launch("ntx_grad_kernel");
+  float* lse_scratch = row_loss + 2 * R;
+  float* grad_scratch = lse_scratch + (ntx_lse_scratch(R, R) + 3) / 4 * 4;
+  int rc = ntx_lse_pass(z, B, d, inv_tau, 0, B, inv_norm, lse, row_loss, loss, cos_pair, lse_scratch, st);   // all rows
+  if (rc != MURCL_OK || dz == nullptr || nb == 0) return rc;
+  return ntx_grad_pass(z, B, d, inv_tau, b0, nb, inv_norm, lse, dz, grad_scratch, st);
+}
+
+int murcl_ntxent_lse_slab(const float* z, int B, int d, float temperature, int b0, int nb, float* inv_norm, float* lse,
+                          float* loss_share, float* cos_pair, float* workspace, void* stream) {
+  MURCL_REQUIRE(z && inv_norm && lse && loss_share && workspace, "ntxent_lse_slab: null pointer");
+  MURCL_REQUIRE(B > 0 && B <= 16384 && d > 0 && temperature > 0.f, "ntxent_lse_slab: bad B=%d d=%d tau=%g", B, d, (double)temperature);
+  MURCL_REQUIRE(b0 >= 0 && nb > 0 && b0 + nb <= B, "ntxent_lse_slab: slab [%d, %d) outside the batch of %d", b0, b0 + nb, B);
+  MURCL_REQUIRE(ntx_fused_ok(d) && !(reinterpret_cast<uintptr_t>(z) & 15), "ntxent_lse_slab: needs d %% 4 == 0, d <= %d, 16-byte aligned z",
+                NTX_MAXD);
+  const int R = 2 * B;
+  float* row_loss = workspace;                                             // [R] (only the slab's rows are written and read)
+  return ntx_lse_pass(z, B, d, 1.f / temperature, b0, nb, inv_norm, lse, row_loss, loss_share, cos_pair, workspace + R, as_stream(stream));
+}
+
+int murcl_ntxent_grad_slab(const float* z, int B, int d, float temperature, int b0, int nb, const float* inv_norm, const float* lse,
+                           float* dz, float* workspace, void* stream) {
+  MURCL_REQUIRE(z && inv_norm && lse && dz && workspace, "ntxent_grad_slab: null pointer");
+  MURCL_REQUIRE(B > 0 && B <= 16384 && d > 0 && temperature > 0.f, "ntxent_grad_slab: bad B=%d d=%d tau=%g", B, d, (double)temperature);
+  MURCL_REQUIRE(b0 >= 0 && nb > 0 && b0 + nb <= B, "ntxent_grad_slab: slab [%d, %d) outside the batch of %d", b0, b0 + nb, B);
+  MURCL_REQUIRE(ntx_fused_ok(d) && !(reinterpret_cast<uintptr_t>(z) & 15) && !(reinterpret_cast<uintptr_t>(workspace) & 15),
+                "ntxent_grad_slab: needs d %% 4 == 0, d <= %d, 16-byte aligned z and workspace", NTX_MAXD);
+  return ntx_grad_pass(z, B, d, 1.f / temperature, b0, nb, inv_norm, lse, dz, workspace, as_stream(stream));
+}
+
+int64_t murcl_ntxent_slab_workspace(int B, int d, int nb) {
+  const int64_t R = 2 * (int64_t)B;
+  const int64_t a = R + ntx_lse_scratch((int)R, 2 * nb), b = ntx_grad_scratch(2 * nb, d);
+  return ((a > b ? a : b) + 3) / 4 * 4;
 }
 
 int murcl_ntxent_fwd_bwd(const float* z, int B, int d, float temperature, float* loss, float* dz, float* cos_pair,

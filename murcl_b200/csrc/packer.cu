@@ -151,15 +151,22 @@ __global__ void __launch_bounds__(512) pack_select_kernel(const int32_t* __restr
 // TI = storage of the CSR feature buffer (fp32 as the reference holds it, or bf16 for the bf16 mode's halved
 // footprint / H2D volume), TO = storage of the packed batch.  The mix is always two rounded fp32 products and
 // one rounded fp32 add (datasets.py:268-270), then one rounding to TO.
+// `slot_order` (may be null): the order in which the grid walks the output slots.  With mixup every slot's source rows are
+// read twice - as its own and as its partner's - and with the slots in plain order the second read comes ~S/3 slots (tens of
+// MB) later: mostly an L2 miss.  Walking the slots along the CYCLES of the permutation (murcl_perm_cycle_order) makes the
+// partner of one slot the very next slot, so every source row comes from DRAM once.  Where a row is written does not change.
 template <typename TI, typename TO, bool MIX>
 __global__ void __launch_bounds__(256) pack_gather_kernel(const TI* __restrict__ feats, int D,
                                                           const int32_t* __restrict__ sel_idx, int64_t n_out_rows,
                                                           int FS, const float* __restrict__ lam,
-                                                          const int32_t* __restrict__ perm, TO* __restrict__ out) {
+                                                          const int32_t* __restrict__ perm,
+                                                          const int32_t* __restrict__ slot_order, TO* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_out_rows) return;
-  const int slot = (int)(row / FS), r = (int)(row % FS);
+  const int64_t vrow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (vrow >= n_out_rows) return;
+  const int pos = (int)(vrow / FS), r = (int)(vrow % FS);
+  const int slot = slot_order != nullptr ? slot_order[pos] : pos;
+  const int64_t row = (int64_t)slot * FS + r;
   const int32_t ia = sel_idx[row];
   const TI* pa = (ia >= 0) ? feats + (int64_t)ia * D : nullptr;
   const TI* pb = nullptr;
@@ -195,12 +202,39 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const TI* __restrict__
 
 template <typename TI, typename TO>
 static void launch_gather(const void* feats, int D, const int32_t* sel_idx, int64_t rows, int FS, const float* lam,
-                          const int32_t* perm, void* out, cudaStream_t st) {
+                          const int32_t* perm, const int32_t* order, void* out, cudaStream_t st) {
   const int grid = ceil_div(rows, 8);
   if (lam != nullptr)
-    pack_gather_kernel<TI, TO, true><<<grid, 256, 0, st>>>((const TI*)feats, D, sel_idx, rows, FS, lam, perm, (TO*)out);
+    pack_gather_kernel<TI, TO, true><<<grid, 256, 0, st>>>((const TI*)feats, D, sel_idx, rows, FS, lam, perm, order, (TO*)out);
   else
-    pack_gather_kernel<TI, TO, false><<<grid, 256, 0, st>>>((const TI*)feats, D, sel_idx, rows, FS, lam, perm, (TO*)out);
+    pack_gather_kernel<TI, TO, false><<<grid, 256, 0, st>>>((const TI*)feats, D, sel_idx, rows, FS, lam, perm, order, (TO*)out);
+}
+
+// One CTA per permutation of S slots: lane 0 walks the cycles (start at the lowest unvisited slot, follow perm until the
+// cycle closes) and appends every slot once.  A malformed `perm` (not a bijection, entries out of range) still yields a
+// valid ordering of all S slots - only the locality is lost.
+__global__ void __launch_bounds__(256) perm_cycle_order_kernel(const int32_t* __restrict__ perm, int S, int32_t* __restrict__ order) {
+  extern __shared__ int32_t sm[];
+  int32_t* p = sm;
+  unsigned char* seen = reinterpret_cast<unsigned char*>(sm + S);
+  const int32_t* src = perm + (int64_t)blockIdx.x * S;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    p[i] = src[i];
+    seen[i] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t* dst = order + (int64_t)blockIdx.x * S;
+    int n = 0;
+    for (int s0 = 0; s0 < S; ++s0) {
+      int cur = s0;
+      while (cur >= 0 && cur < S && !seen[cur]) {
+        seen[cur] = 1;
+        dst[n++] = cur;
+        cur = p[cur];
+      }
+    }
+  }
 }
 
 }  // namespace murcl
@@ -233,6 +267,20 @@ int murcl_pack_select(const int32_t* patch_cluster, const int32_t* patch_rank, c
 
 int murcl_pack_gather(const void* feats, int feat_dtype, int D, const int32_t* sel_idx, int S, int FS, const float* lam,
                       const int32_t* perm, void* out, int out_dtype, void* stream) {
+  return murcl_pack_gather_ordered(feats, feat_dtype, D, sel_idx, S, FS, lam, perm, nullptr, out, out_dtype, stream);
+}
+
+int murcl_perm_cycle_order(const int32_t* perm, int n_perm, int S, int32_t* order, void* stream) {
+  MURCL_REQUIRE(perm && order, "perm_cycle_order: null pointer");
+  MURCL_REQUIRE(n_perm >= 0 && S > 0 && S <= 8192, "perm_cycle_order: n_perm=%d S=%d out of range", n_perm, S);
+  if (n_perm == 0) return MURCL_OK;
+  const size_t smem = sizeof(int32_t) * (size_t)S + ((size_t)S + 3) / 4 * 4;
+  perm_cycle_order_kernel<<<n_perm, 256, smem, as_stream(stream)>>>(perm, S, order);
+  return check_launch("perm_cycle_order_kernel");
+}
+
+int murcl_pack_gather_ordered(const void* feats, int feat_dtype, int D, const int32_t* sel_idx, int S, int FS, const float* lam,
+                              const int32_t* perm, const int32_t* slot_order, void* out, int out_dtype, void* stream) {
   MURCL_REQUIRE(feats && sel_idx && out, "pack_gather: null pointer");
   MURCL_REQUIRE(S >= 0 && FS > 0 && D > 0, "pack_gather: S=%d FS=%d D=%d out of range", S, FS, D);
   MURCL_REQUIRE((lam == nullptr) == (perm == nullptr), "pack_gather: lam and perm must be given together");
@@ -242,11 +290,11 @@ int murcl_pack_gather(const void* feats, int feat_dtype, int D, const int32_t* s
   const int64_t rows = (int64_t)S * FS;
   cudaStream_t st = as_stream(stream);
   if (feat_dtype == MURCL_F32) {
-    if (out_dtype == MURCL_F32) launch_gather<float, float>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
-    else launch_gather<float, __nv_bfloat16>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
+    if (out_dtype == MURCL_F32) launch_gather<float, float>(feats, D, sel_idx, rows, FS, lam, perm, slot_order, out, st);
+    else launch_gather<float, __nv_bfloat16>(feats, D, sel_idx, rows, FS, lam, perm, slot_order, out, st);
   } else {
-    if (out_dtype == MURCL_F32) launch_gather<__nv_bfloat16, float>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
-    else launch_gather<__nv_bfloat16, __nv_bfloat16>(feats, D, sel_idx, rows, FS, lam, perm, out, st);
+    if (out_dtype == MURCL_F32) launch_gather<__nv_bfloat16, float>(feats, D, sel_idx, rows, FS, lam, perm, slot_order, out, st);
+    else launch_gather<__nv_bfloat16, __nv_bfloat16>(feats, D, sel_idx, rows, FS, lam, perm, slot_order, out, st);
   }
   return check_launch("pack_gather_kernel");
 }

@@ -632,6 +632,37 @@ def ntxent_raw(z: torch.Tensor, B: int, temperature: float, want_grad=True, slab
     return loss, dz, cos
 
 
+def ntxent_lse_slab(z: torch.Tensor, B: int, temperature: float, slab):
+    """Log-sum-exp pass over the rows of the samples ``slab = (b0, nb)`` of both views only (murcl_ntxent_lse_slab):
+    ``(inv_norm [2B], lse [2B], loss_share [1], cos [B])`` - only the slab's entries of the three vectors are defined."""
+    _chk(z, "ntxent.z", torch.float32)
+    R, d = z.shape
+    b0, nb = int(slab[0]), int(slab[1])
+    inv_norm = torch.empty((R,), device=z.device, dtype=torch.float32)
+    lse = torch.empty((R,), device=z.device, dtype=torch.float32)
+    share = torch.empty((1,), device=z.device, dtype=torch.float32)
+    cos = torch.empty((B,), device=z.device, dtype=torch.float32)
+    ws = torch.empty((int(_lib.load().murcl_ntxent_slab_workspace(B, d, nb)),), device=z.device, dtype=torch.float32)
+    check(_lib.load().murcl_ntxent_lse_slab(_p(z), B, d, float(temperature), b0, nb, _p(inv_norm), _p(lse), _p(share), _p(cos),
+                                            _p(ws), _s()), "murcl_ntxent_lse_slab")
+    return inv_norm, lse, share, cos
+
+
+def ntxent_grad_slab(z: torch.Tensor, B: int, temperature: float, slab, inv_norm: torch.Tensor, lse: torch.Tensor) -> torch.Tensor:
+    """Gradient rows of the samples ``slab`` of both views from the complete ``inv_norm`` / ``lse`` (murcl_ntxent_grad_slab);
+    the other rows of the returned ``[2B, d]`` tensor are zero."""
+    _chk(z, "ntxent.z", torch.float32); _chk(inv_norm, "ntxent.inv_norm", torch.float32); _chk(lse, "ntxent.lse", torch.float32)
+    R, d = z.shape
+    b0, nb = int(slab[0]), int(slab[1])
+    if inv_norm.numel() != R or lse.numel() != R:
+        raise MurclError("ntxent_grad_slab: inv_norm / lse must have one entry per row of z")
+    dz = torch.zeros_like(z)
+    ws = torch.empty((int(_lib.load().murcl_ntxent_slab_workspace(B, d, nb)),), device=z.device, dtype=torch.float32)
+    check(_lib.load().murcl_ntxent_grad_slab(_p(z), B, d, float(temperature), b0, nb, _p(inv_norm), _p(lse), _p(dz), _p(ws), _s()),
+          "murcl_ntxent_grad_slab")
+    return dz
+
+
 class _NTXent(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z_i, z_j, temperature, slab):

@@ -33,7 +33,7 @@ def draw_patch_step(B: int, K: int, alpha: float, device, actions: Optional[List
 
 def draw_step_batched(T: int, B: int, K: int, alpha: float, device, random_actions: bool):
     """Every random draw of one optimiser step in a handful of launches: ``(actions [T or 1, 2B, K], lam [T, 2B],
-    perm [T, 2B] int32)`` - rows ``[0, B)`` of a patch-step belong to view 0, ``[B, 2B)`` to view 1, each view's
+    perm [T, 2B] int32, order [T, 2B] int32)`` - rows ``[0, B)`` of a patch-step belong to view 0, ``[B, 2B)`` to view 1, each view's
     permutation stays inside its own half (``pack_views``).  Same distributions as ``draw_patch_step`` (uniform actions,
     ``lam ~ alpha + U(0,1)(1 - alpha)``, uniformly random permutations - the arg-sort of i.i.d. uniform keys), but the
     draws do not depend on anything the step computes, so they are issued once: per-step ``rand`` / ``randperm`` / ``cat``
@@ -43,7 +43,9 @@ def draw_step_batched(T: int, B: int, K: int, alpha: float, device, random_actio
     perm = torch.rand((T, 2, B), device=device).argsort(dim=2).to(torch.int32)
     perm[:, 1] += B
     act = torch.rand((T if random_actions else 1, 2 * B, K), device=device)
-    return act, lam, perm.view(T, 2 * B)
+    perm = perm.view(T, 2 * B)
+    from .csr import perm_cycle_order
+    return act, lam, perm, perm_cycle_order(perm)       # + the gathers' slot walk order (csr.gather_rows_padded), all T at once
 
 
 def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dtype, slot_bag=None) -> torch.Tensor:
@@ -151,7 +153,7 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
                     actions = [ppo.select_action(s, m, restart_batch=(t == 1)) for s, m in zip(states, memories)]
             if pre is not None:
                 act_all = pre[0][t if stage == 1 else 0] if actions is None else torch.cat(list(actions), 0)
-                x_all = store.pack(act_all, feat_size, pre[1][t], pre[2][t], dt, slot_bag)
+                x_all = store.pack(act_all, feat_size, pre[1][t], pre[2][t], dt, slot_bag, order=pre[3][t])
             else:
                 if lams is None:
                     draw = draw_patch_step(B, K, alpha, dev, actions)

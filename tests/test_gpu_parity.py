@@ -837,6 +837,78 @@ def test_pretrain_step_golden(golden):
     assert n >= 10
 
 
+@pytest.mark.parametrize("world,b,d", [(4, 128, 128), (8, 16, 64), (3, 20, 256)])
+def test_ntxent_own_rows_passes_match_the_full_kernel(world, b, d):
+    """murcl_ntxent_lse_slab + (exchange of the per-row statistics) + murcl_ntxent_grad_slab - what every rank runs from 4
+    ranks on - reproduce the all-rows kernel (utils/losses.py:24-41): loss = sum of the ranks' shares, the same gradient
+    rows, the same cosines; and both agree with the fp64 oracle."""
+    from murcl_b200 import ops
+    Bg = world * b
+    z = torch.randn(2 * Bg, d, generator=synth.gen(77)).to(DEV)
+    loss_full, dz_full, cos_full = ops.ntxent_raw(z, Bg, 0.7, True)
+    lse = torch.empty(2 * Bg, device=DEV); inv = torch.empty(2 * Bg, device=DEV)
+    shares, cos = [], torch.empty(Bg, device=DEV)
+    for r in range(world):
+        inv_r, lse_r, share, cos_r = ops.ntxent_lse_slab(z, Bg, 0.7, (r * b, b))
+        for sl in (slice(r * b, (r + 1) * b), slice(Bg + r * b, Bg + (r + 1) * b)):
+            lse[sl], inv[sl] = lse_r[sl], inv_r[sl]
+        cos[r * b:(r + 1) * b] = cos_r[r * b:(r + 1) * b]
+        shares.append(share)
+    loss = torch.stack(shares).sum()
+    assert_close(loss, loss_full.reshape(()), 2e-6, "loss from the ranks' shares")
+    assert_close(cos, cos_full, 1e-6, "cosines")
+    dz = torch.zeros_like(z)
+    for r in range(world):
+        dz_r = ops.ntxent_grad_slab(z, Bg, 0.7, (r * b, b), inv, lse)
+        rows = torch.cat([torch.arange(r * b, (r + 1) * b), torch.arange(Bg + r * b, Bg + (r + 1) * b)]).to(DEV)
+        other = torch.ones(2 * Bg, dtype=torch.bool, device=DEV); other[rows] = False
+        assert float(dz_r[other].abs().max()) == 0.0
+        dz[rows] = dz_r[rows]
+    assert_close(dz, dz_full, 2e-6, "gradient rows", floor=1e-9)
+    z64 = z.double().cpu().requires_grad_(True)
+    ref = O.nt_xent(z64[:Bg], z64[Bg:], 0.7)
+    ref.backward()
+    assert_close(loss, ref.float(), FP32_OUT, "loss vs oracle")
+    assert_close(dz, z64.grad.float(), FP32_GRAD, "gradient vs oracle", floor=1e-9)
+
+
+def test_gather_slot_order_never_changes_the_result():
+    """murcl_perm_cycle_order lists the slots cycle by cycle (partner after partner); murcl_pack_gather_ordered walks them in
+    that order.  The packed batch is bit-identical to the plain-order gather (datasets.py:263-308), for cycle orders, for
+    arbitrary orders and for a malformed permutation."""
+    from murcl_b200.csr import BagStore, perm_cycle_order
+    g = synth.gen(31)
+    sizes = [int(v) for v in torch.randint(40, 900, (24,), generator=g)]
+    feats, clusters, _ = synth.make_bags(sizes, 64, 5, seed=32)
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    S = 48
+    slot_bag = torch.arange(24, dtype=torch.int32, device=DEV).repeat(2)
+    act = torch.rand(S, 5, generator=g).to(DEV)
+    lam = (0.9 + 0.1 * torch.rand(S, generator=g)).to(DEV)
+    perm = torch.cat([torch.randperm(24, generator=g), torch.randperm(24, generator=g) + 24]).to(DEV, torch.int32)
+    sel, _ = store.select(act, 128, slot_bag)
+    os.environ["MURCL_GATHER_ORDER"] = "0"
+    try:
+        plain = store.gather(sel, lam, perm, torch.float32)
+    finally:
+        os.environ.pop("MURCL_GATHER_ORDER")
+    order = perm_cycle_order(perm)
+    o = order.cpu().tolist()
+    p = perm.cpu().tolist()
+    assert sorted(o) == list(range(S))
+    follows = sum(1 for a, b in zip(o[:-1], o[1:]) if p[a] == b)
+    cycles = sum(1 for a, b in zip(o[:-1], o[1:]) if p[a] != b) + 1
+    assert follows + cycles == S                       # every step either follows the permutation or opens a new cycle
+    for od in (order, None, torch.randperm(S, generator=g).to(DEV, torch.int32)):
+        assert torch.equal(store.gather(sel, lam, perm, torch.float32, order=od), plain)
+    assert torch.equal(store.gather(sel, lam, perm, torch.bfloat16, order=order), plain.to(torch.bfloat16))
+    bad = perm.clone(); bad[3] = bad[4]; bad[7] = 1000                      # not a bijection, one entry out of range
+    ob = perm_cycle_order(bad)
+    assert sorted(ob.cpu().tolist()) == list(range(S))
+    batch = perm_cycle_order(torch.stack([perm, perm.flip(0).contiguous() * 0 + perm]))
+    assert torch.equal(batch[0], order) and torch.equal(batch[1], order)
+
+
 def test_batched_step_draws_are_the_reference_draws_in_one_go(golden, monkeypatch):
     """``rng="batched"``: every draw of the step issued up front (``draw_step_batched``).  The distributions are the
     reference's (datasets.py:266-267: lam in [alpha, 1), one permutation per view inside its own half) and the step
@@ -847,7 +919,8 @@ def test_batched_step_draws_are_the_reference_draws_in_one_go(golden, monkeypatc
     g = golden("pretrain_step")
     b, k, d, fs, T, L, D, hid, proj = g["cfg"].tolist()
     torch.manual_seed(5)
-    act, lam, perm = pretrain.draw_step_batched(T, b, k, 0.9, DEV, True)
+    act, lam, perm, order = pretrain.draw_step_batched(T, b, k, 0.9, DEV, True)
+    assert order.shape == perm.shape and order.dtype == torch.int32
     assert act.shape == (T, 2 * b, k) and lam.shape == (T, 2 * b) and perm.shape == (T, 2 * b) and perm.dtype == torch.int32
     assert float(lam.min()) >= 0.9 and float(lam.max()) < 1.0 and float(act.min()) >= 0.0 and float(act.max()) < 1.0
     ident = torch.arange(b, device=DEV, dtype=torch.int32)
@@ -863,7 +936,7 @@ def test_batched_step_draws_are_the_reference_draws_in_one_go(golden, monkeypatc
         model = cl.CL(enc, projection_dim=proj, n_features=L)
         fc = _load(rlmil.Full_layer(L, hid, True, proj), synth.full_layer_state(L, hid, proj, seed=93))
         if mode == "batched":
-            monkeypatch.setattr(pretrain, "draw_step_batched", lambda *a, **kw: (act, lam, perm))
+            monkeypatch.setattr(pretrain, "draw_step_batched", lambda *a, **kw: (act, lam, perm, order))
             loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=0.9, precision="fp32", rng="batched")
         else:
             draws = [([act[t, :b], act[t, b:]], [lam[t, :b].view(b, 1), lam[t, b:].view(b, 1)],
