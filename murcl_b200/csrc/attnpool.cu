@@ -25,6 +25,8 @@
 // and h a second time from HBM.
 //
 // Roofline: HBM.  Algorithmic bytes per row: L*2 (h) + NC*2 (uv, when saved) + 8 (s, p).  FLOPs per row: 2*L*NC + 2*L.
+// (Tried and dropped: an L2 prefetch of the NEXT tile's rows by the producer, which bought the GEMMs 3-7 %, costs this
+// kernel 20 % - 104 -> 125 us - because it evicts the current tile's rows before the pooling pass re-reads them.)
 #include <cuda.h>
 
 #include "common.cuh"

@@ -84,6 +84,7 @@ struct Params {
   // the tile `l2pf` tiles ahead into L2, streaming kernels the operand k-blocks `l2pf` k-blocks ahead.  The shared-memory
   // ring alone looks ahead ~1 us of MMA time (4 x 16 KB of A beside the resident B tile), less than the loaded HBM latency.
   int l2pf;
+  int atomic_out;     // EPI_SPLIT: add the partial tile to C with vector atomics (red.global.add.v4.f32) instead of storing it
 };
 
 // CG = cta_group: 1 = one SM per 128 x BN tile; 2 = a CTA pair shares a 256 x BN tile (each CTA holds its 128 rows of A
@@ -470,11 +471,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int col0 = n0 + c0;
           if (row < p.M && col0 < p.N) {
             float* dst = static_cast<float*>(p.C) + (int64_t)sp * p.split_stride + row * p.ldc + col0;
+            if (p.atomic_out) {                            // split_stride == 0: every split adds into the same [M, N] result
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              if (col0 + i < p.N)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+              for (int i = 0; i < 32; i += 4)
+                if (col0 + i < p.N)
+                  atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                            __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                if (col0 + i < p.N)
+                  *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                    __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            }
           }
         }
       } else {
@@ -940,6 +949,20 @@ int tc_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, int 
                    : launch<128, false, true, EPI_DGRAD, __nv_bfloat16>(ma, mb, mc, p, st);
 }
 
+// The splits add their partial tiles straight into dw with vector atomics (red.global.add.v4.f32: 18-74 adds per address,
+// served by the L2 atomic units while the other CTAs still compute) - no workspace round trip and no split-K reduce launch
+// (measured: [512 x 512] 134 -> 130 us, the attention projection's [128 x 512] with 74 splits 81 -> 61 us; 0.22 ms per
+// step).  The price is a summation order that varies from run to run, as for the bias / pooling gradients already;
+// MURCL_WGRAD_ATOMIC=0 restores the workspace + fixed-order reduce.
+static bool wgrad_atomic() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MURCL_WGRAD_ATOMIC");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // The weight gradient is operand-load bound with one CTA per 128 x 256 tile (48 KB of operands per 512 tensor-pipe clocks):
 // a CTA pair on a 256 x 256 tile pulls 32 KB per CTA for the same MMA work and fits a deeper ring.
 static bool wgrad_pair(int64_t M, int N, int K) {
@@ -955,7 +978,10 @@ static void wgrad_plan(int64_t M, int N, int K, int& BN, int& splits, int64_t& k
   BN = (K % 256 == 0) ? 256 : 128;
   const bool pair = wgrad_pair(M, N, K);
   const int tiles = ceil_div(N, pair ? 2 * BLOCK_M : BLOCK_M) * ceil_div(K, BN);
-  splits = (pair ? sm_count() / 2 : sm_count()) / tiles;           // one wave
+  const int slots = pair ? sm_count() / 2 : sm_count();
+  splits = slots / tiles;                                          // one wave
+  // (cutting the reduction finer so that every CTA takes two work items - 4 x 37 = 148 = 2 x 74 slots instead of 72 busy pairs -
+  //  was measured slower: 10.36 -> 10.65 ms per step)
   if (splits < 1) splits = 1;
   const int64_t kb_total = (M + BLOCK_K - 1) / BLOCK_K;
   if (splits > kb_total) splits = (int)kb_total;
@@ -995,6 +1021,11 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
   p.M = N; p.N = K; p.K = M; p.ldc = K; p.C = workspace;
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  const bool atomic = wgrad_atomic() && splits > 1 && K % 4 == 0;
+  if (atomic) {
+    if (!accumulate) MURCL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    p.C = dw; p.split_stride = 0; p.atomic_out = 1;
+  }
   if (wgrad_pair(M, N, K)) {
     p.m_tiles = ceil_div(N, 2 * BLOCK_M);
     rc = launch<256, true, true, EPI_SPLIT, float, 2>(ma, mb, ma, p, st);
@@ -1002,7 +1033,7 @@ int tc_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t M, in
     rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
                    : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
   }
-  if (rc != MURCL_OK) return rc;
+  if (rc != MURCL_OK || atomic) return rc;
   const int64_t n = (int64_t)N * K;
   return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);
 }
@@ -1129,6 +1160,11 @@ int tc_split_bwd_weight(const void* dyp, const void* xp, float* dw, int64_t M, i
   p.splits = splits; p.k_chunk = k_chunk; p.split_stride = (int64_t)N * K;
   p.m_tiles = ceil_div(N, BLOCK_M); p.n_tiles = ceil_div(K, BN);
   split_terms(p, planes, pr, pr);
+  const bool atomic = wgrad_atomic() && splits > 1 && K % 4 == 0;
+  if (atomic) {
+    if (!accumulate) MURCL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    p.C = dw; p.split_stride = 0; p.atomic_out = 1;
+  }
   if (wgrad_pair(M, N, K)) {
     p.m_tiles = ceil_div(N, 2 * BLOCK_M);
     rc = launch<256, true, true, EPI_SPLIT, float, 2>(ma, mb, ma, p, st);
@@ -1136,7 +1172,7 @@ int tc_split_bwd_weight(const void* dyp, const void* xp, float* dw, int64_t M, i
     rc = BN == 256 ? launch<256, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
                    : launch<128, true, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
   }
-  if (rc != MURCL_OK) return rc;
+  if (rc != MURCL_OK || atomic) return rc;
   const int64_t n = (int64_t)N * K;
   return launch_splitk_reduce(workspace, splits, n, dw, n, st, accumulate);
 }
