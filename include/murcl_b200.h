@@ -115,6 +115,13 @@ int murcl_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t M, i
                            const int32_t* row_seg, float* col_sum, float out_scale, const uint64_t* relu_bits,
                            int dtype, int backend, void* stream);
 
+/* dx[M,K] (fp32) += dy[M,N] . w[N,K]: the plain input gradient ADDED to an existing fp32 buffer, with the reduction over N
+ * split across the GPU (vector atomics).  For batch-sized layers with a long reduction - the W_hh step of the GRU head's
+ * backward recurrence (rlmil.py:208-220 differentiated: M = 128, N = 3 x 1024) - where one launch of murcl_linear_bwd_input
+ * is a handful of CTAs.  bf16 operands; murcl_linear_bwd_input_accum_supported tells whether the shape is taken. */
+int murcl_linear_bwd_input_accum_supported(int64_t M, int N, int K, int dtype);
+int murcl_linear_bwd_input_accum(const void* dy, const void* w, float* dx, int64_t M, int N, int K, int dtype, void* stream);
+
 /* dw[N,K] (fp32) = dy[M,N]^T . x[M,K], db[N] (fp32, may be NULL) = column sums of dy.
  * `workspace` (fp32) must hold murcl_linear_bwd_weight_workspace(M,N,K) floats.  accumulate != 0 ADDS to the existing
  * contents of dw / db instead of overwriting them: the T x 2 bag passes of one optimiser step (train_MuRCL.py:291-295:

@@ -34,6 +34,8 @@ SIGNATURES = {
     "murcl_pack_gather_ordered": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _p]),
     "murcl_linear_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p, _p]),
     "murcl_linear_bwd_input": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _f, _p, _i, _i, _p]),
+    "murcl_linear_bwd_input_accum_supported": (_i, [_l, _i, _i, _i]),
+    "murcl_linear_bwd_input_accum": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
     "murcl_linear_bwd_weight_workspace": (_l, [_l, _i, _i]),
     "murcl_linear_bwd_weight": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _p, _i, _p]),
     "murcl_split_planes": (_i, [_p, _l, _i, _i, _l, _p, _p]),

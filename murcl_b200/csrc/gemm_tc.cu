@@ -963,6 +963,40 @@ static bool wgrad_atomic() {
   return v == 1;
 }
 
+// dx[M, K] (fp32) += dy[M, N] . w[N, K] with the reduction split across the whole GPU and the partial tiles added with vector
+// atomics.  For the batch-sized layers of the recurrence (M = 128 rows, reduction 3072): the plain input-gradient launch is 16
+// CTAs that each stream 48 k-blocks (18 us); here ~100 CTAs take 2 k-blocks each, and the sum lands directly in the fp32
+// buffer that already holds the other gradient term of the same state (no bf16 rounding of the carried gradient).
+bool tc_bwd_input_accum_supported(int64_t M, int N, int K, int dtype) {
+  return tc_enabled() && dtype == MURCL_BF16 && M >= 64 && K >= 128 && K % 8 == 0 && N >= 64 && N % 8 == 0;
+}
+
+int tc_linear_bwd_input_accum(const void* dy, const void* w, float* dx, int64_t M, int N, int K, cudaStream_t st) {
+  if (!aligned16(dy) || !aligned16(w) || !aligned16(dx)) {
+    set_error("linear_bwd_input_accum(tcgen05): operands must be 16-byte aligned");
+    return MURCL_EINVAL;
+  }
+  const int BN = (K % 256 == 0) ? 256 : 128;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dy, M, N, BLOCK_K, BLOCK_M);
+  if (rc != MURCL_OK) return rc;
+  rc = make_map(&mb, w, N, K, 64, BLOCK_K);                       // MN-major B: rows = reduction index n
+  if (rc != MURCL_OK) return rc;
+  Params p{};
+  p.M = M; p.N = K; p.K = N; p.ldc = K; p.C = dx; p.split_stride = 0; p.atomic_out = 1;
+  p.m_tiles = ceil_div(M, BLOCK_M); p.n_tiles = ceil_div(K, BN);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int64_t kb_total = ((int64_t)N + BLOCK_K - 1) / BLOCK_K;
+  int splits = sm_count() / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = (int)kb_total;
+  const int64_t kb_per = (kb_total + splits - 1) / splits;
+  p.k_chunk = kb_per * BLOCK_K;
+  p.splits = (int)((kb_total + kb_per - 1) / kb_per);
+  return BN == 256 ? launch<256, false, true, EPI_SPLIT, float>(ma, mb, ma, p, st)
+                   : launch<128, false, true, EPI_SPLIT, float>(ma, mb, ma, p, st);
+}
+
 // The weight gradient is operand-load bound with one CTA per 128 x 256 tile (48 KB of operands per 512 tensor-pipe clocks):
 // a CTA pair on a 256 x 256 tile pulls 32 KB per CTA for the same MMA work and fits a deeper ring.
 static bool wgrad_pair(int64_t M, int N, int K) {

@@ -21,6 +21,9 @@ int tc_linear_bwd_input(const void*, const void*, void*, int64_t, int, int, cons
 int64_t tc_linear_bwd_weight_workspace(int64_t, int, int);
 int tc_linear_bwd_weight(const void*, const void*, float*, int64_t, int, int, float*, cudaStream_t, int accumulate);
 
+bool tc_bwd_input_accum_supported(int64_t M, int N, int K, int dtype);
+int tc_linear_bwd_input_accum(const void*, const void*, float*, int64_t, int, int, cudaStream_t);
+
 int colsum_impl(const void* a, int64_t M, int N, int dtype, float* out, cudaStream_t st, int accumulate = 0);
 bool tc_split_supported(int64_t M, int N, int K);
 int tc_split_fwd(const void*, const void*, const float*, float*, int64_t, int, int, int, int, int64_t, int64_t, cudaStream_t);
@@ -159,6 +162,22 @@ int murcl_linear_bwd_weight_split(const void* dyp, const void* xp, float* dw, in
                 "linear_bwd_weight_split: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
   MURCL_REQUIRE(plane_rows >= M && plane_rows % 64 == 0, "linear_bwd_weight_split: plane pitch must be >= M and a multiple of 64");
   return tc_split_bwd_weight(dyp, xp, dw, M, N, K, planes, plane_rows, workspace, as_stream(stream), accumulate);
+}
+
+int murcl_linear_bwd_input_accum_supported(int64_t M, int N, int K, int dtype) {
+  return tc_bwd_input_accum_supported(M, N, K, dtype) ? 1 : 0;
+}
+
+int murcl_linear_bwd_input_accum(const void* dy, const void* w, float* dx, int64_t M, int N, int K, int dtype, void* stream) {
+  MURCL_REQUIRE(dy && w && dx, "linear_bwd_input_accum: null pointer");
+  MURCL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd_input_accum: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  if (M == 0) return MURCL_OK;
+  if (!tc_bwd_input_accum_supported(M, N, K, dtype)) {
+    set_error("linear_bwd_input_accum: needs bf16 operands, M >= 64, N >= 64, K >= 128 (N, K %% 8 == 0); got M=%lld N=%d K=%d dtype=%d",
+              (long long)M, N, K, dtype);
+    return MURCL_EUNSUPPORTED;
+  }
+  return tc_linear_bwd_input_accum(dy, w, dx, M, N, K, as_stream(stream));
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@ summation order over the calls differs.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List, Sequence
 
 import torch
@@ -157,18 +158,22 @@ class HeadTape:
         carry_f = [torch.empty((B, H), device=dev, dtype=torch.float32) for _ in range(2)]
         carry_s = None
         have_carry = False
+        accum = os.environ.get("MURCL_TAPE_ACCUM_DGRAD", "1") != "0"
         flip = 0
         for c in range(n - 1, -1, -1):
             first = self.restart[c]
             out_f = None if first else carry_f[flip ^ 1]
-            check(lib.murcl_gru_cell_bwd_tape(_p(dHd[c]), _p(carry_s) if have_carry else None,
+            check(lib.murcl_gru_cell_bwd_tape(_p(dHd[c]), _p(carry_s) if (have_carry and carry_s is not None) else None,
                                               _p(carry_f[flip]) if have_carry else None, _p(self.GATES[c]), _p(self.GH[c]),
                                               None if first else _p(self.Hf[c - 1]), _p(DGI[c]), _p(DGH[c]), _p(out_f), B, H,
                                               self.code, _s()), "murcl_gru_cell_bwd_tape")
             if first:
                 have_carry = False
             else:
-                carry_s = ops.linear_bwd_input(DGH[c], self.w_hh_s)                     # [B, H]: through gh = h_prev W_hh^T
+                # through gh = h_prev W_hh^T: added straight into the fp32 buffer that holds the cell's direct term (split-K
+                # with atomics over the whole GPU) where the kernel takes the shape, else a storage-type tensor of its own
+                carry_s = None if (accum and ops.linear_bwd_input_accum_(DGH[c], self.w_hh_s, out_f)) else \
+                    ops.linear_bwd_input(DGH[c], self.w_hh_s)
                 flip ^= 1
                 have_carry = True
         # weight gradients of the recurrence over all calls (h_prev rows of restarting calls are zeros: exact)

@@ -278,6 +278,25 @@ def linear_bwd_input(dy, w, relu_src=None, row_scale=None, row_vec=None, row_seg
     return dx
 
 
+def linear_bwd_input_accum_(dy, w, dx_f32) -> bool:
+    """``dx_f32 += dy @ w`` (fp32 buffer, split-K with atomics: murcl_linear_bwd_input_accum).  Returns False - and does
+    nothing - when the shape / storage type is not taken (fp32 operands, tiny layers): the caller then uses
+    ``linear_bwd_input`` and adds."""
+    if dy.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or _backend() == GEMM_SIMT:
+        return False
+    M, N = dy.shape
+    K = w.shape[1]
+    lib = _lib.load()
+    if not lib.murcl_linear_bwd_input_accum_supported(int(M), int(N), int(K), _DT[dy.dtype]):
+        return False
+    _chk(dy, "linear_bwd_input_accum.dy"); _chk(w, "linear_bwd_input_accum.w"); _chk(dx_f32, "linear_bwd_input_accum.dx", torch.float32)
+    if w.shape[0] != N or tuple(dx_f32.shape) != (M, K):
+        raise MurclError(f"linear_bwd_input_accum: shape mismatch dy{tuple(dy.shape)} w{tuple(w.shape)} dx{tuple(dx_f32.shape)}")
+    with _Timed("head_bwd_input", 2.0 * M * N * K):
+        check(lib.murcl_linear_bwd_input_accum(_p(dy), _p(w), _p(dx_f32), M, N, K, _DT[dy.dtype], _s()), "murcl_linear_bwd_input_accum")
+    return True
+
+
 def linear_bwd_weight(dy, x, want_bias=True, dw_into=None, db_into=None):
     """(dw [N, K], db [N] | None) fp32.  ``dw_into`` / ``db_into`` (fp32, contiguous, e.g. the ``.grad`` views of a
     ``ParamArena``) make the kernels ADD their result to those buffers (no separate accumulation launch); the returned

@@ -96,6 +96,23 @@ def test_tc_input_grad(M, N, K):
     assert_close(cs, dx3.double().sum(0).float(), 2e-5, "fused column sums")
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 3072, 1024), (256, 3072, 512), (131, 384, 1024), (64, 64, 128), (1000, 200, 136)])
+def test_tc_input_grad_accumulate(M, N, K):
+    """dx (fp32) += dy[M,N] w[N,K] with the reduction split over the GPU (vector atomics): the W_hh step of the GRU head's
+    backward recurrence.  Against fp64 on the bf16 operands; twice in a row accumulates twice."""
+    from murcl_b200 import ops
+    _x, w, _, dy = _mk(M, N, K, 3 * M + N + K)
+    base = torch.randn(M, K, generator=synth.gen(M + 1))
+    out = base.to(DEV).contiguous()
+    assert ops.linear_bwd_input_accum_(dy.to(DEV), w.to(DEV), out)
+    ref = dy.double() @ w.double()
+    assert_close(out, (base.double() + ref).float(), 5e-6, "accumulated once")
+    assert ops.linear_bwd_input_accum_(dy.to(DEV), w.to(DEV), out)
+    assert_close(out, (base.double() + 2 * ref).float(), 5e-6, "accumulated twice")
+    # fp32 operands are not taken: the caller falls back to linear_bwd_input
+    assert not ops.linear_bwd_input_accum_(dy.float().to(DEV), w.float().to(DEV), out)
+
+
 @pytest.mark.parametrize("M,N,K", SHAPES + [(131072, 512, 512), (20000, 128, 512)])
 def test_tc_weight_grad(M, N, K):
     """dw[N,K] = dy^T x over M rows: both operands MN-major, split-K across the SMs."""
