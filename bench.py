@@ -6,8 +6,12 @@
 Workload (BASELINE config 3, SURVEY.md 8d "cfg3"): one optimiser step of stage-3 pre-training per "step":
 B=128 slides per GPU (ragged, N_i ~ U[500,15500] x 512-d, K=10 clusters), T=6 patch-steps x 2 views,
 RL actor chooses the windows, select+gather+mixup -> ABMIL(512,512,128) -> Full_layer(512,1024,128) ->
-NT-Xent over the global batch, backward, Adam.  Weak scaling: every rank owns 128 slides; embeddings are
-all-gathered (NCCL) for the loss and gradients all-reduced once per step.
+NT-Xent over the global batch, backward, Adam (optim.ArenaAdam: torch.optim.Adam's update as one launch over the flat
+parameter arena).  The whole step - head / loss chain on its side stream included - replays as one CUDA graph; the step's
+random draws are issued up front (`--rng batched`; `--rng reference` keeps the reference's per-patch-step call order).
+Weak scaling: every rank owns 128 slides; embeddings are all-gathered (NCCL) for the loss (from 4 ranks on each rank
+reduces only its own rows of the global score matrix and the per-row statistics are all-gathered too) and gradients are
+all-reduced once per step.  `roofline.yardstick` times the dominant GEMM shape alone next to cuBLAS on the same shape.
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with the slides already in HBM;
 `e2e` = the same step driven from the PINNED HOST staging of a finite dataset shard (`--dataset-slides` per rank) through
