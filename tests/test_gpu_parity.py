@@ -1065,6 +1065,66 @@ def test_pretrain_step_golden_with_param_arena(golden, precision):
         assert torch.equal(enc.encoder[0].weight._murcl_shadow, enc.encoder[0].weight.detach().bfloat16())
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_step_side_stream_and_graph_replay_match_the_plain_step(golden, precision):
+    """The scheduling of the step must not change its numbers: (a) projection head / loss chain and the tape's weight-gradient
+    GEMMs on the side stream vs everything on one stream; (b) the whole optimiser step (zero_grad, forward, backward, fused
+    Adam) captured by ``GraphedStep`` - fork / join edges included - and replayed vs launched eagerly.  Differences allowed:
+    the summation order of the atomically accumulated gradients."""
+    from murcl_b200 import pretrain
+    from murcl_b200.arena import ParamArena
+    from murcl_b200.csr import BagStore
+    from murcl_b200.dropin import abmil, cl, losses, rlmil
+    from murcl_b200.optim import ArenaAdam
+    g = golden("pretrain_step")
+    b, k, d, fs, T, L, D, hid, proj = g["cfg"].tolist()
+    feats, clusters, _ = synth.make_bags(g["sizes"].tolist(), d, k, seed=91)
+    store = BagStore.from_cluster_lists(feats, clusters, DEV)
+    crit = losses.NT_Xent(b, float(g["tau"]))
+    draws = [([a.to(DEV) for a in acts], [l.to(DEV) for l in lams], [p.to(DEV) for p in perms])
+             for acts, lams, perms in _mini_step_draws(g["cfg"].tolist(), 94)]
+
+    def build():
+        enc = _load(abmil.ABMIL(d, L=L, D=D, dim_out=proj, precision=precision), synth.abmil_state(d, L, D, proj, seed=92))
+        model = cl.CL(enc, projection_dim=proj, n_features=L)
+        fc = _load(rlmil.Full_layer(L, hid, True, proj), synth.full_layer_state(L, hid, proj, seed=93))
+        fc.precision = precision
+        arena = ParamArena(list(enc.parameters()) + list(fc.parameters()), shadow_dtype=torch.bfloat16 if precision == "bf16" else None)
+        return model, fc, arena, ArenaAdam(arena, lr=1e-3, weight_decay=1e-5)
+
+    def step(model, fc, arena, opt, overlap):
+        arena.zero_grad()
+        loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=float(g["alpha"]), draws=draws,
+                                         precision=precision, overlap_heads=overlap)
+        opt.step()
+        return loss
+
+    # strict part - ONE step from identical weights: only the summation order of the atomically accumulated gradients differs
+    tol = 5e-6 if precision == "fp32" else 5e-3
+    first = {}
+    for name, overlap in (("one_stream", False), ("side_stream", True)):
+        model, fc, arena, opt = build()
+        arena.zero_grad()
+        loss, _ = pretrain.pretrain_step(store, model, fc, crit, T=T, feat_size=fs, alpha=float(g["alpha"]), draws=draws,
+                                         precision=precision, overlap_heads=overlap)
+        first[name] = (loss.clone(), arena.grad.clone())
+    assert_close(first["one_stream"][0], g["loss"], FP32_OUT if precision == "fp32" else BF16_OUT, "loss vs the reference fixture")
+    assert_close(first["side_stream"][0], first["one_stream"][0], tol, "loss: side stream vs one stream")
+    assert_close(first["side_stream"][1], first["one_stream"][1], 4 * tol, "gradients: side stream vs one stream", floor=1e-7)
+    # loose part - three optimiser steps, eagerly and as a replayed graph: Adam (update = m / sqrt(v)) amplifies the summation
+    # noise of near-cancelling gradient entries, so the trajectories are compared at the precision mode's own tolerance
+    loose = FP32_GRAD if precision == "fp32" else BF16_OUT
+    model, fc, arena, opt = build()
+    eager = torch.stack([step(model, fc, arena, opt, True).clone() for _ in range(3)])
+    model, fc, arena, opt = build()
+    graphed = pretrain.GraphedStep(lambda: step(model, fc, arena, opt, True), warmup=1)      # the warm-up step is step 1
+    replayed = torch.stack([graphed().clone() for _ in range(2)])
+    torch.cuda.synchronize()
+    assert opt.steps == 3                                          # device-side step counter: warm-up + two replays
+    assert float(eager[2]) != float(eager[0])                      # the optimiser moved the weights: the later losses differ
+    assert_close(replayed, eager[1:], loose, "losses of steps 2, 3: graph replay vs eager")
+
+
 @pytest.mark.parametrize("B,d,b0,nb", [(128, 128, 0, 128), (128, 128, 32, 16), (1024, 128, 896, 128), (24, 32, 5, 7), (8, 256, 0, 3)])
 def test_ntxent_gradient_slab(B, d, b0, nb):
     """murcl_ntxent_fwd_bwd_slab: the loss covers the whole batch, the gradient only the samples [b0, b0+nb) of both views
