@@ -327,6 +327,36 @@ def roofline_probe(job, store, slot_bag, peaks):
             "timing": "CUDA events around every launch of one extra eager step on the launch stream"}
 
 
+def step_roofline(a, ms_per_step, peaks):
+    """Roofline of the WHOLE step from its algorithmic work: per kernel of a patch-step the
+    compulsory HBM bytes (bf16 storage) and FLOPs, roof = sum over kernels of max(bytes / HBM peak, FLOPs / tensor peak).
+    The batch-sized head layers, NT-Xent and the optimiser (< 3 % of the bytes, < 1 % of the FLOPs) are left out of the roof,
+    which makes `frac` conservative."""
+    s = 2 if a.precision == "bf16" else 4
+    rows = 2.0 * a.bags * a.feat_size
+    D, L, DA = float(a.dim), 512.0, 128.0
+    hbm = (peaks.get("hbm_gbs") or 6500.0) * 1e9
+    tc = (peaks.get("bf16_tflops_sustained") or 1400.0) * 1e12
+    k = []                                                    # (name, bytes, flops) of one patch-step, both views
+    k.append(("pack_gather", rows * (3 * D * s + 4), 0.0))
+    for kin in (D, L, L):                                     # encoder forward: x -> h1 -> h2 -> h3 (+ 1 mask bit per output)
+        k.append(("enc_fwd", rows * (kin * s + L * s + L / 8), 2 * rows * kin * L))
+    k.append(("attnpool_fwd", rows * (L * s + DA * s + 8), 2 * rows * L * DA + 2 * rows * L))
+    k.append(("attnpool_bwd", rows * (L * s + 2 * DA * s + 4), 2 * rows * L))
+    k.append(("attn_wgrad", rows * (DA * s + L * s), 2 * rows * DA * L))
+    k.append(("attn_dgrad", rows * (DA * s + L * s + L / 8), 2 * rows * DA * L))
+    for kin in (L, L, D):                                     # encoder weight gradients (dZ and the layer's input)
+        k.append(("enc_wgrad", rows * (L * s + kin * s), 2 * rows * L * kin))
+    for _ in range(2):                                        # encoder input gradients (none for the first layer)
+        k.append(("enc_dgrad", rows * (2 * L * s + L / 8), 2 * rows * L * L))
+    roof = a.T * sum(max(b / hbm, f / tc) for _, b, f in k)
+    tot_b, tot_f = a.T * sum(b for _, b, _ in k), a.T * sum(f for _, _, f in k)
+    return {"roof_ms": round(roof * 1e3, 3), "frac": round(roof * 1e3 / ms_per_step, 4), "hbm_bytes": tot_b, "flop": tot_f,
+            "hbm_only_ms": round(tot_b / hbm * 1e3, 3), "tensor_only_ms": round(tot_f / tc * 1e3, 3),
+            "def": "sum over the step's instance-level kernels of max(algorithmic bytes / measured HBM peak, algorithmic FLOP / "
+                   "measured sustained bf16 peak) / measured ms_per_step"}
+
+
 def gemm_yardstick(rows, n=512, k=512, reps=20):
     """The dominant GEMM shape timed ALONE (burst clocks, back-to-back launches, inputs larger than L2): this repo's fused
     forward kernel (bias + ReLU + bit mask) beside cuBLAS through torch.matmul (no epilogue).  Context for `roofline.frac`:
@@ -644,6 +674,8 @@ def main():
             roof["yardstick"] = gemm_yardstick(2 * a.bags * a.feat_size)
         except Exception as e:                               # noqa: BLE001 - context only, never fatal
             roof["yardstick"] = {"error": f"{type(e).__name__}: {e}"}
+    if roof is not None:
+        roof["step"] = step_roofline(a, ms / a.steps, peaks)
     vlog("roofline probe done")
 
     secondary = {}
