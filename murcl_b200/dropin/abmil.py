@@ -52,6 +52,17 @@ class ABMIL(nn.Module):
             meta.update(shard=True, shard_group=self.shard_group)
         return meta
 
+    def pooled(self, x):
+        """Encoder + attention pooling WITHOUT the decoder: ``[B, L]`` bag vectors (abmil.py:36-43).  For callers that run
+        the decoder layer themselves (the recurrent-head tape batches its backward over the T patch-steps of a step)."""
+        rows = to_rows(x)
+        enc = [p for i in (0, 3, 6) for p in (self.encoder[i].weight, self.encoder[i].bias)]
+        M, p, _s, _il, _pr = ops.mil_aggregate(rows.rows, rows.offsets, rows.row_seg, self._meta(rows),
+                                               self.attention[0].weight, self.attention[0].bias,
+                                               self.attention[2].weight, self.attention[2].bias, None, None, enc)
+        self.last_attention = p
+        return M
+
     def _aggregate(self, x):
         rows = to_rows(x)
         enc = [p for i in (0, 3, 6) for p in (self.encoder[i].weight, self.encoder[i].bias)]

@@ -64,6 +64,51 @@ class HeadTape:
         self.params = (w_ih, w_hh, self.b_ih, self.b_hh, fc.fc.weight, fc.fc.bias)
         self.w_ih_s, self.w_hh_s, self.w_fc_s = (ops.weight_as(w, self.dt) for w in (w_ih, w_hh, fc.fc.weight))
         self.bias = [b.detach().contiguous().float() for b in (self.b_ih, self.b_hh, fc.fc.bias)]
+        self.dec = None                                      # (weight, bias, w_storage, bias_f32) once attach_decoder() ran
+        self.m_inputs: List[torch.Tensor] = []               # decoder inputs (pooled bag vectors), one per call
+
+    # ---------------------------------------------------------------------------------------------------
+    def attach_decoder(self, weight: torch.nn.Parameter, bias: torch.nn.Parameter) -> None:
+        """Also tape the aggregator's ``decoder`` layer (``Linear + ReLU`` on the pooled bag vectors, abmil.py:31,44): the
+        actor needs its OUTPUT at every patch-step, so the forward stays per call (``decode``); its backward - ReLU mask,
+        input gradient, weight gradient, bias column sums - runs ONCE over all calls (M = calls x n_views x B rows) instead
+        of once per patch-step at the head of every aggregator's backward."""
+        if self.step != 0:
+            raise ops.MurclError("HeadTape.attach_decoder: attach before the first call")
+        if weight.shape[0] != self.F:
+            raise ops.MurclError(f"HeadTape.attach_decoder: the decoder produces {weight.shape[0]} features, Full_layer takes {self.F}")
+        dev = self.Xs.device
+        rows = self.nv * self.B
+        self.dec = (weight, bias, ops.weight_as(weight, self.dt), None if bias is None else bias.detach().contiguous().float())
+        self.Ms = torch.empty((self.n_calls, rows, weight.shape[1]), device=dev, dtype=self.dt)       # decoder inputs, storage type
+        self.DEC = torch.empty((self.n_calls, rows, self.F), device=dev, dtype=torch.float32)         # decoder outputs (post-ReLU)
+
+    @torch.no_grad()
+    def decode(self, M: torch.Tensor) -> torch.Tensor:
+        """``relu(M W_dec^T + b_dec)`` of the CURRENT call (call it before ``forward_views``); ``M`` ``[n_views * B, L]`` is
+        recorded as the call's differentiable input.  Returns the ``[n_views * B, F]`` fp32 output (no graph attached): hand
+        it to ``forward_views(..., stacked=...)`` and, detached, to the actor."""
+        if self.dec is None:
+            raise ops.MurclError("HeadTape.decode: attach_decoder() first")
+        if self.step >= self.n_calls or len(self.m_inputs) != self.step:
+            raise ops.MurclError("HeadTape.decode: one decode() per call, before forward_views()")
+        t = self.step
+        src = M.detach().contiguous()
+        if tuple(src.shape) != tuple(self.Ms[t].shape):
+            raise ops.MurclError(f"HeadTape.decode: expected {tuple(self.Ms[t].shape)}, got {tuple(src.shape)}")
+        if src.dtype == self.dt:
+            self.Ms[t].copy_(src)
+        else:
+            ops.cast_into(src.float() if src.dtype != torch.float32 else src, self.Ms[t])
+        ops.linear_fwd(self.Ms[t], self.dec[2], self.dec[3], ops.ACT_RELU, out=self.DEC[t])
+        self.m_inputs.append(M)
+        return self.DEC[t]
+
+    @property
+    def grad_roots(self) -> List[torch.Tensor]:
+        """The tensors ``backward`` returns gradients for, in order: the decoder inputs when a decoder is taped, else the
+        recorded ``forward_views`` inputs."""
+        return self.m_inputs if self.dec is not None else self.x_inputs
 
     # ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -189,6 +234,8 @@ class HeadTape:
             if own[name]:
                 prm.grad = grads[name] if prm.grad is None else prm.grad + grads[name]
         dX = dX.view(n, B, F)
+        if self.dec is not None:
+            return self._decoder_backward(dX, side, main)
         out = []
         for call, stacked in enumerate(self.stacked_inputs):     # same order as x_inputs
             if stacked:
@@ -196,3 +243,30 @@ class HeadTape:
             else:
                 out.extend(dX[call * nv + v] for v in range(nv))
         return out
+
+    def _decoder_backward(self, dX: torch.Tensor, side, main) -> List[torch.Tensor]:
+        """Backward of the taped decoder over ALL calls at once: ``dX`` ``[calls * n_views, B, F]`` (gradient w.r.t. the
+        decoder outputs) -> one gradient per recorded decoder input."""
+        if len(self.m_inputs) != self.step or not all(self.stacked_inputs):
+            raise ops.MurclError("HeadTape: with a taped decoder every call is decode() + forward_views(stacked=its result)")
+        weight, bias, w_s, _ = self.dec
+        calls, rows = self.step, self.nv * self.B
+        dpre = ops.relu_bwd(dX.reshape(calls * rows, self.F).contiguous(), self.DEC[:calls].view(calls * rows, self.F))
+        dpre_s = dpre if self.dt == torch.float32 else ops.cast(dpre, self.dt)
+        dM = ops.linear_bwd_input(dpre_s, w_s)
+        dM = dM.float() if dM.dtype != torch.float32 else dM
+        gw, own_w = self._grad_into(weight, weight.shape)
+        gb, own_b = (None, False) if bias is None else self._grad_into(bias, bias.shape)
+        if own_w or own_b:
+            side = None
+        if side is not None:
+            side.wait_stream(main)
+            self._keep_dec = (dpre_s,)                      # read on the side stream: must outlive this call
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            ops.linear_bwd_weight(dpre_s, self.Ms[:calls].view(calls * rows, -1), bias is not None, dw_into=gw, db_into=gb)
+        if own_w:
+            weight.grad = gw if weight.grad is None else weight.grad + gw
+        if own_b:
+            bias.grad = gb if bias.grad is None else bias.grad + gb
+        dM = dM.view(calls, rows, -1)
+        return [dM[t] for t in range(calls)]

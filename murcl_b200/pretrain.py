@@ -61,11 +61,29 @@ def pack_views(store: BagStore, draw: Draw, feat_size: int, out_dtype: torch.dty
     return store.pack(act, feat_size, lam, perm, out_dtype, slot_bag)
 
 
-def _encode_stacked(model, x_all: torch.Tensor, n_views: int = 2):
+def _tape_decoder(model, tape):
+    """The aggregator whose ``decoder`` layer the tape can take over (ABMIL behind the CL wrapper, same precision, bags not
+    row-sharded), or None."""
+    from .dropin.abmil import ABMIL
+    from .dropin.cl import CL
+    enc = getattr(model, "encoder", None) if isinstance(model, CL) else None
+    if tape is None or not isinstance(enc, ABMIL) or enc.shard_rows or os.environ.get("MURCL_TAPE_DECODER", "1") == "0":
+        return None
+    if ops.storage_dtype(enc.precision or ops.default_precision()) != tape.dt or enc.decoder[0].out_features != tape.F:
+        return None
+    return enc
+
+
+def _encode_stacked(model, x_all: torch.Tensor, n_views: int = 2, tape=None):
     """``encode_views`` that also hands back the un-split ``[n_views * B, F]`` encoder output (None when the model is not
-    the CL wrapper): the recurrent-head tape takes it as one input."""
+    the CL wrapper): the recurrent-head tape takes it as one input.  With a tape that has taken over the aggregator's decoder
+    layer (``HeadTape.attach_decoder``) the pooled vectors go through ``tape.decode``."""
     from .dropin.cl import CL
     B = x_all.shape[0] // n_views
+    if tape is not None and tape.dec is not None:
+        out = tape.decode(model.encoder.pooled(x_all))
+        outs = [out[v * B:(v + 1) * B] for v in range(n_views)]
+        return out, outs, outs
     if isinstance(model, CL):
         out = model.encoder(x_all)[0]
         outs = [out[v * B:(v + 1) * B] for v in range(n_views)]
@@ -135,6 +153,9 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         # Full_layer over the T x 2 calls of this step on the recurrent-head tape: batched backward (headtape.py)
         from .headtape import HeadTape
         tape = HeadTape(fc, T, 2, B, dev, getattr(fc, "precision", None) or precision or ops.default_precision())
+        dec_owner = _tape_decoder(model, tape)
+        if dec_owner is not None:        # the aggregator's decoder layer joins the tape: one batched backward for all T calls
+            tape.attach_decoder(dec_owner.decoder[0].weight, dec_owner.decoder[0].bias)
     if overlap_heads is None:
         overlap_heads = tape is not None and os.environ.get("MURCL_OVERLAP_HEADS", "1") != "0"
     side = head_stream(dev) if (overlap_heads and torch.device(dev).type == "cuda") else None
@@ -162,7 +183,7 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
                         actions = [torch.rand((B, K), device=dev) for _ in range(2)]
                     draw = (actions, lams, perms)
                 x_all = pack_views(store, draw, feat_size, dt, slot_bag)
-            out_all, outputs, states = _encode_stacked(model, x_all)
+            out_all, outputs, states = _encode_stacked(model, x_all, tape=tape)
             if side is not None:
                 side.wait_stream(torch.cuda.current_stream())           # fork: the bag embeddings are complete
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
@@ -197,7 +218,7 @@ def pretrain_step(store: BagStore, model, fc, criterion, *, T: int = 6, feat_siz
         d_outs = tape.backward(dzs, side=wgrad_side)
         if after_head_backward is not None:
             after_head_backward()
-        torch.autograd.backward(tape.x_inputs, d_outs)
+        torch.autograd.backward(tape.grad_roots, d_outs)
         if wgrad_side is not None:
             torch.cuda.current_stream().wait_stream(wgrad_side)
     elif backward:
