@@ -105,31 +105,51 @@ def make_host_batch(a, seed, pin=True, n_slides=None, precision=None):
 # clocks sampler (B200_PROFILING.md "clocks line")
 # ------------------------------------------------------------------------------------------------------
 class Clocks:
+    """nvidia-smi sampler (25 ms period).  The process takes a few hundred ms to deliver its first line - longer than a short
+    timed region - so it is started BEFORE the warm-up steps (`start` waits for the first sample) and only the samples that
+    arrive between `mark_begin()` and `stop()` are reported; if the region was shorter than a sampling period the nearest
+    samples around it are used and `samples_in_region` says so."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.lines, self.proc, self.index = [], None, index
+        self.t_begin = None
 
-    def start(self):
+    def start(self, wait_s=5.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < wait_s:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
+        time.sleep(0.06)                                    # let the sample that was in flight at t_end arrive
         self.proc.terminate()
+        t_begin = self.t_begin if self.t_begin is not None else 0.0
+        inside = [l for t, l in self.lines if t_begin <= t <= t_end + 0.05]
+        used = inside
+        if not used:                                        # region shorter than a sampling period: the samples around it
+            before = [l for t, l in self.lines if t < t_begin][-1:]
+            after = [l for t, l in self.lines if t > t_end][:1]
+            used = before + after
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in used:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
                 continue
@@ -142,7 +162,7 @@ class Clocks:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_region": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -602,13 +622,15 @@ def main():
         slot_bag.copy_(table[i % table.shape[0]])          # device-to-device: this step's slide ids
         job.run(store, slot_bag)
 
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()                                      # before the warm-up: the sampler needs a moment to come up
     for i in range(a.warmup):
         resident_step(i)
     torch.cuda.synchronize()
     vlog("warm-up done")
-    clocks = Clocks(local)
     if rank == 0:
-        clocks.start()
+        clocks.mark_begin()
     l0 = _lib.launch_count()
     ms = timed(lambda i: resident_step(a.warmup + i), a.steps, world, device)
     launches = job.launches_per_step * a.steps if graphed else _lib.launch_count() - l0
