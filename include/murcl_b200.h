@@ -55,6 +55,12 @@ const char* murcl_last_error(void);
 int murcl_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernel launches issued by this library on the calling process so far. */
 int64_t murcl_launch_count(void);
+/* Scheduling hint, per calling thread, sticky until changed; returns the previous value.  descending != 0: the following
+ * murcl_linear_fwd / murcl_linear_bwd_input (tcgen05 path) and murcl_attnpool_fwd launches walk their row tiles from the
+ * LAST rows to the first.  Results do not change.  A chain of layers over an activation larger than L2 alternates the
+ * direction so that every consumer starts with the rows its producer wrote last - the ones still in L2 - instead of the
+ * ones written first, which have been evicted by then. */
+int murcl_set_row_order(int descending);
 
 /* ---- (1) ragged-bag packer: utils/datasets.py:274-308 (get_feats), :263-271 (mixup) ---- */
 

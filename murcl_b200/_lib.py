@@ -27,6 +27,7 @@ SIGNATURES = {
     "murcl_last_error": (C.c_char_p, []),
     "murcl_device_info": (_i, [C.POINTER(_i)] * 3),
     "murcl_launch_count": (_l, []),
+    "murcl_set_row_order": (_i, [_i]),
     "murcl_csr_rank_patches": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "murcl_pack_select": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "murcl_pack_gather": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _p]),

@@ -6,6 +6,7 @@
 namespace murcl {
 
 static thread_local std::string t_last_error;
+static thread_local int t_row_order = 0;
 std::atomic<int64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -16,6 +17,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
   t_last_error = buf;
 }
+
+int row_order_descending() { return t_row_order; }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -38,6 +41,12 @@ int murcl_version(void) { return MURCL_ABI_VERSION; }
 const char* murcl_last_error(void) { return murcl::t_last_error.c_str(); }
 
 int64_t murcl_launch_count(void) { return murcl::g_launches.load(); }
+
+int murcl_set_row_order(int descending) {
+  const int prev = murcl::t_row_order;
+  murcl::t_row_order = descending ? 1 : 0;
+  return prev;
+}
 
 int murcl_device_info(int* sms, int* cc_major, int* cc_minor) {
   int dev = 0;

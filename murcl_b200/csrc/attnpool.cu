@@ -86,6 +86,7 @@ struct Params {
   __nv_bfloat16* uv;      // may be null (inference: nothing is kept for a backward pass)
   float* s;
   float* rec;
+  int reverse;                 // walk the tiles from the last rows to the first (murcl_set_row_order)
   int skip;                    // MURCL_DEBUG_ATTNPOOL_SKIP bit mask (timing experiments; results are wrong when set)
   unsigned long long* trace;   // MURCL_DEBUG_ATTNPOOL=1: %globaltimer stamps of CTA 0 / warp 0, 8 per tile
 };
@@ -171,7 +172,8 @@ attnpool_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         mbar_expect_tx(bres_bar, (uint32_t)(nkb * SLAB_BYTES));
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(bres + kb * SLAB_BYTES, &map_w, bres_bar, kb * BLOCK_K, 0);
       }
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
+        const int t = p.reverse ? p.n_tiles - 1 - ti : ti;
         const int row0 = t * TILE_M;
         for (int j = 0; j < n_pass; ++j) {
           for (int kb = 0; kb < nkb; ++kb) {
@@ -237,7 +239,8 @@ attnpool_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     const bool act0 = 8 * lane < L, act1 = 256 + 8 * lane < L;           // pooling: lane owns columns [8*lane, +8) and [256 + 8*lane, +8)
     uint32_t aph = 0;
     for (int it = team; blockIdx.x + (int64_t)it * gridDim.x < p.n_tiles; it += p.n_acc) {
-      const int t = blockIdx.x + it * gridDim.x;
+      const int ti = blockIdx.x + it * gridDim.x;
+      const int t = p.reverse ? p.n_tiles - 1 - ti : ti;
       const int64_t row0 = (int64_t)t * TILE_M;
       const int64_t row = row0 + r;
       const bool valid = row < p.n_rows;
@@ -538,6 +541,7 @@ int murcl_attnpool_fwd(const void* h, const void* wab, const float* bab, const f
     prm.h = static_cast<const __nv_bfloat16*>(h);
     prm.bab = bab; prm.wc = wc; prm.bc = bc; prm.offsets = offsets; prm.row_seg = row_seg;
     prm.uv = static_cast<__nv_bfloat16*>(uv); prm.s = s; prm.rec = workspace;
+    prm.reverse = row_order_descending();
     static int debug = -1;
     static unsigned long long* trace_buf = nullptr;
     if (debug < 0) {

@@ -45,6 +45,8 @@ inline int check_launch(const char* what) {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 int sm_count();
+// murcl_set_row_order: 1 = the row-tile walk of the next launches (dense layers, fused pooling) starts at the LAST rows
+int row_order_descending();
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: one flag per device ordinal, so that a
 // process driving several GPUs (nn.DataParallel-style) configures the kernel on each of them.

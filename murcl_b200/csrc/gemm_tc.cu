@@ -84,6 +84,7 @@ struct Params {
   // the tile `l2pf` tiles ahead into L2, streaming kernels the operand k-blocks `l2pf` k-blocks ahead.  The shared-memory
   // ring alone looks ahead ~1 us of MMA time (4 x 16 KB of A beside the resident B tile), less than the loaded HBM latency.
   int l2pf;
+  int reverse;        // walk the row tiles from the last to the first (murcl_set_row_order)
   int atomic_out;     // EPI_SPLIT: add the partial tile to C with vector atomics (red.global.add.v4.f32) instead of storing it
 };
 
@@ -189,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     nb = (int)(ut - r * nt);
     sp = (int)(r / mt);
     mb = (int)(r - (unsigned)sp * mt);
+    if (p.reverse) mb = p.m_tiles - 1 - mb;
   };
   auto k_range = [&](int sp, int64_t& k0, int& nkb) {
     k0 = (int64_t)sp * p.k_chunk;
@@ -772,6 +774,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     }
     pp.l2pf = BSTAT ? pf_tiles : pf_kb;
   }
+  pp.reverse = (EPI != EPI_SPLIT && row_order_descending()) ? 1 : 0;
   static unsigned long long* trace_buf = nullptr;
   if (debug & 8) {
     if (!trace_buf) cudaMalloc(&trace_buf, sizeof(unsigned long long) * 24 * 4096);

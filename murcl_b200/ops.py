@@ -96,6 +96,16 @@ class _Timed:
 # ------------------------------------------------------------------------------------------------
 # raw (non-differentiable) wrappers
 # ------------------------------------------------------------------------------------------------
+def set_row_order(descending: bool) -> bool:
+    """Scheduling hint for the next dense-layer / fused-pooling launches of this thread (murcl_set_row_order): walk the row
+    tiles from the last rows to the first.  Returns the previous setting.  Never changes results."""
+    return bool(_lib.load().murcl_set_row_order(1 if descending else 0))
+
+
+def _serpentine() -> bool:
+    return os.environ.get("MURCL_SERPENTINE", "1") != "0"
+
+
 def cast(src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     _chk(src, "cast.src")
     if src.dtype == dtype:
@@ -732,14 +742,22 @@ class _MILAggregate(torch.autograd.Function):
         seeds = None
         if drop is not None:
             seeds = torch.randint(0, 2 ** 62, (len(enc) // 2 + 1,), device=x.device, dtype=torch.int64)
+        # serpentine row order: an activation (268 MB at the pre-training shape) is larger than L2, so a consumer that starts
+        # at row 0 finds the rows its producer wrote FIRST - evicted by then.  Alternate layers walk the rows in opposite
+        # directions: every layer starts with the rows the previous one wrote last, which are still in L2.
+        serp = _serpentine()
         for i in range(0, len(enc), 2):
             w = weight_as(enc[i], dt)
             enc_w.append(w)
             dropped = drop is not None and drop["enc"][i // 2] > 0
-            if w.shape[0] % 64 == 0 and not dropped:
-                h, hb = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU, relu_bits=True)
-            else:
-                h, hb = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU), None
+            prev_order = set_row_order(serp and (i // 2) % 2 == 1)
+            try:
+                if w.shape[0] % 64 == 0 and not dropped:
+                    h, hb = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU, relu_bits=True)
+                else:
+                    h, hb = linear_fwd(hs[-1], w, enc[i + 1].detach().contiguous(), ACT_RELU), None
+            finally:
+                set_row_order(prev_order)
             if dropped:
                 dropout_(h, drop["enc"][i // 2], seeds[i // 2:i // 2 + 1])   # mask = zeros of h (inactive or dropped)
             hs.append(h)
@@ -751,8 +769,12 @@ class _MILAggregate(torch.autograd.Function):
         attn_drop = drop is not None and drop["attn"] > 0
         if not attn_drop and attnpool_supported(H.shape[1], D, gated, H.dtype):
             # one pass over H: projection (tcgen05) + gating + score + online softmax + weighted sum
-            uv, s, p, M, _ = attnpool_fwd(H, wab_s, bab.detach().contiguous().float(), wc_f, bc_f, offsets, row_seg, B, D,
-                                          gated, meta["inv_sqrt_n"] and not meta.get("shard"))
+            prev_order = set_row_order(serp and (len(enc) // 2) % 2 == 1)
+            try:
+                uv, s, p, M, _ = attnpool_fwd(H, wab_s, bab.detach().contiguous().float(), wc_f, bc_f, offsets, row_seg, B, D,
+                                              gated, meta["inv_sqrt_n"] and not meta.get("shard"))
+            finally:
+                set_row_order(prev_order)
             M = M.reshape(B, -1)
         else:
             uv = linear_fwd(H, wab_s, bab.detach().contiguous(), ACT_TANH_SIGMOID if gated else ACT_TANH)
@@ -877,25 +899,56 @@ class _MILAggregate(torch.autograd.Function):
             if n_enc > 0:
                 drows = drows * (rows > 0) * q_enc[n_enc - 1]           # same ReLU (+dropout) mask as the fused epilogue
             scatter_add_rows_(dz, idx, drows.contiguous())
-        grads_enc = []
-        for l in range(n_enc, 0, -1):
+        # The input-gradient CHAIN first, in serpentine row order (each launch starts with the rows the previous one wrote
+        # last: still in L2, the 268 MB gradient as a whole is not), then the weight gradients, the freshest gradient first.
+        # MURCL_SERPENTINE=0: one direction and the layer-by-layer order (weight gradient, then input gradient).
+        serp = _serpentine()
+        dzs = [None] * (n_enc + 1)
+        dzs[n_enc] = dz
+        dx_raw = None
+
+        def wgrad(l):
             if enc_in_place:
-                linear_bwd_weight(dz, hs[l - 1], want_bias=False, dw_into=g_enc[2 * (l - 1)])
-                dw = db = None
-            else:
-                dw, db = linear_bwd_weight(dz, hs[l - 1], want_bias=not fuse_db)
-                if fuse_db:
-                    db = db_next[l - 1]
-            grads_enc = [dw, db] + grads_enc
-            if l > 1:
-                dz = linear_bwd_input(dz, enc_w[l - 1], hs[l - 1] if hbits[l - 1] is None else None,
-                                      col_sum=db_next[l - 2] if fuse_db else None, out_scale=q_enc[l - 2],
-                                      relu_bits=hbits[l - 1])
-            elif ctx.needs_input_grad[0]:
-                dz = linear_bwd_input(dz, enc_w[0])
+                linear_bwd_weight(dzs[l], hs[l - 1], want_bias=False, dw_into=g_enc[2 * (l - 1)])
+                return None, None
+            dw, db = linear_bwd_weight(dzs[l], hs[l - 1], want_bias=not fuse_db)
+            return dw, (db_next[l - 1] if fuse_db else db)
+
+        def dgrad(l):
+            prev_order = set_row_order(serp and (n_enc - l) % 2 == 0)
+            try:
+                if l > 1:
+                    return linear_bwd_input(dzs[l], enc_w[l - 1], hs[l - 1] if hbits[l - 1] is None else None,
+                                            col_sum=db_next[l - 2] if fuse_db else None, out_scale=q_enc[l - 2],
+                                            relu_bits=hbits[l - 1])
+                return linear_bwd_input(dzs[1], enc_w[0]) if ctx.needs_input_grad[0] else None
+            finally:
+                set_row_order(prev_order)
+
+        gw = {}
+        if serp:
+            for l in range(n_enc, 0, -1):
+                nxt = dgrad(l)
+                if l > 1:
+                    dzs[l - 1] = nxt
+                else:
+                    dx_raw = nxt
+            for l in range(1, n_enc + 1):
+                gw[l] = wgrad(l)
+        else:
+            for l in range(n_enc, 0, -1):
+                gw[l] = wgrad(l)
+                nxt = dgrad(l)
+                if l > 1:
+                    dzs[l - 1] = nxt
+                else:
+                    dx_raw = nxt
+        grads_enc = []
+        for l in range(1, n_enc + 1):
+            grads_enc += list(gw[l])
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = dz.to(ctx.x_dtype)
+            dx = (dx_raw if n_enc > 0 else dz).to(ctx.x_dtype)
         return (dx, None, None, None, dwab, dbab, None if dwc is None else dwc.reshape(1, -1), dbc, d_inst_w, d_inst_b,
                 *grads_enc)
 
